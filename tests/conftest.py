@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+T2_CASES = [
+    "t2_seed42_P10_K5_u100",
+    "t2_seed7_P100_K5_u60_o5",
+    "t2_seed3_P1000_K20_u24_organic_count",
+    "t2_seed5_P60_K8_u40_bandit_count_flips",
+    "t2_seed9_P33_K3_u40_omega_bandits",
+]
+
+
+def oracle_env_from_golden(g):
+    from oracle import oracle as O
+    return O.OracleEnv(g["Gamma"], g["mu_organic"], g["beta"], g["mu_bandit"], g["state_transition"],
+                       float(g["sigma_omega_initial"]), float(g["sigma_omega"]), int(g["seed"]),
+                       bool(int(g["change_omega_for_bandits"])))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
