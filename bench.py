@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- simulated user-steps/sec of the reco-gym-v1 hot path on N B200s (driver contract).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU baseline on the box's host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[2], the one the metric "reco-env-v1, P=10k" is quoted on):
+num_products=10000, K=20, 1M users per GPU per step, organic_count agent (trained with the
+reference-compatible OrganicCount.train on logged users, compiled to a device table).
+A step = one fused rollout of `users_per_gpu` fresh users to the end of their episodes on every
+rank + the all-reduce of the CTR counters.  1 user-step = one Markov event of one user
+(SURVEY.md 8d).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (P, K, policy, users per GPU per step)
+    "c2": dict(P=100, K=5, policy="uniform", users=1_000_000,
+               label="reco-env-v1 P=100 K=5 1M users/GPU/step, default uniform logging policy (configs[1])"),
+    "c3": dict(P=10000, K=20, policy="organic_count", users=1_000_000,
+               label="reco-env-v1 P=10000 K=20 1M users/GPU/step, organic_count agent (configs[2])"),
+    "c4": dict(P=100000, K=64, policy="bandit_count", users=1_250_000,
+               label="reco-env-v1 P=100000 K=64 1.25M users/GPU/step (10M over 8 GPUs), bandit_count agent (configs[3])"),
+}
+SEED = 42
+# algorithmic HBM bytes per user-step of the step-synchronous protocol
+# (4K read omega + p_o*4K write + (1-f_org)*(4K+4) beta gather + 12 state/action/event bytes)
+ALG_BYTES_PER_STEP = {5: 55.0, 20: 175.0, 64: 520.0}
+F_ORG = 0.23  # fraction of events that are organic views
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def static_params(P, K):
+    import recogym_b200 as rg
+    from recogym_b200.envs.static_params import draw_static_params
+    cfg = rg.Configuration({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED})
+    return cfg, draw_static_params(cfg)
+
+
+def train_policy_table(kind, P, K, n_train):
+    """Trains the count agent exactly as test_agent does (bench_agents.py:176-190) on n_train logged
+    users through the RecoEnv1 facade (GPU), then compiles it to a last-view -> action table."""
+    import recogym_b200 as rg
+    if kind == "uniform":
+        return "uniform", None
+    env = rg.make("reco-gym-v1")
+    env.init_gym({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED})
+    if kind == "organic_count":
+        agent = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
+    else:
+        agent = _SparseBanditCount(P)
+    for uid in range(n_train):
+        env.reset(uid)
+        new_obs, _, done, reward = env.step(None)
+        while not done:
+            old_obs = new_obs
+            action, new_obs, reward, done, _ = env.step_offline(old_obs, reward, done)
+            agent.train(old_obs, action, reward, False)
+        old_obs = new_obs
+        action, _, reward, done, _ = env.step_offline(old_obs, reward, done)
+        agent.train(old_obs, action, reward, True)
+    return "table", agent.device_policy()["table"]
+
+
+class _SparseBanditCount:
+    """BanditCount (agents/bandit_count.py) with the P x P matrices held sparsely: dense is
+    3 x 80 GB at P=100k.  Same update rule, same argmax with the (0+1)/(0+2) prior."""
+
+    def __init__(self, P):
+        self.P, self.pulls, self.clicks, self.lpv = P, {}, {}, None
+
+    def train(self, observation, action, reward, done=False):
+        if action is not None and reward is not None:
+            ix, jx = self.lpv, int(action["a"])
+            if observation.sessions():
+                self.lpv = observation.sessions()[-1]["v"]
+            if ix is not None:
+                self.pulls[(ix, jx)] = self.pulls.get((ix, jx), 0) + 1
+                self.clicks[(ix, jx)] = self.clicks.get((ix, jx), 0) + reward
+
+    def device_policy(self):
+        table = np.zeros(self.P, np.int32)
+        best = {}
+        for (ix, jx), n in self.pulls.items():
+            ctr = (self.clicks[(ix, jx)] + 1) / (n + 2)
+            cur = best.get(ix)
+            if ctr > 0.5 and (cur is None or ctr > cur[0] or (ctr == cur[0] and jx < cur[1])):
+                best[ix] = (ctr, jx)
+        for ix, (_, jx) in best.items():
+            table[ix] = jx
+        return {"policy": "table", "table": table}
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's algorithm on the box's host cores.  The reference itself is
+    Python and does not travel to the GPU box, so this is the C oracle port (oracle/rg_oracle.c),
+    all host threads, each step a bounded sample of the same workload."""
+    from oracle import oracle as O
+    cfg, sp = static_params(wl["P"], wl["K"])
+    oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                     cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
+    cores = os.cpu_count() or 1
+    policy, table = ("uniform", None)
+    if wl["policy"] != "uniform":
+        policy, table = "table", np.random.RandomState(SEED).randint(0, wl["P"], wl["P"]).astype(np.int32)
+    # users per step sized for ~2-4 s per step on all cores
+    per_user_s = {100: 6e-5, 10000: 4.5e-3, 100000: 0.15}.get(wl["P"], 4.5e-3)
+    users = max(4 * cores, int(3.0 * cores / per_user_s))
+    base = 10_000_000
+    for w in range(args.warmup):
+        O.rollout(oe, base + w * users, max(cores, users // 8), policy=policy, table=table, threads=cores)
+    events = 0
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        r = O.rollout(oe, s * users, users, policy=policy, table=table, threads=cores)
+        events += int(r["totals"][1])
+    dt = time.perf_counter() - t0
+    val = events / dt
+    sample = "%d users/step x %d steps of the same workload, users 0.." % (users, args.steps)
+    line = {
+        "impl": "reference", "metric": "simulated user-steps/sec", "value": val, "unit": "user-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "users_per_step": users, "seed": SEED},
+        "cpu_baseline": {"value": val, "unit": "user-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "user-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--users", type=int, default=0, help="users per GPU per step (default: workload's)")
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--train-users", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.users:
+        wl["users"] = args.users
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import recogym_b200 as rg
+    from recogym_b200 import _lib as L
+    from recogym_b200.parallel import allreduce_counters
+
+    if L.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device and recogym_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    math_mode = L.MATH_FAST if args.math == "fast" else L.MATH_EXACT
+    P, K, U = wl["P"], wl["K"], wl["users"]
+
+    cfg, sp = static_params(P, K)
+    policy, table = train_policy_table(wl["policy"], P, K, args.train_users)
+    de = rg.DeviceEnv(sp, cfg.sigma_omega_initial, cfg.sigma_omega, SEED, device=local_rank)
+    table_dev = torch.as_tensor(table, device=dev) if table is not None else None
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    step_tots = torch.zeros((args.steps, 8), dtype=torch.int64, device=dev)
+
+    def step(s, tot):
+        """one fused rollout of U fresh users on this rank + the all-reduce of the CTR counters"""
+        first = (s * world + rank) * U
+        de.rollout_device(U, policy, table_dev, first, 0, math_mode, per_user=False, totals=tot)
+        allreduce_counters(tot)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(1000 + w, torch.zeros(8, dtype=torch.int64, device=dev))
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)              # L2 flush between timed iterations (outside the event pair)
+        evs[s][0].record()
+        step(s, step_tots[s])
+        evs[s][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ev = step_tots.sum(0).cpu().numpy()   # every row was all-reduced: job-wide counters of the timed steps
+    events = int(ev[1])
+    value = events / (total_ms * 1e-3)
+
+    # ---- e2e: the reference-facing host API (C ABI with HOST buffers), copies inside the timed region
+    host_table = table
+    barrier()
+    t0 = time.perf_counter()
+    e2e_events = 0
+    d2h = 0
+    for s in range(args.steps):
+        first = ((s + 5000) * world + rank) * U
+        r = de.rollout_host(U, policy, host_table, first, 0, math_mode, per_user=False)
+        e2e_events += int(r["totals"][1])
+        d2h = 64
+    if world > 1:
+        # counters of the host path are reduced with the same collective, on device
+        tt = torch.tensor([e2e_events], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        e2e_events = int(tt.item())
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_events / float(e2e_dt.item())
+    h2d = 4 * P if table is not None else 0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src, sm_max = peaks()
+    per_gpu_steps_s = value / world
+    alg_bytes = ALG_BYTES_PER_STEP.get(K, 4.0 * K * 2.2 + 16)
+    avg_launch_s = (total_ms * 1e-3) / args.steps
+    launch_events = events / world / args.steps
+    achieved_gbs = alg_bytes * launch_events / avg_launch_s / 1e9
+    # compute roofline (the physically binding one): fp32 FMA pipe of the organic contraction
+    flops_per_step = F_ORG * (2.0 * P * K)
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6
+    line = {
+        "metric": "simulated user-steps/sec", "value": value, "unit": "user-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
+        "data": "synthetic",
+        "config": {"workload": wl["label"], "num_products": P, "K": K, "users_per_gpu_per_step": U,
+                   "policy": wl["policy"], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
+                   "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
+                   "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
+                   "fast_path_fallbacks": int(ev[6]), "f64_ambiguous": int(ev[7])},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_user_step": alg_bytes,
+                     "note": "fused rollout keeps user state on chip: HBM is not the physical bound (SURVEY.md 8d); "
+                             "see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32-fma", "achieved": per_gpu_steps_s * flops_per_step / 1e12,
+                          "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                          "frac": per_gpu_steps_s * flops_per_step / fp32_peak,
+                          "flops_per_user_step": flops_per_step},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                         cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
+        cores = os.cpu_count() or 1
+        per_user_s = {100: 6e-5, 10000: 4.5e-3, 100000: 0.15}.get(P, 4.5e-3)
+        n_cpu = max(4 * cores, int(12.0 * cores / per_user_s))
+        t0 = time.perf_counter()
+        rc = O.rollout(oe, 0, n_cpu, policy=policy, table=table, threads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": float(rc["totals"][1]) / dt, "unit": "user-steps/s", "cores": cores,
+                                "kind": "port", "sample": "users 0..%d of the same workload (%.1f s, C oracle port of "
+                                "the reference algorithm, all host threads)" % (n_cpu - 1, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

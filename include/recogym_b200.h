@@ -1,0 +1,156 @@
+/*
+ * recogym_b200.h -- C ABI of the B200-native reco-gym-v1 simulation hot path.
+ *
+ * The reference (criteo-research/reco-gym) has no FFI: its hot path is a Python object protocol
+ * (SURVEY.md 8b).  This header is the native boundary a maintainer of the reference would bind
+ * (ctypes stub in INTEGRATION.md); every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - every function returns RG_OK (0) or a negative RG_E* code; rg_last_error() gives the text
+ *     (thread-local).  Nothing aborts the process (reference: bare asserts -> AssertionError).
+ *   - "host" entry points take HOST buffers and perform the host<->device copies themselves;
+ *     "_device" entry points take DEVICE buffers (caller-owned, e.g. torch tensors) and launch
+ *     asynchronously on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *   - ids are int32/int64 (the reference's int16/UInt16 casts, reco_env_v1.py:123 and
+ *     abstract.py:214,319-321, overflow beyond P=32767 / 65535 users; widened on purpose).
+ *   - all discrete results are defined by the RNG spec in DESIGN.md: Philox4x32-10,
+ *     key = seed, counter = (user_lo, user_hi, event_time, slot).
+ */
+#ifndef RECOGYM_B200_H
+#define RECOGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_OK 0
+#define RG_EINVAL (-1)   /* bad argument (shape, null pointer, out-of-range probability) */
+#define RG_ECUDA (-2)    /* CUDA runtime error; text in rg_last_error() */
+#define RG_ENOMEM (-3)
+#define RG_ENODEVICE (-4) /* no CUDA device / wrong architecture: there is NO CPU fallback */
+
+/* Markov states, recogym/envs/abstract.py:41-43 */
+#define RG_ORGANIC 0
+#define RG_BANDIT 1
+#define RG_STOP 2
+
+/* device policies for the fused rollout */
+#define RG_POLICY_UNIFORM 0 /* default logging policy, abstract.py:211-221 (uniform over products) */
+#define RG_POLICY_TABLE 1   /* action = table[last viewed product]: OrganicCount.act (agents/organic_count.py:54-72),
+                               BanditCount.act (agents/bandit_count.py:28-47), BanditMFSquare.act (agents/bandit_mf.py:44-87) */
+
+/* math modes of the organic-view sampler */
+#define RG_MATH_EXACT 0 /* every view sampled in binary64 (reference arithmetic) */
+#define RG_MATH_FAST 1  /* fp32 CUDA-core contraction with a rigorous ambiguity filter; ambiguous
+                           events are re-sampled in binary64, so discrete results equal RG_MATH_EXACT */
+
+/* Static parameters of one environment == what RecoEnv1.set_static_params() builds
+ * (recogym/envs/reco_env_v1.py:51-75) plus the config scalars update_state()/reset() read. */
+typedef struct rg_env_desc {
+    int32_t num_products;            /* config.num_products */
+    int32_t K;                       /* config.K */
+    const double *Gamma;             /* host [P][K] row-major   (reco_env_v1.py:64-66) */
+    const double *mu_organic;        /* host [P]                (reco_env_v1.py:69-72) */
+    const double *beta;              /* host [P][K] row-major   (reco_env_v1.py:133-174) */
+    const double *mu_bandit;         /* host [P] */
+    double state_transition[9];      /* row-major 3x3           (reco_env_v1.py:54-61) */
+    double sigma_omega_initial;      /* reco_env_v1.py:80-82 */
+    double sigma_omega;              /* reco_env_v1.py:96-99 */
+    int32_t change_omega_for_bandits;/* reco_env_v1.py:95,106 */
+    int32_t reserved;
+    uint64_t seed;                   /* config.random_seed + epoch (abstract.py:59-62) */
+} rg_env_desc;
+
+typedef struct rg_env rg_env; /* opaque: owns the device copies of the static parameters */
+
+/* AbstractEnv.init_gym + RecoEnv1.set_static_params (abstract.py:64-88): uploads the parameters
+ * to `device` (f64 row-major beta, f64 K-major Gamma, fp32 copies for RG_MATH_FAST). */
+int rg_env_create(const rg_env_desc *desc, int device, rg_env **out);
+/* AbstractEnv.reset_random_seed(epoch) (abstract.py:59-62): seed = random_seed + epoch */
+int rg_env_set_seed(rg_env *env, uint64_t seed);
+int rg_env_destroy(rg_env *env);
+
+typedef struct rg_policy {
+    int32_t kind;          /* RG_POLICY_* */
+    int32_t reserved;
+    const int32_t *table;  /* [P] (RG_POLICY_TABLE); host pointer for rg_rollout_host,
+                              device pointer for rg_rollout_device */
+} rg_policy;
+
+/* Outputs of a rollout; every pointer is nullable.  Per-user arrays are indexed by
+ * (user_id - user_begin) and have n_organic_users + n_users entries. */
+typedef struct rg_rollout_out {
+    int32_t *n_events;   /* update_state() calls of the user == its final current_time */
+    int32_t *n_organic;  /* organic views */
+    int32_t *n_bandit;   /* delivered recommendations (phantom row excluded) */
+    int32_t *n_clicks;
+    int32_t *last_view;
+    uint64_t *hash;      /* FNV-1a chain over the user's event records (DESIGN.md "event hash") */
+    double *omega;       /* [users][K] final latent state */
+    int64_t *view_hist;  /* [P] accumulated */
+    int64_t *action_hist;/* [P] accumulated (delivered actions) */
+    int64_t *click_hist; /* [P] accumulated (clicked actions; evaluate_agent.py:121-124) */
+    int64_t *totals;     /* [8] accumulated: users, events, organic, bandit, clicks, phantom rows,
+                            fast-path fallbacks, f64-ambiguous samples (diagnostic, expected 0) */
+} rg_rollout_out;
+
+/* AbstractEnv.generate_logs(num_offline_users=n_users, agent, num_organic_offline_users=
+ * n_organic_users) (abstract.py:241-327) reduced to counters: users user_begin.. are simulated to
+ * the end of their episode with the policy acting on device.  The first n_organic_users ids are
+ * organic-only (abstract.py:293-297).  test_agent's and verify_agents' success/failure counts
+ * (bench_agents.py:203-206, evaluate_agent.py:742-745) are totals[4] and totals[3]+totals[5]-totals[4]. */
+int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, int64_t n_organic_users,
+                      int64_t n_users, const rg_rollout_out *out_device, int math_mode, void *stream);
+/* Same through HOST buffers: table H2D, outputs D2H, synchronous. */
+int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, int64_t n_organic_users,
+                    int64_t n_users, const rg_rollout_out *out_host, int math_mode);
+
+/* Batched gym protocol.  State of N concurrent users is a caller-owned SoA on the device:
+ *   user_id[N] int64, state[N] int32 (RG_*), t[N] int32 (current_time), last_view[N] int32,
+ *   omega[N][K] double.
+ * Organic sessions are returned as sess_v[N][sess_cap] + sess_len[N]; a user whose session did not
+ * fit keeps state RG_ORGANIC and is counted in *n_unfinished (device int32, accumulated): call
+ * rg_batch_continue_device to obtain the rest (appended semantics: the caller concatenates). */
+
+/* env.reset(user_id) + env.step(None) (abstract.py:90-103,157-172; reco_env_v1.py:78-82) */
+int rg_batch_reset_device(rg_env *env, int64_t N, const int64_t *user_id, int32_t *state, int32_t *t,
+                          int32_t *last_view, double *omega, int32_t *sess_v, int32_t *sess_len,
+                          int32_t sess_cap, int32_t *n_unfinished, int math_mode, void *stream);
+/* env.step(action) (abstract.py:174-197): reward[N] = click; users with state RG_STOP are left
+ * untouched (reward 0, empty session). done == (state == RG_STOP). */
+int rg_batch_step_device(rg_env *env, int64_t N, const int64_t *user_id, const int32_t *action, int32_t *state,
+                         int32_t *t, int32_t *last_view, double *omega, int32_t *reward, int32_t *sess_v,
+                         int32_t *sess_len, int32_t sess_cap, int32_t *n_unfinished, int math_mode,
+                         void *stream);
+/* continues generate_organic_sessions (abstract.py:105-121) for users still RG_ORGANIC */
+int rg_batch_continue_device(rg_env *env, int64_t N, const int64_t *user_id, int32_t *state, int32_t *t,
+                             int32_t *last_view, double *omega, int32_t *sess_v, int32_t *sess_len,
+                             int32_t sess_cap, int32_t *n_unfinished, int math_mode, void *stream);
+
+/* Scalar spec functions evaluated on the HOST by the same source the kernels compile
+ * (no GPU needed): used by the CPU tests to pin the RNG/math spec. */
+void rg_spec_philox(uint64_t seed, uint64_t user, uint32_t t, uint32_t slot, uint32_t out[4]);
+double rg_spec_exp(double x);
+double rg_spec_log(double x);
+double rg_spec_norm_ppf(double p);
+double rg_spec_ff(double x);            /* reco_env_v1.py:38-41 */
+double rg_spec_event_uniform(uint64_t seed, uint64_t user, uint32_t t, int which);
+void rg_spec_normals(uint64_t seed, uint64_t user, uint32_t t, int K, double *z);
+int32_t rg_spec_policy_uniform_action(uint64_t seed, uint64_t user, uint32_t t, int32_t P);
+
+/* The same functions evaluated ON THE DEVICE (device buffers): kind 0 exp, 1 log, 2 norm_ppf, 3 ff map
+ * in[n] -> out[n]; kinds 4 (first normal pair), 5 (event uniforms), 6 (uniform action for P=1000003, word 3)
+ * map in[3n] = (seed, user, t) triples, each exactly representable in a double, to out[2n]. */
+int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *out_device, void *stream);
+
+int rg_device_count(void);              /* 0 when no usable GPU: callers must fail, not fall back */
+int rg_version(void);
+const char *rg_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOGYM_B200_H */

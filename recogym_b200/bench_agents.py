@@ -1,0 +1,82 @@
+"""test_agent: train an agent on logged users, evaluate it online, return Beta-posterior CTR
+quantiles (reference: recogym/bench_agents.py:66-251; the pickle cache :17-63 is out of scope).
+
+Training runs through the RecoEnv1 facade because `agent.train` is arbitrary Python; the online
+evaluation -- the expensive part -- runs as ONE fused CUDA rollout whenever the trained agent
+compiles to a device policy (recogym_b200.policy), else through the facade's generate_logs.
+"""
+from copy import deepcopy
+
+import numpy as np
+from scipy.stats.distributions import beta
+
+from .constants import AgentStats
+from .policy import device_policy
+
+
+def _collect_stats(args):
+    env, agent = args["env"], args["agent"]
+    epoch = args["epoch"]
+    new_agent = deepcopy(agent)
+    if args["epoch_with_random_reset"]:
+        train_env = deepcopy(env)
+        train_env.reset_random_seed(epoch)
+    else:
+        train_env = env
+    uid = 0
+    # offline organic training (bench_agents.py:169-173)
+    for _ in range(args["num_organic_offline_users"]):
+        train_env.reset(uid)
+        uid += 1
+        obs, _, _, _ = train_env.step(None)
+        new_agent.train(obs, None, None, True)
+    # offline organic + bandit training under the env's logging policy (bench_agents.py:176-190)
+    for _ in range(args["num_offline_users"]):
+        train_env.reset(uid)
+        uid += 1
+        new_obs, _, done, reward = train_env.step(None)
+        while not done:
+            old_obs = new_obs
+            action, new_obs, reward, done, _ = train_env.step_offline(old_obs, reward, done)
+            new_agent.train(old_obs, action, reward, False)
+        old_obs = new_obs
+        action, _, reward, done, _ = train_env.step_offline(old_obs, reward, done)
+        new_agent.train(old_obs, action, reward, True)
+
+    if args["epoch_with_random_reset"]:
+        eval_env = deepcopy(env)
+        eval_env.reset_random_seed(epoch)
+    else:
+        eval_env = env
+    pol = device_policy(new_agent, eval_env.config.num_products, allow_probe=args.get("allow_probe", False))
+    if pol is not None:
+        r = eval_env.generate_logs_counters(args["num_online_users"], pol["policy"], pol.get("table"))
+        successes, failures = r["successes"], r["failures"]
+    else:
+        data = eval_env.generate_logs(args["num_online_users"], agent=new_agent)
+        rewards = data[~np.isnan(data["a"].astype("float64"))]["c"]
+        successes = np.sum(rewards)
+        failures = rewards.shape[0] - successes
+    return {AgentStats.SUCCESSES: successes, AgentStats.FAILURES: failures}
+
+
+def test_agent(env, agent, num_offline_users=1000, num_online_users=100, num_organic_offline_users=0,
+               num_epochs=1, epoch_with_random_reset=False, with_cache=False, allow_probe=False):
+    """-> (median, q0.025, q0.975) of Beta(successes+1, failures+1) (bench_agents.py:215-251)."""
+    if with_cache:
+        raise NotImplementedError("the on-disk training-log cache of the reference is out of scope")
+    successes = failures = 0
+    for epoch in range(num_epochs):
+        res = _collect_stats({
+            "env": env, "agent": agent, "num_offline_users": num_offline_users,
+            "num_online_users": num_online_users, "num_organic_offline_users": num_organic_offline_users,
+            "epoch_with_random_reset": epoch_with_random_reset, "epoch": epoch, "allow_probe": allow_probe,
+        })
+        successes += res[AgentStats.SUCCESSES]
+        failures += res[AgentStats.FAILURES]
+    return (beta.ppf(0.500, successes + 1, failures + 1),
+            beta.ppf(0.025, successes + 1, failures + 1),
+            beta.ppf(0.975, successes + 1, failures + 1))
+
+
+test_agent.__test__ = False  # not a pytest test

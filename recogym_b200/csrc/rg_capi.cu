@@ -1,0 +1,342 @@
+// rg_capi.cu -- the C ABI of include/recogym_b200.h (host side: validation, parameter upload,
+// launches, host<->device copies of the *_host entry points).  No CPU compute path exists here:
+// without a usable GPU every entry point returns RG_ENODEVICE.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rg_host.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RG_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return fail(RG_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__),  \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+template <typename T>
+cudaError_t upload(T **dst, const std::vector<T> &src) {
+    cudaError_t e = cudaMalloc((void **)dst, sizeof(T) * src.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+}
+
+void free_env(rg_env_impl &e) {
+    cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.diag);
+}
+
+rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
+    rg::RolloutOutDev d;
+    d.n_events = o.n_events; d.n_organic = o.n_organic; d.n_bandit = o.n_bandit; d.n_clicks = o.n_clicks;
+    d.last_view = o.last_view; d.hash = o.hash; d.omega = o.omega;
+    d.view_hist = (unsigned long long *)o.view_hist;
+    d.action_hist = (unsigned long long *)o.action_hist;
+    d.click_hist = (unsigned long long *)o.click_hist;
+    d.totals = (unsigned long long *)o.totals;
+    return d;
+}
+
+int check_rollout_args(const rg_env *env, const rg_policy *policy, int64_t n_organic_users, int64_t n_users,
+                       const rg_rollout_out *out, int math_mode) {
+    if (!env || !policy || !out) return fail(RG_EINVAL, "null argument");
+    if (n_organic_users < 0 || n_users < 0) return fail(RG_EINVAL, "negative user count");
+    if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE)
+        return fail(RG_EINVAL, "unknown policy kind %d", policy->kind);
+    if (policy->kind == RG_POLICY_TABLE && !policy->table) return fail(RG_EINVAL, "table policy without table");
+    if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST)
+        return fail(RG_EINVAL, "unknown math mode %d", math_mode);
+    return RG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rg_last_error(void) { return g_err; }
+int rg_version(void) { return 100; }
+
+int rg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
+    if (!d || !out) return fail(RG_EINVAL, "null argument");
+    *out = nullptr;
+    const int P = d->num_products, K = d->K;
+    if (P < 1) return fail(RG_EINVAL, "num_products must be >= 1 (got %d)", P);
+    if (K < 1 || K > rg::kMaxK) return fail(RG_EINVAL, "K must be in [1,%d] (got %d)", rg::kMaxK, K);
+    if (!d->Gamma || !d->mu_organic || !d->beta || !d->mu_bandit) return fail(RG_EINVAL, "null parameter array");
+    if (!(d->sigma_omega_initial >= 0.0) || !(d->sigma_omega >= 0.0)) return fail(RG_EINVAL, "negative sigma");
+    for (int r = 0; r < 3; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) {
+            const double p = d->state_transition[3 * r + c];
+            // numpy RandomState.choice: "probabilities are not non-negative" / "do not sum to 1"
+            if (!(p >= 0.0) || !(p <= 1.0)) return fail(RG_EINVAL, "state_transition[%d][%d]=%g is not a probability", r, c, p);
+            s += p;
+        }
+        if (std::fabs(s - 1.0) > 1.4901161193847656e-08)
+            return fail(RG_EINVAL, "state_transition row %d does not sum to 1 (%.17g)", r, s);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(RG_ENODEVICE, "no CUDA device: recogym_b200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(RG_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    RG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RG_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+
+    rg_env *env = new (std::nothrow) rg_env();
+    if (!env) return fail(RG_ENOMEM, "out of host memory");
+    rg_env_impl &e = env->impl;
+    e.device = device;
+    e.num_sms = prop.multiProcessorCount;
+    const int Ppad = (P + 31) & ~31;
+
+    std::vector<double> GT((size_t)K * Ppad, 0.0), mu(Ppad, 0.0);
+    std::vector<float> GT32((size_t)K * Ppad, 0.f), mu32(Ppad, 0.f);
+    double gmax = 0.0, mumax = -INFINITY;
+    for (int p = 0; p < P; ++p) {
+        double n2 = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double g = d->Gamma[(size_t)p * K + k];
+            GT[(size_t)k * Ppad + p] = g;
+            GT32[(size_t)k * Ppad + p] = (float)g;
+            n2 += g * g;
+        }
+        mu[p] = d->mu_organic[p];
+        mu32[p] = (float)d->mu_organic[p];
+        gmax = std::fmax(gmax, std::sqrt(n2));
+        mumax = std::fmax(mumax, d->mu_organic[p]);
+    }
+    std::vector<double> beta(d->beta, d->beta + (size_t)P * K), mub(d->mu_bandit, d->mu_bandit + P);
+
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = upload(&e.d_GammaT, GT);
+    if (ce == cudaSuccess) ce = upload(&e.d_mu_o, mu);
+    if (ce == cudaSuccess) ce = upload(&e.d_beta, beta);
+    if (ce == cudaSuccess) ce = upload(&e.d_mu_b, mub);
+    if (ce == cudaSuccess) ce = upload(&e.d_GammaT32, GT32);
+    if (ce == cudaSuccess) ce = upload(&e.d_mu_o32, mu32);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.diag, sizeof(unsigned long long) * 4);
+    if (ce == cudaSuccess) ce = cudaMemset(e.diag, 0, sizeof(unsigned long long) * 4);
+    if (ce != cudaSuccess) {
+        free_env(e);
+        delete env;
+        return fail(ce == cudaErrorMemoryAllocation ? RG_ENOMEM : RG_ECUDA, "parameter upload failed: %s",
+                    cudaGetErrorString(ce));
+    }
+
+    rg::EnvDev &v = e.dev;
+    v.P = P; v.K = K; v.Ppad = Ppad;
+    v.GammaT = e.d_GammaT; v.mu_o = e.d_mu_o; v.beta = e.d_beta; v.mu_b = e.d_mu_b;
+    v.GammaT32 = e.d_GammaT32; v.mu_o32 = e.d_mu_o32;
+    for (int r = 0; r < 3; ++r) {
+        // numpy legacy choice: cdf = p.cumsum(); cdf /= cdf[-1]
+        const double c0 = d->state_transition[3 * r], c1 = c0 + d->state_transition[3 * r + 1];
+        const double c2 = c1 + d->state_transition[3 * r + 2];
+        v.thr[r][0] = c0 / c2;
+        v.thr[r][1] = c1 / c2;
+    }
+    v.sigma0 = d->sigma_omega_initial;
+    v.sigma = d->sigma_omega;
+    // slack so that rounding in the bound itself can never put a logit above it
+    v.gmax = gmax * (1.0 + 1e-12);
+    v.mumax = mumax + 1e-9 * std::fabs(mumax) + 1e-12;
+    v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
+    v.seed = d->seed;
+    *out = env;
+    return RG_OK;
+}
+
+int rg_env_set_seed(rg_env *env, uint64_t seed) {
+    if (!env) return fail(RG_EINVAL, "null env");
+    env->impl.dev.seed = seed;
+    return RG_OK;
+}
+
+int rg_env_destroy(rg_env *env) {
+    if (!env) return RG_OK;
+    cudaSetDevice(env->impl.device);
+    free_env(env->impl);
+    delete env;
+    return RG_OK;
+}
+
+int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, int64_t n_organic_users,
+                      int64_t n_users, const rg_rollout_out *out, int math_mode, void *stream) {
+    int rc = check_rollout_args(env, policy, n_organic_users, n_users, out, math_mode);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(cudaSetDevice(env->impl.device));
+    rg::PolicyDev pol{policy->kind, policy->table};
+    const rg::RolloutOutDev od = to_dev(*out);
+    if (math_mode == RG_MATH_FAST)
+        RG_CUDA(rg::launch_rollout_fast(env->impl, pol, user_begin, n_organic_users, n_organic_users + n_users, od,
+                                        (cudaStream_t)stream));
+    else
+        RG_CUDA(rg::launch_rollout_exact(env->impl, pol, user_begin, n_organic_users, n_organic_users + n_users, od,
+                                         (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, int64_t n_organic_users,
+                    int64_t n_users, const rg_rollout_out *out, int math_mode) {
+    int rc = check_rollout_args(env, policy, n_organic_users, n_users, out, math_mode);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(cudaSetDevice(env->impl.device));
+    const int64_t n = n_organic_users + n_users;
+    const int P = env->impl.dev.P, K = env->impl.dev.K;
+    // one device arena for the table and every requested output
+    struct Seg { void *host; size_t bytes; size_t off; bool accumulate; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    auto add = [&](void *host, size_t bytes, bool acc) -> size_t {
+        const size_t off = total;
+        if (host) { segs.push_back(Seg{host, bytes, off, acc}); total += (bytes + 255) & ~(size_t)255; }
+        return off;
+    };
+    const size_t o_ne = add(out->n_events, 4 * n, false), o_no = add(out->n_organic, 4 * n, false);
+    const size_t o_nb = add(out->n_bandit, 4 * n, false), o_nc = add(out->n_clicks, 4 * n, false);
+    const size_t o_lv = add(out->last_view, 4 * n, false), o_h = add(out->hash, 8 * n, false);
+    const size_t o_om = add(out->omega, 8 * (size_t)n * K, false);
+    const size_t o_vh = add(out->view_hist, 8 * (size_t)P, true), o_ah = add(out->action_hist, 8 * (size_t)P, true);
+    const size_t o_ch = add(out->click_hist, 8 * (size_t)P, true), o_t = add(out->totals, 8 * 8, true);
+    const size_t o_tab = total;
+    if (policy->kind == RG_POLICY_TABLE) total += ((size_t)4 * P + 255) & ~(size_t)255;
+    char *arena = nullptr;
+    if (total == 0) total = 256;
+    RG_CUDA(cudaMalloc((void **)&arena, total));
+    cudaError_t ce = cudaMemsetAsync(arena, 0, total, 0);
+    rg_policy pd = *policy;
+    if (ce == cudaSuccess && policy->kind == RG_POLICY_TABLE) {
+        ce = cudaMemcpyAsync(arena + o_tab, policy->table, (size_t)4 * P, cudaMemcpyHostToDevice, 0);
+        pd.table = (const int32_t *)(arena + o_tab);
+    }
+    rg_rollout_out dv;
+    std::memset(&dv, 0, sizeof(dv));
+    if (out->n_events) dv.n_events = (int32_t *)(arena + o_ne);
+    if (out->n_organic) dv.n_organic = (int32_t *)(arena + o_no);
+    if (out->n_bandit) dv.n_bandit = (int32_t *)(arena + o_nb);
+    if (out->n_clicks) dv.n_clicks = (int32_t *)(arena + o_nc);
+    if (out->last_view) dv.last_view = (int32_t *)(arena + o_lv);
+    if (out->hash) dv.hash = (uint64_t *)(arena + o_h);
+    if (out->omega) dv.omega = (double *)(arena + o_om);
+    if (out->view_hist) dv.view_hist = (int64_t *)(arena + o_vh);
+    if (out->action_hist) dv.action_hist = (int64_t *)(arena + o_ah);
+    if (out->click_hist) dv.click_hist = (int64_t *)(arena + o_ch);
+    if (out->totals) dv.totals = (int64_t *)(arena + o_t);
+    if (ce == cudaSuccess) {
+        rc = rg_rollout_device(env, &pd, user_begin, n_organic_users, n_users, &dv, math_mode, nullptr);
+        if (rc != RG_OK) { cudaFree(arena); return rc; }
+    }
+    std::vector<int64_t> tmp;
+    for (const Seg &s : segs) {
+        if (ce != cudaSuccess) break;
+        if (!s.accumulate) {
+            ce = cudaMemcpy(s.host, arena + s.off, s.bytes, cudaMemcpyDeviceToHost);
+        } else {
+            tmp.resize(s.bytes / 8);
+            ce = cudaMemcpy(tmp.data(), arena + s.off, s.bytes, cudaMemcpyDeviceToHost);
+            if (ce == cudaSuccess)
+                for (size_t i = 0; i < tmp.size(); ++i) ((int64_t *)s.host)[i] += tmp[i];
+        }
+    }
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    cudaFree(arena);
+    if (ce != cudaSuccess) return fail(RG_ECUDA, "rollout failed: %s", cudaGetErrorString(ce));
+    return RG_OK;
+}
+
+static int batch_common(rg_env *env, int mode, int64_t N, const int64_t *user_id, const int32_t *action,
+                        int32_t *state, int32_t *t, int32_t *last_view, double *omega, int32_t *reward,
+                        int32_t *sess_v, int32_t *sess_len, int32_t sess_cap, int32_t *n_unfinished, int math_mode,
+                        void *stream) {
+    if (!env) return fail(RG_EINVAL, "null env");
+    if (N < 0) return fail(RG_EINVAL, "negative batch size");
+    if (!user_id || !state || !t || !last_view || !omega || !sess_v || !sess_len)
+        return fail(RG_EINVAL, "null state/session buffer");
+    if (mode == 1 && (!action || !reward)) return fail(RG_EINVAL, "step needs action and reward buffers");
+    if (sess_cap < 1) return fail(RG_EINVAL, "sess_cap must be >= 1");
+    if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST) return fail(RG_EINVAL, "unknown math mode");
+    RG_CUDA(cudaSetDevice(env->impl.device));
+    RG_CUDA(rg::launch_batch(env->impl, mode, N, (const long long *)user_id, action, state, t, last_view, omega,
+                             reward, sess_v, sess_len, sess_cap, n_unfinished, (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_batch_reset_device(rg_env *env, int64_t N, const int64_t *user_id, int32_t *state, int32_t *t,
+                          int32_t *last_view, double *omega, int32_t *sess_v, int32_t *sess_len, int32_t sess_cap,
+                          int32_t *n_unfinished, int math_mode, void *stream) {
+    return batch_common(env, 0, N, user_id, nullptr, state, t, last_view, omega, nullptr, sess_v, sess_len, sess_cap,
+                        n_unfinished, math_mode, stream);
+}
+
+int rg_batch_step_device(rg_env *env, int64_t N, const int64_t *user_id, const int32_t *action, int32_t *state,
+                         int32_t *t, int32_t *last_view, double *omega, int32_t *reward, int32_t *sess_v,
+                         int32_t *sess_len, int32_t sess_cap, int32_t *n_unfinished, int math_mode, void *stream) {
+    return batch_common(env, 1, N, user_id, action, state, t, last_view, omega, reward, sess_v, sess_len, sess_cap,
+                        n_unfinished, math_mode, stream);
+}
+
+int rg_batch_continue_device(rg_env *env, int64_t N, const int64_t *user_id, int32_t *state, int32_t *t,
+                             int32_t *last_view, double *omega, int32_t *sess_v, int32_t *sess_len,
+                             int32_t sess_cap, int32_t *n_unfinished, int math_mode, void *stream) {
+    return batch_common(env, 2, N, user_id, nullptr, state, t, last_view, omega, nullptr, sess_v, sess_len, sess_cap,
+                        n_unfinished, math_mode, stream);
+}
+
+int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *out_device, void *stream) {
+    if (kind < 0 || kind > 6 || n < 0 || !in_device || !out_device) return fail(RG_EINVAL, "bad spec_eval argument");
+    RG_CUDA(rg::launch_spec_eval(kind, n, in_device, out_device, (cudaStream_t)stream));
+    return RG_OK;
+}
+
+// ---- scalar spec functions, host instantiations of rg_math.cuh ---------------------------------
+void rg_spec_philox(uint64_t seed, uint64_t user, uint32_t t, uint32_t slot, uint32_t out[4]) {
+    const rg::u32x4 w = rg::draw(seed, user, t, slot);
+    out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
+}
+double rg_spec_exp(double x) { return rg::exp64(x); }
+double rg_spec_log(double x) { return rg::log64(x); }
+double rg_spec_norm_ppf(double p) { return rg::norm_ppf(p); }
+double rg_spec_ff(double x) { return rg::ff64(x); }
+double rg_spec_event_uniform(uint64_t seed, uint64_t user, uint32_t t, int which) {
+    const rg::u32x4 w = rg::draw(seed, user, t, rg::SLOT_EVENT);
+    return which ? rg::uniform53(w.z, w.w) : rg::uniform53(w.x, w.y);
+}
+void rg_spec_normals(uint64_t seed, uint64_t user, uint32_t t, int K, double *z) {
+    for (int j = 0; 2 * j < K; ++j) {
+        const rg::u32x4 w = rg::draw(seed, user, t, rg::SLOT_NORMAL + (uint32_t)j);
+        z[2 * j] = rg::normal_from_words(w.x, w.y);
+        if (2 * j + 1 < K) z[2 * j + 1] = rg::normal_from_words(w.z, w.w);
+    }
+}
+int32_t rg_spec_policy_uniform_action(uint64_t seed, uint64_t user, uint32_t t, int32_t P) {
+    return rg::uniform_action(rg::draw(seed, user, t, rg::SLOT_POLICY).x, P);
+}
+
+}  // extern "C"

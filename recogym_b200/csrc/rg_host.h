@@ -1,0 +1,34 @@
+// rg_host.h -- host-side handle behind the opaque rg_env of include/recogym_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "rg_device.cuh"
+
+struct rg_env_impl {
+    int device = 0;
+    int num_sms = 0;
+    rg::EnvDev dev{};
+    // owned device allocations
+    double *d_GammaT = nullptr, *d_mu_o = nullptr, *d_beta = nullptr, *d_mu_b = nullptr;
+    float *d_GammaT32 = nullptr, *d_mu_o32 = nullptr;
+    float *d_Gamma32 = nullptr;          // [Ppad][Kpad4] row-major fp32 (fast-path tiles)
+    unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
+};
+
+struct rg_env {
+    rg_env_impl impl;
+};
+
+namespace rg {
+cudaError_t launch_rollout_exact(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
+                                 long long n_organic_users, long long n_total, const RolloutOutDev &out,
+                                 cudaStream_t stream);
+cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
+                                long long n_organic_users, long long n_total, const RolloutOutDev &out,
+                                cudaStream_t stream);
+cudaError_t launch_batch(const rg_env_impl &e, int mode, long long N, const long long *user_id,
+                         const int32_t *action, int32_t *state, int32_t *t, int32_t *last_view, double *omega,
+                         int32_t *reward, int32_t *sess_v, int32_t *sess_len, int sess_cap, int32_t *n_unfinished,
+                         cudaStream_t stream);
+cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);
+}  // namespace rg

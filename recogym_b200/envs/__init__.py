@@ -1,0 +1,7 @@
+from .configuration import Configuration
+from .context import Context, DefaultContext
+from .observation import Observation
+from .session import Session, OrganicSessions
+from .reco_env_v1 import RecoEnv1, env_args, env_1_args
+from .device_env import DeviceEnv, BatchState
+from .features.time import TimeGenerator, DefaultTimeGenerator, NormalTimeGenerator

@@ -1,0 +1,222 @@
+"""DeviceEnv: the static parameters of one reco-gym-v1 environment resident on a B200, plus the
+vectorised entry points (fused rollout, batched reset/step) that call the CUDA kernels through the
+C ABI (include/recogym_b200.h).  torch supplies device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib as L
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeviceEnv:
+    """Owns an `rg_env` handle (device copies of Gamma, mu, beta and the transition thresholds)."""
+
+    def __init__(self, static_params, sigma_omega_initial, sigma_omega, seed, change_omega_for_bandits=False,
+                 device=0):
+        self.Gamma = np.ascontiguousarray(static_params["Gamma"], np.float64)
+        self.P, self.K = self.Gamma.shape
+        self.mu_organic = np.ascontiguousarray(np.ravel(static_params["mu_organic"]), np.float64)
+        self.beta = np.ascontiguousarray(static_params["beta"], np.float64)
+        self.mu_bandit = np.ascontiguousarray(np.ravel(static_params["mu_bandit"]), np.float64)
+        self.state_transition = np.ascontiguousarray(static_params["state_transition"], np.float64)
+        self.device = int(device)
+        self.seed = int(seed)
+        d = L.EnvDesc()
+        d.num_products, d.K = self.P, self.K
+        d.Gamma = self.Gamma.ctypes.data
+        d.mu_organic = self.mu_organic.ctypes.data
+        d.beta = self.beta.ctypes.data
+        d.mu_bandit = self.mu_bandit.ctypes.data
+        for i, v in enumerate(self.state_transition.reshape(9)):
+            d.state_transition[i] = float(v)
+        d.sigma_omega_initial = float(sigma_omega_initial)
+        d.sigma_omega = float(sigma_omega)
+        d.change_omega_for_bandits = int(bool(change_omega_for_bandits))
+        d.seed = self.seed
+        h = C.c_void_p()
+        L.check(L.lib().rg_env_create(C.byref(d), self.device, C.byref(h)))
+        self._h = h
+        self._desc_args = (sigma_omega_initial, sigma_omega, change_omega_for_bandits)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            L.lib().rg_env_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clone(self):
+        """Independent handle with the same parameters (deepcopy support of the facade)."""
+        sp = {"Gamma": self.Gamma, "mu_organic": self.mu_organic, "beta": self.beta, "mu_bandit": self.mu_bandit,
+              "state_transition": self.state_transition}
+        return DeviceEnv(sp, self._desc_args[0], self._desc_args[1], self.seed, self._desc_args[2], self.device)
+
+    def set_seed(self, seed):
+        """AbstractEnv.reset_random_seed(epoch): seed = random_seed + epoch (abstract.py:59-62)."""
+        self.seed = int(seed)
+        L.check(L.lib().rg_env_set_seed(self._h, self.seed))
+
+    @property
+    def torch_device(self):
+        return _torch().device("cuda", self.device)
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.torch_device).cuda_stream)
+
+    # -- fused rollout -------------------------------------------------------------------------
+    def rollout_device(self, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
+                       math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False, totals=None):
+        """generate_logs(n_users, agent, n_organic_users) reduced to counters, everything on device.
+
+        Returns a dict of torch tensors (device): per-user n_events/n_organic/n_bandit/n_clicks/
+        last_view/hash (if per_user), omega (if requested), view/action/click histograms (if hist)
+        and totals[8] (int64, accumulated into `totals` when given).  Asynchronous on the current stream.
+        """
+        torch = _torch()
+        dev = self.torch_device
+        n = int(n_users) + int(n_organic_users)
+        res = {}
+        out = L.RolloutOut()
+        if per_user:
+            for name in ("n_events", "n_organic", "n_bandit", "n_clicks", "last_view"):
+                res[name] = torch.empty(n, dtype=torch.int32, device=dev)
+                setattr(out, name, res[name].data_ptr())
+            res["hash"] = torch.empty(n, dtype=torch.int64, device=dev)
+            out.hash = res["hash"].data_ptr()
+        if omega:
+            res["omega"] = torch.empty((n, self.K), dtype=torch.float64, device=dev)
+            out.omega = res["omega"].data_ptr()
+        if hist:
+            for name in ("view_hist", "action_hist", "click_hist"):
+                res[name] = torch.zeros(self.P, dtype=torch.int64, device=dev)
+                setattr(out, name, res[name].data_ptr())
+        res["totals"] = totals if totals is not None else torch.zeros(8, dtype=torch.int64, device=dev)
+        out.totals = res["totals"].data_ptr()
+        pol = L.Policy()
+        if policy == "uniform":
+            pol.kind = L.POLICY_UNIFORM
+        elif policy == "table":
+            pol.kind = L.POLICY_TABLE
+            if not (hasattr(table, "is_cuda") and table.is_cuda):
+                table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
+            assert table.dtype == torch.int32 and table.numel() == self.P
+            res["_table"] = table  # keep alive until the launch has been enqueued
+            pol.table = table.data_ptr()
+        else:
+            raise ValueError("unknown policy %r" % (policy,))
+        L.check(L.lib().rg_rollout_device(self._h, C.byref(pol), int(user_begin), int(n_organic_users),
+                                          int(n_users), C.byref(out), int(math_mode), self._stream()))
+        return res
+
+    def rollout_host(self, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
+                     math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False):
+        """Same through HOST (numpy) buffers: the C ABI performs the H2D/D2H copies. Synchronous."""
+        n = int(n_users) + int(n_organic_users)
+        res = {}
+        out = L.RolloutOut()
+        if per_user:
+            for name in ("n_events", "n_organic", "n_bandit", "n_clicks", "last_view"):
+                res[name] = np.zeros(n, np.int32)
+                setattr(out, name, res[name].ctypes.data)
+            res["hash"] = np.zeros(n, np.uint64)
+            out.hash = res["hash"].ctypes.data
+        if omega:
+            res["omega"] = np.zeros((n, self.K), np.float64)
+            out.omega = res["omega"].ctypes.data
+        if hist:
+            for name in ("view_hist", "action_hist", "click_hist"):
+                res[name] = np.zeros(self.P, np.int64)
+                setattr(out, name, res[name].ctypes.data)
+        res["totals"] = np.zeros(8, np.int64)
+        out.totals = res["totals"].ctypes.data
+        pol = L.Policy()
+        keep = None
+        if policy == "uniform":
+            pol.kind = L.POLICY_UNIFORM
+        elif policy == "table":
+            pol.kind = L.POLICY_TABLE
+            keep = np.ascontiguousarray(table, np.int32)
+            assert keep.shape == (self.P,)
+            pol.table = keep.ctypes.data
+        else:
+            raise ValueError("unknown policy %r" % (policy,))
+        L.check(L.lib().rg_rollout_host(self._h, C.byref(pol), int(user_begin), int(n_organic_users), int(n_users),
+                                        C.byref(out), int(math_mode)))
+        del keep
+        return res
+
+
+class BatchState:
+    """Device SoA of N concurrent users for the batched gym protocol."""
+
+    def __init__(self, env, user_ids, sess_cap=32):
+        torch = _torch()
+        dev = env.torch_device
+        self.env = env
+        self.user_id = torch.as_tensor(np.ascontiguousarray(user_ids, np.int64), device=dev)
+        self.N = int(self.user_id.numel())
+        self.sess_cap = int(sess_cap)
+        # one int32 slab: state | t | last_view | reward | sess_len | sess_v   (a single D2H reads it all)
+        self.slab = torch.zeros(self.N * (5 + self.sess_cap), dtype=torch.int32, device=dev)
+        N = self.N
+        self.state = self.slab[0:N]
+        self.t = self.slab[N:2 * N]
+        self.last_view = self.slab[2 * N:3 * N]
+        self.reward = self.slab[3 * N:4 * N]
+        self.sess_len = self.slab[4 * N:5 * N]
+        self.sess_v = self.slab[5 * N:].view(N, self.sess_cap)
+        self.omega = torch.zeros((N, env.K), dtype=torch.float64, device=dev)
+        self.n_unfinished = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _common(self):
+        return (_ptr(self.state), _ptr(self.t), _ptr(self.last_view), _ptr(self.omega))
+
+    def reset(self, math_mode=L.MATH_EXACT):
+        """env.reset(user) + env.step(None) for every user (abstract.py:90-103,157-172)."""
+        e = self.env
+        self.n_unfinished.zero_()
+        L.check(L.lib().rg_batch_reset_device(e._h, self.N, _ptr(self.user_id), *self._common(), _ptr(self.sess_v),
+                                              _ptr(self.sess_len), self.sess_cap, _ptr(self.n_unfinished),
+                                              int(math_mode), e._stream()))
+
+    def step(self, action, math_mode=L.MATH_EXACT):
+        """env.step(action) for every user not yet done (abstract.py:174-197)."""
+        torch = _torch()
+        e = self.env
+        if not (hasattr(action, "is_cuda") and action.is_cuda):
+            action = torch.as_tensor(np.ascontiguousarray(action, np.int32), device=e.torch_device)
+        assert action.dtype == torch.int32 and action.numel() == self.N
+        self.n_unfinished.zero_()
+        L.check(L.lib().rg_batch_step_device(e._h, self.N, _ptr(self.user_id), _ptr(action), *self._common(),
+                                             _ptr(self.reward), _ptr(self.sess_v), _ptr(self.sess_len),
+                                             self.sess_cap, _ptr(self.n_unfinished), int(math_mode), e._stream()))
+
+    def continue_sessions(self, math_mode=L.MATH_EXACT):
+        """more views for users whose organic session did not fit in sess_cap (abstract.py:105-121)."""
+        e = self.env
+        self.n_unfinished.zero_()
+        L.check(L.lib().rg_batch_continue_device(e._h, self.N, _ptr(self.user_id), *self._common(),
+                                                 _ptr(self.sess_v), _ptr(self.sess_len), self.sess_cap,
+                                                 _ptr(self.n_unfinished), int(math_mode), e._stream()))
+
+    def read(self):
+        """One D2H copy of the int32 slab -> dict of numpy views (synchronises)."""
+        h = self.slab.cpu().numpy()
+        N = self.N
+        return {"state": h[0:N], "t": h[N:2 * N], "last_view": h[2 * N:3 * N], "reward": h[3 * N:4 * N],
+                "sess_len": h[4 * N:5 * N], "sess_v": h[5 * N:].reshape(N, self.sess_cap)}
