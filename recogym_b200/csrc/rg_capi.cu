@@ -134,6 +134,22 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
         mumax = std::fmax(mumax, d->mu_organic[p]);
     }
     std::vector<double> beta(d->beta, d->beta + (size_t)P * K), mub(d->mu_bandit, d->mu_bandit + P);
+    // fp32 tiles of the fast sampler: [nsub][K+1][128], pre-scaled by log2(e) so that the kernel's
+    // exponential is a bare ex2; row K carries mu_organic; products past P get mass 0 (mu = -1e30).
+    const int nsub = (P + 127) / 128;
+    const double kLog2e = 1.4426950408889634074;
+    double muabsmax = 0.0;
+    std::vector<float> G32((size_t)nsub * (K + 1) * 128, 0.f);
+    for (int p = 0; p < nsub * 128; ++p) {
+        const size_t base = (size_t)(p / 128) * (K + 1) * 128 + (p % 128);
+        if (p < P) {
+            for (int k = 0; k < K; ++k) G32[base + (size_t)k * 128] = (float)(d->Gamma[(size_t)p * K + k] * kLog2e);
+            G32[base + (size_t)K * 128] = (float)(d->mu_organic[p] * kLog2e);
+            muabsmax = std::fmax(muabsmax, std::fabs(d->mu_organic[p]));
+        } else {
+            G32[base + (size_t)K * 128] = -1e30f;
+        }
+    }
 
     cudaError_t ce = cudaSuccess;
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT, GT);
@@ -142,6 +158,7 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     if (ce == cudaSuccess) ce = upload(&e.d_mu_b, mub);
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT32, GT32);
     if (ce == cudaSuccess) ce = upload(&e.d_mu_o32, mu32);
+    if (ce == cudaSuccess) ce = upload(&e.d_Gamma32, G32);
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.diag, sizeof(unsigned long long) * 4);
     if (ce == cudaSuccess) ce = cudaMemset(e.diag, 0, sizeof(unsigned long long) * 4);
     if (ce != cudaSuccess) {
@@ -167,6 +184,9 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     // slack so that rounding in the bound itself can never put a logit above it
     v.gmax = gmax * (1.0 + 1e-12);
     v.mumax = mumax + 1e-9 * std::fabs(mumax) + 1e-12;
+    v.muabsmax = muabsmax;
+    v.G32 = e.d_Gamma32;
+    v.nsub = nsub;
     v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
     v.seed = d->seed;
     *out = env;

@@ -21,6 +21,9 @@ struct EnvDev {
     double thr[3][2];          // numpy-choice thresholds of each transition row: cdf0/cdf2, cdf1/cdf2
     double sigma0, sigma;
     double gmax, mumax;        // max_p |Gamma_p|_2 and max_p mu_organic[p]: logit upper bound
+    double muabsmax;           // max_p |mu_organic[p]|
+    const float *G32;          // [nsub][K+1][128] fp32 tiles of log2(e)*Gamma (row K = log2(e)*mu_organic)
+    int nsub;                  // number of 128-product tiles
     int change_omega_for_bandits;
     uint64_t seed;
 };

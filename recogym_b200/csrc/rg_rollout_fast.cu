@@ -1,10 +1,623 @@
-// rg_rollout_fast.cu -- RG_MATH_FAST rollout (placeholder: routes to the exact kernel until the
-// CTA-batched fp32 kernel lands).
+// rg_rollout_fast.cu -- RG_MATH_FAST: the CTA-batched fused rollout kernel.
+//
+// A persistent CTA owns TU=128 user slots.  Work proceeds in rounds; at the start of a round every
+// live slot is in the ORGANIC state, so the expensive part of the model -- the product-view draw
+// from Categorical(softmax(Gamma omega + mu)) (reco_env_v1.py:119-128) -- is one dense
+// [128 users] x [P products] x [K] fp32 contraction per round:
+//
+//   pass 1  Gamma tiles (128 products x (K+1) floats, pre-scaled by log2 e, mu as row K) stream
+//           L2 -> shared memory through a ring of TMA bulk copies (cp.async.bulk + mbarrier);
+//           each thread owns an 8-user x 8-product register tile, 64 FFMA per 4 LDS.128; the
+//           epilogue turns logits into masses with a bare ex2 (shifted by a per-user upper bound of
+//           the logits, so no running maximum is needed) and keeps per-user partial sums per
+//           "record tile" in shared memory.
+//   pass 2  one warp per user: total mass, tau = u * Z, locate the record tile, recompute only that
+//           tile in natural product order with a warp scan -> candidate index + its CDF margins.
+//   filter  the margins are compared with a rigorous bound of the fp32 error (DESIGN.md "fast
+//           sampler"); a draw that could be affected is re-sampled in binary64 by the whole CTA.
+//           Every discrete result therefore equals the all-binary64 sampler (RG_MATH_EXACT).
+//   advance one thread per slot: transition, omega drift, then the whole run of cheap bandit events
+//           (policy action, click ~ Bernoulli(ff(beta_a.omega + mu_a)), transition) until the user is
+//           organic again or stops; stopped users are written out and the slot claims the next
+//           user id from a global queue.
+//
+// All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
+#include "rg_device.cuh"
 #include "rg_host.h"
+
 namespace rg {
+namespace fast {
+
+constexpr int TU = 128;     // user slots per CTA
+constexpr int SUB = 128;    // products per shared-memory tile
+constexpr int NT = 256;     // threads per CTA
+constexpr int CHUNK = 256;  // products per partial sum of the cooperative binary64 sampler
+constexpr int kMaxStages = 4;
+
+struct Layout {  // byte offsets into dynamic shared memory
+    int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
+        amb_list, misc, om32, tilesum, gtile, total;
+};
+
+struct Params {
+    EnvDev env;
+    PolicyDev pol;
+    long long user_begin, n_organic_users, n_total;
+    RolloutOutDev out;
+    unsigned long long *queue;
+    int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
+    Layout L;
+};
+
+__host__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+__host__ inline void make_layout(Params &p) {
+    const int K = p.env.K, K1 = K + 1;
+    Layout &L = p.L;
+    int o = 0;
+    L.mbar = o; o += 8 * kMaxStages;
+    L.om64 = o; o += 8 * TU * p.kp;
+    L.csum = o; o += 8 * p.ncs;
+    L.user = o; o += 8 * TU;
+    L.hash = o; o += 8 * TU;
+    L.t = o; o += 4 * TU;
+    L.state = o; o += 4 * TU;
+    L.last_view = o; o += 4 * TU;
+    L.n_org = o; o += 4 * TU;
+    L.n_ban = o; o += 4 * TU;
+    L.n_clk = o; o += 4 * TU;
+    L.view = o; o += 4 * TU;
+    L.live = o; o += 4 * TU;
+    L.pos2slot = o; o += 4 * TU;
+    L.shift = o; o += 4 * TU;
+    L.eps = o; o += 4 * TU;
+    L.amb_list = o; o += 4 * TU;
+    L.misc = o; o += 64;
+    o = align_up(o, 16);
+    L.om32 = o; o += 4 * K1 * TU;
+    L.tilesum = o; o += 4 * TU * p.nrec_pad;
+    o = align_up(o, 128);
+    L.gtile = o; o += 4 * p.nstage * K1 * SUB;
+    L.total = o;
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- scalar (one thread per user) pieces --------------------------------------------------------
+// omega init / drift by ONE thread: same operation sequence as warp_omega_update.
+__device__ __forceinline__ void thread_omega_update(double *omega, int K, double scale, bool init, uint64_t seed,
+                                                    uint64_t user, uint32_t t) {
+    for (int j = 0; 2 * j < K; ++j) {
+        const u32x4 w = draw(seed, user, t, SLOT_NORMAL + (uint32_t)j);
+        const double z0 = normal_from_words(w.x, w.y);
+        const double b0 = init ? 0.0 : omega[2 * j];
+        omega[2 * j] = b0 + scale * z0;
+        if (2 * j + 1 < K) {
+            const double z1 = normal_from_words(w.z, w.w);
+            const double b1 = init ? 0.0 : omega[2 * j + 1];
+            omega[2 * j + 1] = b1 + scale * z1;
+        }
+    }
+}
+
+// Binary64 view sample for one user by the whole CTA (fallback of the filter; rare).
+// Same mathematics as warp_sample_view_exact; partial sums per CHUNK products in `csum`.
+__device__ int block_sample_view_exact(const EnvDev &env, const double *omega, double *csum, int *result,
+                                       double u, int tid, unsigned &ambig) {
+    const int K = env.K, P = env.P, Ppad = env.Ppad;
+    const int lane = tid & 31, warp = tid >> 5;
+    double n2 = 0.0;
+    for (int k = 0; k < K; ++k) n2 = fma(omega[k], omega[k], n2);
+    const double B = sqrt(n2) * env.gmax + env.mumax;
+    auto mass = [&](int j) -> double {
+        if (j >= P) return 0.0;
+        const double *g = env.GammaT + j;
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
+        return exp64(acc + __ldg(env.mu_o + j) - B);
+    };
+    const int nch = (Ppad + CHUNK - 1) / CHUNK;
+    for (int c = warp; c < nch; c += NT / 32) {
+        double part = 0.0;
+        for (int g = 0; g < CHUNK / 32; ++g) part += mass(c * CHUNK + g * 32 + lane);
+        const double tot = warp_sum(part);
+        if (lane == 0) csum[c] = tot;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double Z = 0.0;
+        for (int c = 0; c < nch; ++c) Z += csum[c];
+        const double tau = u * Z;
+        double cum = 0.0;
+        int c = 0;
+        for (; c < nch - 1; ++c) {
+            const double nx = cum + csum[c];
+            if (nx > tau) break;
+            cum = nx;
+        }
+        int found = -1;
+        double lower = 0.0, upper = 0.0;
+        const int end = min((c + 1) * CHUNK, Ppad);
+        for (int base = c * CHUNK; base < end; base += 32) {
+            double x = mass(base + lane);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            const double pre = cum + x;
+            const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (base + lane < P));
+            if (m) {
+                const int fl = __ffs(m) - 1;
+                found = base + fl;
+                upper = __shfl_sync(0xffffffffu, pre, fl);
+                const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                lower = fl > 0 ? below : cum;
+                break;
+            }
+            cum = __shfl_sync(0xffffffffu, pre, 31);
+        }
+        bool amb = false;
+        if (found < 0) {
+            found = min(end, P) - 1;
+            amb = true;
+        } else {
+            const double tol = 1e-11 * Z;
+            amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
+        }
+        if (lane == 0) {
+            *result = found;
+            if (amb) ambig += 1;
+        }
+    }
+    __syncthreads();
+    return *result;
+}
+
+__global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const EnvDev &env = p.env;
+    const Layout &L = p.L;
+    const int K = env.K, K1 = K + 1, KP = p.kp, P = env.P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    uint64_t *mbar = (uint64_t *)(smem + L.mbar);
+    double *om64 = (double *)(smem + L.om64);
+    double *csum = (double *)(smem + L.csum);
+    uint64_t *s_user = (uint64_t *)(smem + L.user);
+    uint64_t *s_hash = (uint64_t *)(smem + L.hash);
+    uint32_t *s_t = (uint32_t *)(smem + L.t);
+    int *s_state = (int *)(smem + L.state);
+    int *s_last_view = (int *)(smem + L.last_view);
+    int *s_n_org = (int *)(smem + L.n_org);
+    int *s_n_ban = (int *)(smem + L.n_ban);
+    int *s_n_clk = (int *)(smem + L.n_clk);
+    int *s_view = (int *)(smem + L.view);
+    int *s_live = (int *)(smem + L.live);
+    int *pos2slot = (int *)(smem + L.pos2slot);
+    float *s_shift = (float *)(smem + L.shift);
+    float *s_eps = (float *)(smem + L.eps);
+    int *amb_list = (int *)(smem + L.amb_list);
+    int *misc = (int *)(smem + L.misc);  // [0] nlive, [1] amb_count, [2] exact result
+    float *om32 = (float *)(smem + L.om32);
+    float *tilesum = (float *)(smem + L.tilesum);
+    float *gtile = (float *)(smem + L.gtile);
+
+    const unsigned tile_bytes = (unsigned)(4 * K1 * SUB);
+    const int nsub = env.nsub, nstage = p.nstage;
+
+    // ---- set-up: barriers, first claims, first tile loads
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+        fence_barrier_init();
+        misc[1] = 0;
+    }
+    unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
+    unsigned long long n_fallback = 0;
+    unsigned ambig64 = 0;
+
+    auto claim = [&](int slot) -> bool {  // next user id from the global queue -> reset()
+        const unsigned long long q = atomicAdd(p.queue, 1ull);
+        if (q >= (unsigned long long)p.n_total) {
+            s_live[slot] = 0;
+            return false;
+        }
+        const uint64_t user = (uint64_t)(p.user_begin + (long long)q);
+        s_user[slot] = user;
+        s_hash[slot] = kHashInit;
+        s_t[slot] = 0u;
+        s_state[slot] = RG_ORGANIC;
+        s_last_view[slot] = -1;
+        s_n_org[slot] = 0; s_n_ban[slot] = 0; s_n_clk[slot] = 0;
+        s_live[slot] = 1;
+        thread_omega_update(om64 + (size_t)slot * KP, K, env.sigma0, true, env.seed, user, 0u);  // reco_env_v1.py:80-82
+        return true;
+    };
+    if (tid < TU) claim(tid);
+    __syncthreads();
+
+    unsigned seq_use = 0;  // sequence number of the next tile to consume (same in every thread)
+    auto issue_load = [&](unsigned seq) {  // thread 0 only: tile (seq % nsub) -> ring stage (seq % nstage)
+        const int stage = (int)(seq % (unsigned)nstage);
+        const int sub = (int)(seq % (unsigned)nsub);
+        mbar_expect_tx(&mbar[stage], tile_bytes);
+        tma_bulk_g2s(gtile + (size_t)stage * K1 * SUB, env.G32 + (size_t)sub * K1 * SUB, tile_bytes, &mbar[stage]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < nstage - 1; ++s) issue_load((unsigned)s);
+
+    const int tx = tid & 15, ty = tid >> 4;
+
+    for (;;) {
+        // ---- A: compact the live slots into positions 0..nlive-1 (no data moves: pos2slot indirection)
+        if (warp == 0) {
+            int base = 0;
+            for (int c = 0; c < TU / 32; ++c) {
+                const int slot = c * 32 + lane;
+                const bool lv = s_live[slot] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, lv);
+                if (lv) pos2slot[base + __popc(m & ((1u << lane) - 1u))] = slot;
+                base += __popc(m);
+            }
+            if (lane == 0) misc[0] = base;
+        }
+        __syncthreads();
+        const int nlive = misc[0];
+        if (nlive == 0) break;
+
+        // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
+        // error bound.  Dead positions get zeros.
+        for (int idx = tid; idx < K1 * TU; idx += NT) {
+            const int k = idx / TU, i = idx - k * TU;
+            float v = 0.f;
+            if (i < nlive) v = (k < K) ? (float)om64[(size_t)pos2slot[i] * KP + k] : 1.f;
+            om32[idx] = v;
+        }
+        if (tid < TU) {
+            float sh = 0.f, ep = 1.f;
+            if (tid < nlive) {
+                const double *om = om64 + (size_t)pos2slot[tid] * KP;
+                double n2 = 0.0;
+                for (int k = 0; k < K; ++k) n2 = fma(om[k], om[k], n2);
+                const double nrm = sqrt(n2);
+                const double kLog2e = 1.4426950408889634074;
+                const double bl2 = (nrm * env.gmax + env.mumax) * kLog2e;    // >= every log2-logit
+                const double shift = bl2 - 100.0;                              // top mass <= 2^100
+                const double aub = (nrm * env.gmax + env.muabsmax) * kLog2e;  // >= sum_k |G'_pk w_k| + |mu'_p|
+                const double u24 = 5.9604644775390625e-08;                    // 2^-24
+                // log2-logit error: input rounding + K+1 fma roundings + the shift subtraction
+                const double dl2 = (K + 4) * u24 * aub + u24 * (aub + fabs(shift)) + u24 * fabs(shift);
+                // relative mass error: exp of that, ex2.approx (2^-21 covers its 2 ulp), fp32 partial sums of pass 1
+                const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 +
+                                     (8.0 * p.rec_sub + 6.0) * u24;
+                sh = (float)shift;
+                ep = (float)(2.0 * delta * 1.05 + 1e-7);
+            }
+            s_shift[tid] = sh;
+            s_eps[tid] = ep;
+        }
+        __syncthreads();
+
+        // ---- B: pass 1, dense contraction + exponentials + per-record-tile partial sums
+        {
+            const bool warp_active = warp * 16 < nlive;
+            float sh[8], part[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { sh[u] = s_shift[ty * 8 + u]; part[u] = 0.f; }
+            int rec = 0, sub_in_rec = 0;
+            for (int sub = 0; sub < nsub; ++sub) {
+                const unsigned seq = seq_use + (unsigned)sub;
+                const int stage = (int)(seq % (unsigned)nstage);
+                mbar_wait(&mbar[stage], (seq / (unsigned)nstage) & 1u);
+                if (warp_active) {
+                    const float *gt = gtile + (size_t)stage * K1 * SUB;
+                    float acc[8][8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[u][j] = 0.f;
+#pragma unroll 3
+                    for (int k = 0; k < K1; ++k) {
+                        const float4 w0 = *reinterpret_cast<const float4 *>(om32 + k * TU + ty * 8);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(om32 + k * TU + ty * 8 + 4);
+                        const float4 g0 = *reinterpret_cast<const float4 *>(gt + k * SUB + tx * 4);
+                        const float4 g1 = *reinterpret_cast<const float4 *>(gt + k * SUB + 64 + tx * 4);
+                        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(w[u], g[j], acc[u][j]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) part[u] += ex2_approx(acc[u][j] - sh[u]);
+                }
+                if (++sub_in_rec == p.rec_sub || sub == nsub - 1) {
+                    if (warp_active) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            float v = part[u];
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            if (tx == 0) tilesum[(size_t)(ty * 8 + u) * p.nrec_pad + rec] = v;
+                            part[u] = 0.f;
+                        }
+                    }
+                    ++rec;
+                    sub_in_rec = 0;
+                }
+                __syncthreads();  // everyone is done with this ring stage
+                if (tid == 0) issue_load(seq + (unsigned)nstage - 1u);
+            }
+            seq_use += (unsigned)nsub;
+        }
+
+        // ---- C: pass 2, one warp per live user: total mass, locate, recompute one record tile, margins
+        for (int i = warp; i < nlive; i += NT / 32) {
+            const int slot = pos2slot[i];
+            const uint64_t user = s_user[slot];
+            const u32x4 w = draw(env.seed, user, s_t[slot], SLOT_EVENT);
+            const double u = uniform53(w.x, w.y);
+            const float *ts = tilesum + (size_t)i * p.nrec_pad;
+            double zl = 0.0;
+            for (int r = lane; r < p.nrec; r += 32) zl += (double)ts[r];
+            const double Z = warp_sum(zl);
+            const double tau = u * Z;
+            double cum = 0.0;
+            int rsel = -1;
+            for (int r0 = 0; r0 < p.nrec && rsel < 0; r0 += 32) {
+                const int r = r0 + lane;
+                double x = r < p.nrec ? (double)ts[r] : 0.0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= d) x += y;
+                }
+                const double pre = cum + x;
+                const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (r < p.nrec));
+                if (m) {
+                    const int fl = __ffs(m) - 1;
+                    rsel = r0 + fl;
+                    const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                    cum = fl > 0 ? below : cum;
+                } else {
+                    cum = __shfl_sync(0xffffffffu, pre, 31);
+                }
+            }
+            int found = -1;
+            bool amb = false;
+            double lower = 0.0, upper = 0.0;
+            if (rsel < 0) {
+                amb = true;
+            } else {
+                const float shf = s_shift[i];
+                const int p0 = rsel * p.rec_sub * SUB;
+                const int p1 = min(p0 + p.rec_sub * SUB, nsub * SUB);
+                for (int base = p0; base < p1; base += 32) {
+                    const int pj = base + lane;
+                    const float *g = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & 127);
+                    float acc = 0.f;
+                    for (int k = 0; k < K1; ++k) acc = fmaf(om32[k * TU + i], __ldg(g + k * SUB), acc);
+                    double x = (double)ex2_approx(acc - shf);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= d) x += y;
+                    }
+                    const double pre = cum + x;
+                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        found = base + fl;
+                        upper = __shfl_sync(0xffffffffu, pre, fl);
+                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                        lower = fl > 0 ? below : cum;
+                        break;
+                    }
+                    cum = __shfl_sync(0xffffffffu, pre, 31);
+                }
+                if (found < 0) {
+                    amb = true;
+                } else {
+                    const double tol = (double)s_eps[i] * Z;
+                    amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
+                }
+            }
+            if (lane == 0) {
+                s_view[slot] = found;
+                if (amb) amb_list[atomicAdd(&misc[1], 1)] = i;
+            }
+        }
+        __syncthreads();
+
+        // ---- C2: binary64 re-sampling of the draws the filter could not certify
+        {
+            const int namb = misc[1];
+            for (int a = 0; a < namb; ++a) {
+                const int slot = pos2slot[amb_list[a]];
+                const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
+                const int v = block_sample_view_exact(env, om64 + (size_t)slot * KP, csum, &misc[2],
+                                                      uniform53(w.x, w.y), tid, ambig64);
+                if (tid == 0) s_view[slot] = v;
+            }
+            if (tid == 0) {
+                n_fallback += (unsigned long long)namb;
+                misc[1] = 0;
+            }
+            __syncthreads();
+        }
+
+        // ---- D: one thread per slot: finish the organic event, run the bandit events, recycle the slot
+        if (tid < TU && s_live[tid]) {
+            const int slot = tid;
+            double *om = om64 + (size_t)slot * KP;
+            uint64_t user = s_user[slot];
+            uint64_t h = s_hash[slot];
+            uint32_t t = s_t[slot];
+            int last_view, n_org = s_n_org[slot], n_ban = s_n_ban[slot], n_clk = s_n_clk[slot];
+            const long long idx = (long long)user - p.user_begin;
+            const bool organic_only = idx < p.n_organic_users;
+            {   // abstract.py:110-119: the view was drawn above; now update_state
+                const int v = s_view[slot];
+                last_view = v;
+                n_org += 1;
+                h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
+                if (p.out.view_hist) atomicAdd(p.out.view_hist + v, 1ull);
+            }
+            const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
+            int st = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
+            t += 1;
+            if (env.change_omega_for_bandits || st == RG_ORGANIC)
+                thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+            while (st == RG_BANDIT && !organic_only) {  // abstract.py:174-181
+                int a;
+                if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
+                else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
+                const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
+                const int c = click_from_uniform(ctr_of_action(env, om, a), uniform53(wb.x, wb.y));
+                st = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
+                t += 1;
+                if (env.change_omega_for_bandits || st == RG_ORGANIC)
+                    thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+                if (c) st = RG_ORGANIC;
+                n_ban += 1;
+                n_clk += c;
+                h = hash_fold(h, ((uint64_t)(uint32_t)a << 2) | ((uint64_t)c << 1) | 1u);
+                if (p.out.action_hist) atomicAdd(p.out.action_hist + a, 1ull);
+                if (c && p.out.click_hist) atomicAdd(p.out.click_hist + a, 1ull);
+            }
+            if (st != RG_ORGANIC) {  // episode over: write the user out, claim the next one
+                h = hash_fold(h, ((uint64_t)t << 2) | 3u);
+                if (p.out.n_events) p.out.n_events[idx] = (int32_t)t;
+                if (p.out.n_organic) p.out.n_organic[idx] = n_org;
+                if (p.out.n_bandit) p.out.n_bandit[idx] = n_ban;
+                if (p.out.n_clicks) p.out.n_clicks[idx] = n_clk;
+                if (p.out.last_view) p.out.last_view[idx] = last_view;
+                if (p.out.hash) p.out.hash[idx] = h;
+                if (p.out.omega)
+                    for (int k = 0; k < K; ++k) p.out.omega[(size_t)idx * K + k] = om[k];
+                tot_users += 1; tot_events += t; tot_org += n_org; tot_ban += n_ban; tot_clk += n_clk;
+                tot_ph += organic_only ? 0 : 1;
+                claim(slot);
+            } else {
+                s_hash[slot] = h; s_t[slot] = t; s_last_view[slot] = last_view;
+                s_n_org[slot] = n_org; s_n_ban[slot] = n_ban; s_n_clk[slot] = n_clk;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- drain the prefetched tiles (a CTA must not exit with bulk copies in flight)
+    for (int s = 0; s < nstage - 1; ++s) {
+        const unsigned seq = seq_use + (unsigned)s;
+        mbar_wait(&mbar[seq % (unsigned)nstage], (seq / (unsigned)nstage) & 1u);
+    }
+
+    // ---- totals: warp reduction, one atomic per counter per warp
+    if (p.out.totals) {
+        unsigned long long v[8] = {tot_users, tot_events, tot_org, tot_ban, tot_clk, tot_ph, n_fallback,
+                                   (unsigned long long)ambig64};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            unsigned long long x = v[c];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+            if (lane == 0 && x) atomicAdd(p.out.totals + c, x);
+        }
+    }
+}
+
+}  // namespace fast
+
 cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
                                 long long n_organic_users, long long n_total, const RolloutOutDev &out,
                                 cudaStream_t stream) {
-    return launch_rollout_exact(e, pol, user_begin, n_organic_users, n_total, out, stream);
+    using namespace fast;
+    if (n_total <= 0) return cudaSuccess;
+    Params p;
+    p.env = e.dev;
+    p.pol = pol;
+    p.user_begin = user_begin;
+    p.n_organic_users = n_organic_users;
+    p.n_total = n_total;
+    p.out = out;
+    const int K1 = e.dev.K + 1;
+    p.kp = e.dev.K | 1;  // odd row stride of the binary64 omega rows: conflict-free per-slot access
+    p.ncs = (e.dev.Ppad + CHUNK - 1) / CHUNK + 1;
+    const int nsub = e.dev.nsub;
+    // record tiles: at most 64 partial sums per user, at least 2 sub-tiles each
+    int rec_sub = 2;
+    while ((nsub + rec_sub - 1) / rec_sub > 64) ++rec_sub;
+    if (rec_sub > nsub) rec_sub = nsub;
+    p.rec_sub = rec_sub;
+    p.nrec = (nsub + rec_sub - 1) / rec_sub;
+    p.nrec_pad = p.nrec | 1;
+    // ring depth: as deep as shared memory allows (2 CTAs/SM when possible)
+    int best_stage = 0;
+    for (int nstage = 3; nstage >= 2 && !best_stage; --nstage) {
+        p.nstage = nstage;
+        make_layout(p);
+        if (p.L.total <= 110 * 1024) best_stage = nstage;
+    }
+    if (!best_stage) {
+        for (int nstage = 3; nstage >= 2 && !best_stage; --nstage) {
+            p.nstage = nstage;
+            make_layout(p);
+            if (p.L.total <= 227 * 1024) best_stage = nstage;
+        }
+    }
+    if (!best_stage) return cudaErrorInvalidConfiguration;  // K/P too large for the CTA-batched kernel
+    p.nstage = best_stage;
+    make_layout(p);
+    (void)K1;
+    static thread_local unsigned launch_seq = 0;
+    p.queue = e.diag + 4 + (launch_seq++ % 60u);
+    cudaError_t ce = cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), stream);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaFuncSetAttribute(rollout_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+    if (ce != cudaSuccess) return ce;
+    int ctas_per_sm = p.L.total <= 110 * 1024 ? 2 : 1;
+    long long blocks = (n_total + TU - 1) / TU;
+    const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
+    if (blocks > max_blocks) blocks = max_blocks;
+    rollout_cta_kernel<<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+    return cudaGetLastError();
 }
+
 }  // namespace rg

@@ -220,8 +220,8 @@ def test_batch_protocol_equals_oracle(oracle):
     """rg_batch_reset/step/continue == the oracle's reset/step, sessions included (tiny sess_cap
     forces the continuation path)."""
     from recogym_b200 import BatchState
-    oe, de = both_envs(40, 5, 21)
-    N = 700
+    oe, de = both_envs(40, 5, 21, prob_leave_organic=0.06)   # short episodes: the host loop is per step
+    N = 300
     uids = np.arange(3, 3 + N)
     st, off, sv = oracle.batch_reset(oe, uids)
     bs = BatchState(de, uids, sess_cap=3)
@@ -241,7 +241,7 @@ def test_batch_protocol_equals_oracle(oracle):
 
     bs.reset()
     views, h = gather(True)
-    for it in range(400):
+    for it in range(3000):
         for i in range(N):
             assert views[i] == sv[off[i]:off[i + 1]].tolist(), (it, i)
         assert np.array_equal(h["state"], st["state"]) and np.array_equal(h["t"], st["t"])
