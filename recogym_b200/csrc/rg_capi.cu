@@ -159,8 +159,8 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT32, GT32);
     if (ce == cudaSuccess) ce = upload(&e.d_mu_o32, mu32);
     if (ce == cudaSuccess) ce = upload(&e.d_Gamma32, G32);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.diag, sizeof(unsigned long long) * 4);
-    if (ce == cudaSuccess) ce = cudaMemset(e.diag, 0, sizeof(unsigned long long) * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.diag, sizeof(unsigned long long) * 64);
+    if (ce == cudaSuccess) ce = cudaMemset(e.diag, 0, sizeof(unsigned long long) * 64);
     if (ce != cudaSuccess) {
         free_env(e);
         delete env;

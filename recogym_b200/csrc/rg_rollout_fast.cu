@@ -33,10 +33,11 @@ constexpr int SUB = 128;    // products per shared-memory tile
 constexpr int NT = 256;     // threads per CTA
 constexpr int CHUNK = 256;  // products per partial sum of the cooperative binary64 sampler
 constexpr int kMaxStages = 4;
+constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampler
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, misc, om32, tilesum, gtile, total;
+        amb_list, fb_slot, fb_u, pend, pend_list, misc, om32, tilesum, gtile, total;
 };
 
 struct Params {
@@ -57,7 +58,8 @@ __host__ inline void make_layout(Params &p) {
     int o = 0;
     L.mbar = o; o += 8 * kMaxStages;
     L.om64 = o; o += 8 * TU * p.kp;
-    L.csum = o; o += 8 * p.ncs;
+    L.csum = o; o += 8 * p.ncs * FB;
+    L.fb_u = o; o += 8 * FB;
     L.user = o; o += 8 * TU;
     L.hash = o; o += 8 * TU;
     L.t = o; o += 4 * TU;
@@ -72,6 +74,9 @@ __host__ inline void make_layout(Params &p) {
     L.shift = o; o += 4 * TU;
     L.eps = o; o += 4 * TU;
     L.amb_list = o; o += 4 * TU;
+    L.fb_slot = o; o += 4 * FB;
+    L.pend = o; o += 4 * TU;
+    L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
     o = align_up(o, 16);
     L.om32 = o; o += 4 * K1 * TU;
@@ -132,45 +137,117 @@ __device__ __forceinline__ void thread_omega_update(double *omega, int K, double
     }
 }
 
-// Binary64 view sample for one user by the whole CTA (fallback of the filter; rare).
-// Same mathematics as warp_sample_view_exact; partial sums per CHUNK products in `csum`.
-__device__ int block_sample_view_exact(const EnvDev &env, const double *omega, double *csum, int *result,
-                                       double u, int tid, unsigned &ambig) {
+// Binary64 view samples for up to FB users at once by the whole CTA (fallback of the filter).
+// Same mathematics as warp_sample_view_exact.  Every Gamma column is loaded once from L2 and used
+// for all users of the batch (the single-user version was L2-bandwidth bound: 1.6 MB per draw);
+// partial sums per CHUNK products in csum[f][c]; the inverse CDF of user f is then located by warp f.
+template <int NB>
+__device__ __forceinline__ void exact_batch_partial_sums(const EnvDev &env, const double *om64, int KP, double *csum,
+                                                         int ncs, const int *slots, int nb, const double *B,
+                                                         int lane, int warp) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
-    const int lane = tid & 31, warp = tid >> 5;
-    double n2 = 0.0;
-    for (int k = 0; k < K; ++k) n2 = fma(omega[k], omega[k], n2);
-    const double B = sqrt(n2) * env.gmax + env.mumax;
-    auto mass = [&](int j) -> double {
-        if (j >= P) return 0.0;
-        const double *g = env.GammaT + j;
-        double acc = 0.0;
-        for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
-        return exp64(acc + __ldg(env.mu_o + j) - B);
-    };
+    const double *om[NB];
+#pragma unroll
+    for (int f = 0; f < NB; ++f) om[f] = om64 + (size_t)slots[f < nb ? f : nb - 1] * KP;
     const int nch = (Ppad + CHUNK - 1) / CHUNK;
     for (int c = warp; c < nch; c += NT / 32) {
-        double part = 0.0;
-        for (int g = 0; g < CHUNK / 32; ++g) part += mass(c * CHUNK + g * 32 + lane);
-        const double tot = warp_sum(part);
-        if (lane == 0) csum[c] = tot;
+        double part[NB];
+#pragma unroll
+        for (int f = 0; f < NB; ++f) part[f] = 0.0;
+        for (int g = 0; g < CHUNK / 32; ++g) {
+            const int j = c * CHUNK + g * 32 + lane;
+            if (j < P) {
+                double acc[NB];
+#pragma unroll
+                for (int f = 0; f < NB; ++f) acc[f] = 0.0;
+                const double *gp = env.GammaT + j;
+                for (int k = 0; k < K; ++k) {
+                    const double gk = __ldg(gp + (size_t)k * Ppad);
+#pragma unroll
+                    for (int f = 0; f < NB; ++f) acc[f] = fma(gk, om[f][k], acc[f]);
+                }
+                const double mu = __ldg(env.mu_o + j);
+#pragma unroll
+                for (int f = 0; f < NB; ++f)
+                    if (f < nb) part[f] += exp64(acc[f] + mu - B[f]);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NB; ++f) {
+            const double tot = warp_sum(part[f]);
+            if (lane == 0 && f < nb) csum[(size_t)f * ncs + c] = tot;
+        }
     }
+}
+
+__device__ __noinline__ void block_sample_views_exact(const EnvDev &env, const double *om64, int KP, double *csum,
+                                                      int ncs, const int *slots, const double *us, int nb,
+                                                      int *s_view, int tid, unsigned &ambig) {
+    const int K = env.K, P = env.P, Ppad = env.Ppad;
+    const int lane = tid & 31, warp = tid >> 5;
+    double B[FB];
+#pragma unroll
+    for (int f = 0; f < FB; ++f) {
+        const double *om = om64 + (size_t)slots[f < nb ? f : nb - 1] * KP;
+        double n2 = 0.0;
+        for (int k = 0; k < K; ++k) n2 = fma(om[k], om[k], n2);
+        B[f] = sqrt(n2) * env.gmax + env.mumax;
+    }
+    if (nb <= 1) exact_batch_partial_sums<1>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
+    else if (nb <= 2) exact_batch_partial_sums<2>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
+    else if (nb <= 4) exact_batch_partial_sums<4>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
+    else exact_batch_partial_sums<8>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
     __syncthreads();
-    if (warp == 0) {
-        double Z = 0.0;
-        for (int c = 0; c < nch; ++c) Z += csum[c];
-        const double tau = u * Z;
+    if (warp < nb) {
+        const int f = warp;
+        const double *omega = om64 + (size_t)slots[f] * KP;
+        const double *cs = csum + (size_t)f * ncs;
+        const double Bf = B[f < FB ? f : 0];
+        auto mass = [&](int j) -> double {
+            if (j >= P) return 0.0;
+            const double *g = env.GammaT + j;
+            double acc = 0.0;
+            for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
+            return exp64(acc + __ldg(env.mu_o + j) - Bf);
+        };
+        const int nch = (Ppad + CHUNK - 1) / CHUNK;
+        double zl = 0.0;
+        for (int c = lane; c < nch; c += 32) zl += cs[c];
+        const double Z = warp_sum(zl);
+        const double tau = us[f] * Z;
+        // chunk containing tau: 32 chunks per step, inclusive scan over lanes
         double cum = 0.0;
-        int c = 0;
-        for (; c < nch - 1; ++c) {
-            const double nx = cum + csum[c];
-            if (nx > tau) break;
-            cum = nx;
+        int csel = nch - 1;
+        bool have = false;
+        for (int c0 = 0; c0 < nch && !have; c0 += 32) {
+            const int c = c0 + lane;
+            double x = c < nch ? cs[c] : 0.0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            const double pre = cum + x;
+            const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (c < nch));
+            if (m) {
+                const int fl = __ffs(m) - 1;
+                csel = c0 + fl;
+                const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                cum = fl > 0 ? below : cum;
+                have = true;
+            } else {
+                cum = __shfl_sync(0xffffffffu, pre, 31);
+            }
+        }
+        if (!have) {  // tau >= every prefix (rounding-level): walk the last chunk from its start
+            double c2 = 0.0;
+            for (int c = 0; c < nch - 1; ++c) c2 += cs[c];
+            cum = c2;
         }
         int found = -1;
         double lower = 0.0, upper = 0.0;
-        const int end = min((c + 1) * CHUNK, Ppad);
-        for (int base = c * CHUNK; base < end; base += 32) {
+        const int end = min((csel + 1) * CHUNK, Ppad);
+        for (int base = csel * CHUNK; base < end; base += 32) {
             double x = mass(base + lane);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -198,12 +275,11 @@ __device__ int block_sample_view_exact(const EnvDev &env, const double *omega, d
             amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
         }
         if (lane == 0) {
-            *result = found;
+            s_view[slots[f]] = found;
             if (amb) ambig += 1;
         }
     }
     __syncthreads();
-    return *result;
 }
 
 __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
@@ -230,6 +306,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *s_shift = (float *)(smem + L.shift);
     float *s_eps = (float *)(smem + L.eps);
     int *amb_list = (int *)(smem + L.amb_list);
+    int *fb_slot = (int *)(smem + L.fb_slot);
+    double *fb_u = (double *)(smem + L.fb_u);
+    int *s_pend = (int *)(smem + L.pend);      // 0 none, 1 drift into s_t, 2 init of a fresh user
+    int *pend_list = (int *)(smem + L.pend_list);
     int *misc = (int *)(smem + L.misc);  // [0] nlive, [1] amb_count, [2] exact result
     float *om32 = (float *)(smem + L.om32);
     float *tilesum = (float *)(smem + L.tilesum);
@@ -262,10 +342,43 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         s_last_view[slot] = -1;
         s_n_org[slot] = 0; s_n_ban[slot] = 0; s_n_clk[slot] = 0;
         s_live[slot] = 1;
-        thread_omega_update(om64 + (size_t)slot * KP, K, env.sigma0, true, env.seed, user, 0u);  // reco_env_v1.py:80-82
+        s_pend[slot] = 2;  // omega = sigma0 * z(user, 0) (reco_env_v1.py:80-82), done by omega_phase()
         return true;
     };
-    if (tid < TU) claim(tid);
+    // Pending omega updates of all slots, spread over the whole CTA: task = (slot, normal pair j).
+    auto omega_phase = [&]() {
+        if (warp == 0) {
+            int base = 0;
+            for (int c = 0; c < TU / 32; ++c) {
+                const int slot = c * 32 + lane;
+                const bool pd = s_pend[slot] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, pd);
+                if (pd) pend_list[base + __popc(m & ((1u << lane) - 1u))] = slot;
+                base += __popc(m);
+            }
+            if (lane == 0) misc[3] = base;
+        }
+        __syncthreads();
+        const int npend = misc[3], npairs = (K + 1) / 2;
+        for (int task = tid; task < npend * npairs; task += NT) {
+            const int slot = pend_list[task / npairs], j = task - (task / npairs) * npairs;
+            const bool init = s_pend[slot] == 2;
+            double *om = om64 + (size_t)slot * KP;
+            const double scale = init ? env.sigma0 : env.sigma * 1.0;
+            const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_NORMAL + (uint32_t)j);
+            const double z0 = normal_from_words(w.x, w.y);
+            om[2 * j] = (init ? 0.0 : om[2 * j]) + scale * z0;
+            if (2 * j + 1 < K) {
+                const double z1 = normal_from_words(w.z, w.w);
+                om[2 * j + 1] = (init ? 0.0 : om[2 * j + 1]) + scale * z1;
+            }
+        }
+        __syncthreads();
+        if (tid < TU) s_pend[tid] = 0;
+    };
+    if (tid < TU) { s_pend[tid] = 0; claim(tid); }
+    __syncthreads();
+    omega_phase();
     __syncthreads();
 
     unsigned seq_use = 0;  // sequence number of the next tile to consume (same in every thread)
@@ -466,15 +579,19 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
 
-        // ---- C2: binary64 re-sampling of the draws the filter could not certify
+        // ---- C2: binary64 re-sampling of the draws the filter could not certify, FB users per sweep of Gamma
         {
             const int namb = misc[1];
-            for (int a = 0; a < namb; ++a) {
-                const int slot = pos2slot[amb_list[a]];
-                const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
-                const int v = block_sample_view_exact(env, om64 + (size_t)slot * KP, csum, &misc[2],
-                                                      uniform53(w.x, w.y), tid, ambig64);
-                if (tid == 0) s_view[slot] = v;
+            for (int b0 = 0; b0 < namb; b0 += FB) {
+                const int nb = min(FB, namb - b0);
+                if (tid < nb) {
+                    const int slot = pos2slot[amb_list[b0 + tid]];
+                    const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
+                    fb_slot[tid] = slot;
+                    fb_u[tid] = uniform53(w.x, w.y);
+                }
+                __syncthreads();
+                block_sample_views_exact(env, om64, KP, csum, p.ncs, fb_slot, fb_u, nb, s_view, tid, ambig64);
             }
             if (tid == 0) {
                 n_fallback += (unsigned long long)namb;
@@ -483,11 +600,13 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             __syncthreads();
         }
 
-        // ---- D: one thread per slot: finish the organic event, run the bandit events, recycle the slot
+        // ---- D: one thread per slot: finish the organic event, run the bandit events, recycle the slot.
+        // omega updates that precede an ORGANIC event are deferred to omega_phase() (whole CTA); the ones
+        // that precede a bandit event (change_omega_for_bandits only) are done inline.
         if (tid < TU && s_live[tid]) {
             const int slot = tid;
             double *om = om64 + (size_t)slot * KP;
-            uint64_t user = s_user[slot];
+            const uint64_t user = s_user[slot];
             uint64_t h = s_hash[slot];
             uint32_t t = s_t[slot];
             int last_view, n_org = s_n_org[slot], n_ban = s_n_ban[slot], n_clk = s_n_clk[slot];
@@ -503,17 +622,23 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
             int st = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
             t += 1;
-            if (env.change_omega_for_bandits || st == RG_ORGANIC)
-                thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+            int pend = 0;
+            if (st == RG_ORGANIC) pend = 1;
+            else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
             while (st == RG_BANDIT && !organic_only) {  // abstract.py:174-181
                 int a;
                 if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
                 else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
                 const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
-                const int c = click_from_uniform(ctr_of_action(env, om, a), uniform53(wb.x, wb.y));
+                const double uc = uniform53(wb.x, wb.y);
+                // ff() never exceeds sig(5*0.5-6) = 0.02931, so the click threshold (1-ctr)/((1-ctr)+ctr)
+                // is above 0.9706: below that the click is 0 whatever omega is (97% of the bandit events).
+                int c = 0;
+                if (uc >= 0.9706) c = click_from_uniform(ctr_of_action(env, om, a), uc);
                 st = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
                 t += 1;
-                if (env.change_omega_for_bandits || st == RG_ORGANIC)
+                if (st == RG_ORGANIC) pend = 1;  // the loop ends here: deferred
+                else if (env.change_omega_for_bandits)
                     thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
                 if (c) st = RG_ORGANIC;
                 n_ban += 1;
@@ -538,8 +663,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             } else {
                 s_hash[slot] = h; s_t[slot] = t; s_last_view[slot] = last_view;
                 s_n_org[slot] = n_org; s_n_ban[slot] = n_ban; s_n_clk[slot] = n_clk;
+                s_pend[slot] = pend;
             }
         }
+        __syncthreads();
+        omega_phase();
         __syncthreads();
     }
 
@@ -547,6 +675,17 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     for (int s = 0; s < nstage - 1; ++s) {
         const unsigned seq = seq_use + (unsigned)s;
         mbar_wait(&mbar[seq % (unsigned)nstage], (seq / (unsigned)nstage) & 1u);
+    }
+
+    // ---- hand the user queue back clean: the last CTA to get here zeroes the ticket and the arrival counter
+    if (tid == 0) {
+        __threadfence();
+        const unsigned long long done = atomicAdd(p.queue + 1, 1ull);
+        if (done == (unsigned long long)gridDim.x - 1ull) {
+            p.queue[0] = 0ull;
+            p.queue[1] = 0ull;
+            __threadfence();
+        }
     }
 
     // ---- totals: warp reduction, one atomic per counter per warp
@@ -607,10 +746,11 @@ cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long
     make_layout(p);
     (void)K1;
     static thread_local unsigned launch_seq = 0;
-    p.queue = e.diag + 4 + (launch_seq++ % 60u);
-    cudaError_t ce = cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), stream);
-    if (ce != cudaSuccess) return ce;
-    ce = cudaFuncSetAttribute(rollout_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+    // queue[0] = next user ticket, queue[1] = CTAs finished; the last CTA to finish zeroes both, so a
+    // launch never needs a memset (and profiler kernel replays see a clean queue).  30 pairs in rotation
+    // keep launches on different streams apart.
+    p.queue = e.diag + 4 + 2 * (launch_seq++ % 30u);
+    cudaError_t ce = cudaFuncSetAttribute(rollout_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
     if (ce != cudaSuccess) return ce;
     int ctas_per_sm = p.L.total <= 110 * 1024 ? 2 : 1;
     long long blocks = (n_total + TU - 1) / TU;

@@ -21,7 +21,7 @@ timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -k r
 tail -3 gpurun_out/ncu_launch_$TAG.log
 echo "== ncu full capture of the rollout kernel"
 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:rollout_cta -s 3 -c 1 \
-    -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --users 100000 --train-users 20 \
+    -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --users 500000 --train-users 20 \
     --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
 fi
