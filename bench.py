@@ -234,7 +234,7 @@ def main():
     table_dev = torch.as_tensor(table, device=dev) if table is not None else None
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step_tots = torch.zeros((args.steps, 8), dtype=torch.int64, device=dev)
+    step_tots = torch.zeros((args.steps, 16), dtype=torch.int64, device=dev)
 
     def step(s, tot):
         """one fused rollout of U fresh users on this rank + the all-reduce of the CTR counters"""
@@ -248,7 +248,7 @@ def main():
         torch.cuda.synchronize()
 
     for w in range(args.warmup):
-        step(1000 + w, torch.zeros(8, dtype=torch.int64, device=dev))
+        step(1000 + w, torch.zeros(16, dtype=torch.int64, device=dev))
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -318,7 +318,7 @@ def main():
                    "policy": wl["policy"], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
                    "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
                    "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
-                   "fast_path_fallbacks": int(ev[6]), "f64_ambiguous": int(ev[7])},
+                   "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7])},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": args.steps,

@@ -93,8 +93,9 @@ typedef struct rg_rollout_out {
     int64_t *view_hist;  /* [P] accumulated */
     int64_t *action_hist;/* [P] accumulated (delivered actions) */
     int64_t *click_hist; /* [P] accumulated (clicked actions; evaluate_agent.py:121-124) */
-    int64_t *totals;     /* [8] accumulated: users, events, organic, bandit, clicks, phantom rows,
-                            fast-path fallbacks, f64-ambiguous samples (diagnostic, expected 0) */
+    int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
+                            [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] binary64-ambiguous
+                            samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, rest reserved */
 } rg_rollout_out;
 
 /* AbstractEnv.generate_logs(num_offline_users=n_users, agent, num_organic_offline_users=

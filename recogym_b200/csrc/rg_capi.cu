@@ -244,7 +244,7 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     const size_t o_lv = add(out->last_view, 4 * n, false), o_h = add(out->hash, 8 * n, false);
     const size_t o_om = add(out->omega, 8 * (size_t)n * K, false);
     const size_t o_vh = add(out->view_hist, 8 * (size_t)P, true), o_ah = add(out->action_hist, 8 * (size_t)P, true);
-    const size_t o_ch = add(out->click_hist, 8 * (size_t)P, true), o_t = add(out->totals, 8 * 8, true);
+    const size_t o_ch = add(out->click_hist, 8 * (size_t)P, true), o_t = add(out->totals, 8 * 16, true);
     const size_t o_tab = total;
     if (policy->kind == RG_POLICY_TABLE) total += ((size_t)4 * P + 255) & ~(size_t)255;
     char *arena = nullptr;

@@ -37,7 +37,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_u, pend, pend_list, misc, om32, tilesum, gtile, total;
+        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pend, pend_list, misc, om32, tilesum, gtile, total;
 };
 
 struct Params {
@@ -58,8 +58,10 @@ __host__ inline void make_layout(Params &p) {
     int o = 0;
     L.mbar = o; o += 8 * kMaxStages;
     L.om64 = o; o += 8 * TU * p.kp;
-    L.csum = o; o += 8 * p.ncs * FB;
+    L.csum = o; o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
+    L.fb_lse = o; o += 8 * FB;
+    L.lse = o; o += 8 * TU;
     L.user = o; o += 8 * TU;
     L.hash = o; o += 8 * TU;
     L.t = o; o += 4 * TU;
@@ -75,6 +77,8 @@ __host__ inline void make_layout(Params &p) {
     L.eps = o; o += 4 * TU;
     L.amb_list = o; o += 4 * TU;
     L.fb_slot = o; o += 4 * FB;
+    L.fb_pos = o; o += 4 * FB;
+    L.fb_unres = o; o += 4 * FB;
     L.pend = o; o += 4 * TU;
     L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
@@ -137,23 +141,33 @@ __device__ __forceinline__ void thread_omega_update(double *omega, int K, double
     }
 }
 
-// Binary64 view samples for up to FB users at once by the whole CTA (fallback of the filter).
-// Same mathematics as warp_sample_view_exact.  Every Gamma column is loaded once from L2 and used
-// for all users of the batch (the single-user version was L2-bandwidth bound: 1.6 MB per draw);
-// partial sums per CHUNK products in csum[f][c]; the inverse CDF of user f is then located by warp f.
-template <int NB>
-__device__ __forceinline__ void exact_batch_partial_sums(const EnvDev &env, const double *om64, int KP, double *csum,
-                                                         int ncs, const int *slots, int nb, const double *B,
-                                                         int lane, int warp) {
+// Re-sampling of the draws the fp32 filter could not certify: up to FB users per sweep of Gamma, whole CTA.
+// Every Gamma column (binary64, K-major) is loaded once from L2 and used for all users of the batch; partial
+// sums per CHUNK products go to csum[f][c]; the inverse CDF of user f is then located by warp f.
+//
+//   TIER 2 (T2 = true): binary64 logits (same fma chains as the oracle), but the mass is a bare
+//     ex2.approx of the logit relative to the user's log-sum-exp `lse` known from the fp32 pass:
+//     m = ex2(float(x)), x = log2e*(l) - lse <= ~0.  Its relative error is at most
+//     ln2*2^-24*|x| (rounding x to fp32) + 2^-21 (ex2.approx), so the error of ANY prefix sum is at most
+//     E = sum_p m_p*(c1*|x_p| + c2), accumulated alongside in esum[f][c] (an a-posteriori bound, about
+//     6e-7 of the total: ~250x tighter than the fp32 pass).  A draw whose margins exceed 2E is final.
+//   TIER 3 (T2 = false): everything in binary64 (exp64), the reference arithmetic; final.
+template <int NB, bool T2>
+__device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const double *om64, int KP, double *csum,
+                                                   double *esum, int ncs, const int *slots, int nb,
+                                                   const double *shiftv, int lane, int warp) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
     const double *om[NB];
 #pragma unroll
     for (int f = 0; f < NB; ++f) om[f] = om64 + (size_t)slots[f < nb ? f : nb - 1] * KP;
+    double sv[NB];
+#pragma unroll
+    for (int f = 0; f < NB; ++f) sv[f] = shiftv[f < nb ? f : nb - 1];
     const int nch = (Ppad + CHUNK - 1) / CHUNK;
     for (int c = warp; c < nch; c += NT / 32) {
-        double part[NB];
+        double part[NB], perr[NB];
 #pragma unroll
-        for (int f = 0; f < NB; ++f) part[f] = 0.0;
+        for (int f = 0; f < NB; ++f) { part[f] = 0.0; perr[f] = 0.0; }
         for (int g = 0; g < CHUNK / 32; ++g) {
             const int j = c * CHUNK + g * 32 + lane;
             if (j < P) {
@@ -168,52 +182,88 @@ __device__ __forceinline__ void exact_batch_partial_sums(const EnvDev &env, cons
                 }
                 const double mu = __ldg(env.mu_o + j);
 #pragma unroll
-                for (int f = 0; f < NB; ++f)
-                    if (f < nb) part[f] += exp64(acc[f] + mu - B[f]);
+                for (int f = 0; f < NB; ++f) {
+                    if (T2) {
+                        const double x = (acc[f] + mu) * 1.4426950408889634074 - sv[f];
+                        const double m = (double)ex2_approx((float)x);
+                        part[f] += m;
+                        perr[f] = fma(m, fma(fabs(x), 4.14e-8, 4.8e-7), perr[f]);
+                    } else {
+                        part[f] += exp64(acc[f] + mu - sv[f]);
+                    }
+                }
             }
         }
 #pragma unroll
         for (int f = 0; f < NB; ++f) {
             const double tot = warp_sum(part[f]);
             if (lane == 0 && f < nb) csum[(size_t)f * ncs + c] = tot;
+            if (T2) {
+                const double te = warp_sum(perr[f]);
+                if (lane == 0 && f < nb) esum[(size_t)f * ncs + c] = te;
+            }
         }
     }
 }
 
-__device__ __noinline__ void block_sample_views_exact(const EnvDev &env, const double *om64, int KP, double *csum,
-                                                      int ncs, const int *slots, const double *us, int nb,
-                                                      int *s_view, int tid, unsigned &ambig) {
+// slots/us/shiftv: shared arrays [FB] (slot index, view uniform, tier-2 log-sum-exp or unused);
+// unresolved[f] (shared) is set to 1 when tier 2 cannot certify the draw of user f.
+template <bool T2>
+__device__ __noinline__ void block_sample_views(const EnvDev &env, const double *om64, int KP, double *csum, int ncs,
+                                                const int *slots, const double *us, const double *lse, int nb,
+                                                int *s_view, int *unresolved, int tid, unsigned &ambig) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
     const int lane = tid & 31, warp = tid >> 5;
-    double B[FB];
-#pragma unroll
-    for (int f = 0; f < FB; ++f) {
-        const double *om = om64 + (size_t)slots[f < nb ? f : nb - 1] * KP;
-        double n2 = 0.0;
-        for (int k = 0; k < K; ++k) n2 = fma(om[k], om[k], n2);
-        B[f] = sqrt(n2) * env.gmax + env.mumax;
+    double *esum = csum + (size_t)FB * ncs;
+    __shared__ double sh_shift[FB];
+    if (tid < FB) {
+        double v = 0.0;
+        if (tid < nb) {
+            if (T2) {
+                v = lse[tid];
+            } else {  // upper bound of the logits (nats), as in warp_sample_view_exact
+                const double *om = om64 + (size_t)slots[tid] * KP;
+                double n2 = 0.0;
+                for (int k = 0; k < K; ++k) n2 = fma(om[k], om[k], n2);
+                v = sqrt(n2) * env.gmax + env.mumax;
+            }
+        }
+        sh_shift[tid] = v;
     }
-    if (nb <= 1) exact_batch_partial_sums<1>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
-    else if (nb <= 2) exact_batch_partial_sums<2>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
-    else if (nb <= 4) exact_batch_partial_sums<4>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
-    else exact_batch_partial_sums<8>(env, om64, KP, csum, ncs, slots, nb, B, lane, warp);
+    __syncthreads();
+    switch (nb) {
+        case 1: batch_partial_sums<1, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 2: batch_partial_sums<2, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 3: batch_partial_sums<3, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 4: batch_partial_sums<4, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 5: batch_partial_sums<5, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 6: batch_partial_sums<6, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 7: batch_partial_sums<7, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        default: batch_partial_sums<8, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+    }
     __syncthreads();
     if (warp < nb) {
         const int f = warp;
         const double *omega = om64 + (size_t)slots[f] * KP;
         const double *cs = csum + (size_t)f * ncs;
-        const double Bf = B[f < FB ? f : 0];
+        const double sf = sh_shift[f];
         auto mass = [&](int j) -> double {
             if (j >= P) return 0.0;
             const double *g = env.GammaT + j;
             double acc = 0.0;
             for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
-            return exp64(acc + __ldg(env.mu_o + j) - Bf);
+            const double l = acc + __ldg(env.mu_o + j);
+            if (T2) return (double)ex2_approx((float)(l * 1.4426950408889634074 - sf));
+            return exp64(l - sf);
         };
         const int nch = (Ppad + CHUNK - 1) / CHUNK;
-        double zl = 0.0;
-        for (int c = lane; c < nch; c += 32) zl += cs[c];
+        double zl = 0.0, el = 0.0;
+        for (int c = lane; c < nch; c += 32) {
+            zl += cs[c];
+            if (T2) el += esum[(size_t)f * ncs + c];
+        }
         const double Z = warp_sum(zl);
+        const double E = T2 ? warp_sum(el) : 0.0;
         const double tau = us[f] * Z;
         // chunk containing tau: 32 chunks per step, inclusive scan over lanes
         double cum = 0.0;
@@ -271,12 +321,18 @@ __device__ __noinline__ void block_sample_views_exact(const EnvDev &env, const d
             found = min(end, P) - 1;
             amb = true;
         } else {
-            const double tol = 1e-11 * Z;
+            // tier 2: twice the a-posteriori error bound of a prefix sum; tier 3: binary64 summation-order level
+            const double tol = T2 ? (2.02 * E + 1e-12 * Z) : 1e-11 * Z;
             amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
         }
         if (lane == 0) {
-            s_view[slots[f]] = found;
-            if (amb) ambig += 1;
+            if (T2) {
+                unresolved[f] = amb ? 1 : 0;
+                if (!amb) s_view[slots[f]] = found;
+            } else {
+                s_view[slots[f]] = found;
+                if (amb) ambig += 1;
+            }
         }
     }
     __syncthreads();
@@ -308,6 +364,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     int *amb_list = (int *)(smem + L.amb_list);
     int *fb_slot = (int *)(smem + L.fb_slot);
     double *fb_u = (double *)(smem + L.fb_u);
+    double *fb_lse = (double *)(smem + L.fb_lse);
+    double *s_lse = (double *)(smem + L.lse);  // log2-sum-exp of the fp32 pass, per position (ambiguous draws)
+    int *fb_pos = (int *)(smem + L.fb_pos);
+    int *fb_unres = (int *)(smem + L.fb_unres);
     int *s_pend = (int *)(smem + L.pend);      // 0 none, 1 drift into s_t, 2 init of a fresh user
     int *pend_list = (int *)(smem + L.pend_list);
     int *misc = (int *)(smem + L.misc);  // [0] nlive, [1] amb_count, [2] exact result
@@ -325,7 +385,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         misc[1] = 0;
     }
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
-    unsigned long long n_fallback = 0;
+    unsigned long long n_fallback = 0, n_tier3 = 0;
     unsigned ambig64 = 0;
 
     auto claim = [&](int slot) -> bool {  // next user id from the global queue -> reset()
@@ -542,28 +602,52 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const float shf = s_shift[i];
                 const int p0 = rsel * p.rec_sub * SUB;
                 const int p1 = min(p0 + p.rec_sub * SUB, nsub * SUB);
-                for (int base = p0; base < p1; base += 32) {
-                    const int pj = base + lane;
-                    const float *g = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & 127);
-                    float acc = 0.f;
-                    for (int k = 0; k < K1; ++k) acc = fmaf(om32[k * TU + i], __ldg(g + k * SUB), acc);
-                    double x = (double)ex2_approx(acc - shf);
+                // one 128-product tile per step: 4 masses per lane (4 independent FFMA chains keep 4 x K1 L2
+                // loads in flight), the 4 group totals by butterfly sums, a scan only in the crossing group
+                bool done = false;
+                for (int base = p0; base < p1 && !done; base += SUB) {
+                    const float *g0 = env.G32 + (size_t)(base >> 7) * K1 * SUB + lane;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                    for (int k = 0; k < K1; ++k) {
+                        const float wv = om32[k * TU + i];
+                        const float *gk = g0 + k * SUB;
+                        const float v0 = __ldg(gk), v1 = __ldg(gk + 32), v2 = __ldg(gk + 64), v3 = __ldg(gk + 96);
+                        a0 = fmaf(wv, v0, a0); a1 = fmaf(wv, v1, a1); a2 = fmaf(wv, v2, a2); a3 = fmaf(wv, v3, a3);
+                    }
+                    double xs[4] = {(double)ex2_approx(a0 - shf), (double)ex2_approx(a1 - shf),
+                                    (double)ex2_approx(a2 - shf), (double)ex2_approx(a3 - shf)};
+                    double tq[4] = {xs[0], xs[1], xs[2], xs[3]};
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double y = __shfl_up_sync(0xffffffffu, x, d);
-                        if (lane >= d) x += y;
+                    for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tq[q] += __shfl_xor_sync(0xffffffffu, tq[q], d);
                     }
-                    const double pre = cum + x;
-                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
-                    if (m) {
-                        const int fl = __ffs(m) - 1;
-                        found = base + fl;
-                        upper = __shfl_sync(0xffffffffu, pre, fl);
-                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
-                        lower = fl > 0 ? below : cum;
-                        break;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (done) break;
+                        if (cum + tq[q] > tau) {  // the crossing is in this group of 32 (or a rounding-level tie)
+                            double x = xs[q];
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const double y = __shfl_up_sync(0xffffffffu, x, d);
+                                if (lane >= d) x += y;
+                            }
+                            const double pre = cum + x;
+                            const int pj = base + q * 32 + lane;
+                            const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
+                            if (m) {
+                                const int fl = __ffs(m) - 1;
+                                found = base + q * 32 + fl;
+                                upper = __shfl_sync(0xffffffffu, pre, fl);
+                                const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                                lower = fl > 0 ? below : cum;
+                            }
+                            done = true;  // found, or inconsistent rounding (found < 0 -> ambiguous)
+                        } else {
+                            cum += tq[q];
+                        }
                     }
-                    cum = __shfl_sync(0xffffffffu, pre, 31);
                 }
                 if (found < 0) {
                     amb = true;
@@ -574,27 +658,50 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
             if (lane == 0) {
                 s_view[slot] = found;
-                if (amb) amb_list[atomicAdd(&misc[1], 1)] = i;
+                if (amb) {
+                    amb_list[atomicAdd(&misc[1], 1)] = i;
+                    s_lse[i] = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
+                }
             }
         }
         __syncthreads();
 
-        // ---- C2: binary64 re-sampling of the draws the filter could not certify, FB users per sweep of Gamma
+        // ---- C2: re-sampling of the draws the fp32 filter could not certify: tier 2 (binary64 logits, fp32 ex2,
+        // a-posteriori bound) for all of them, tier 3 (all binary64) for what tier 2 leaves open
         {
             const int namb = misc[1];
-            for (int b0 = 0; b0 < namb; b0 += FB) {
-                const int nb = min(FB, namb - b0);
-                if (tid < nb) {
-                    const int slot = pos2slot[amb_list[b0 + tid]];
-                    const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
-                    fb_slot[tid] = slot;
-                    fb_u[tid] = uniform53(w.x, w.y);
-                }
+            if (tid == 0) misc[4] = 0;
+            for (int tier = 2; tier <= 3; ++tier) {
                 __syncthreads();
-                block_sample_views_exact(env, om64, KP, csum, p.ncs, fb_slot, fb_u, nb, s_view, tid, ambig64);
+                const int n = tier == 2 ? namb : misc[4];
+                const int *list = tier == 2 ? amb_list : pend_list;  // pend_list doubles as the tier-3 list here
+                for (int b0 = 0; b0 < n; b0 += FB) {
+                    const int nb = min(FB, n - b0);
+                    if (tid < nb) {
+                        const int pos = list[b0 + tid];
+                        const int slot = pos2slot[pos];
+                        const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
+                        fb_slot[tid] = slot;
+                        fb_pos[tid] = pos;
+                        fb_u[tid] = uniform53(w.x, w.y);
+                        fb_lse[tid] = s_lse[pos];
+                        fb_unres[tid] = 0;
+                    }
+                    __syncthreads();
+                    if (tier == 2) {
+                        block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
+                                                 tid, ambig64);
+                        if (tid < nb && fb_unres[tid]) pend_list[atomicAdd(&misc[4], 1)] = fb_pos[tid];
+                    } else {
+                        block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view,
+                                                  fb_unres, tid, ambig64);
+                    }
+                    __syncthreads();
+                }
             }
             if (tid == 0) {
                 n_fallback += (unsigned long long)namb;
+                n_tier3 += (unsigned long long)misc[4];
                 misc[1] = 0;
             }
             __syncthreads();
@@ -690,10 +797,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
     // ---- totals: warp reduction, one atomic per counter per warp
     if (p.out.totals) {
-        unsigned long long v[8] = {tot_users, tot_events, tot_org, tot_ban, tot_clk, tot_ph, n_fallback,
-                                   (unsigned long long)ambig64};
+        unsigned long long v[9] = {tot_users, tot_events, tot_org, tot_ban, tot_clk, tot_ph, n_fallback,
+                                   (unsigned long long)ambig64, n_tier3};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 9; ++c) {
             unsigned long long x = v[c];
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);

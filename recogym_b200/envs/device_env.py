@@ -105,7 +105,7 @@ class DeviceEnv:
             for name in ("view_hist", "action_hist", "click_hist"):
                 res[name] = torch.zeros(self.P, dtype=torch.int64, device=dev)
                 setattr(out, name, res[name].data_ptr())
-        res["totals"] = totals if totals is not None else torch.zeros(8, dtype=torch.int64, device=dev)
+        res["totals"] = totals if totals is not None else torch.zeros(16, dtype=torch.int64, device=dev)
         out.totals = res["totals"].data_ptr()
         pol = L.Policy()
         if policy == "uniform":
@@ -142,7 +142,7 @@ class DeviceEnv:
             for name in ("view_hist", "action_hist", "click_hist"):
                 res[name] = np.zeros(self.P, np.int64)
                 setattr(out, name, res[name].ctypes.data)
-        res["totals"] = np.zeros(8, np.int64)
+        res["totals"] = np.zeros(16, np.int64)
         out.totals = res["totals"].ctypes.data
         pol = L.Policy()
         keep = None
