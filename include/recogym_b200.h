@@ -147,6 +147,12 @@ int32_t rg_spec_policy_uniform_action(uint64_t seed, uint64_t user, uint32_t t, 
  * map in[3n] = (seed, user, t) triples, each exactly representable in a double, to out[2n]. */
 int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *out_device, void *stream);
 
+/* Test hook of the tensor-core contraction: shifted log2-logits of 128 users against every product,
+ * out[128][ceil(P/128)*128] = log2(e)*(Gamma omega + mu_organic) - shift (tcgen05, tf32 hi/lo split).
+ * omega: device [128][K] double, shift: device [128] float (log2 units). */
+int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *shift_device, float *out_device,
+                        void *stream);
+
 int rg_device_count(void);              /* 0 when no usable GPU: callers must fail, not fall back */
 int rg_version(void);
 const char *rg_last_error(void);

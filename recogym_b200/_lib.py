@@ -50,7 +50,7 @@ EXPORTS = (
     "rg_batch_reset_device", "rg_batch_step_device", "rg_batch_continue_device",
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
     "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
-    "rg_spec_eval_device", "rg_device_count", "rg_version", "rg_last_error",
+    "rg_spec_eval_device", "rg_tc_logits_device", "rg_device_count", "rg_version", "rg_last_error",
 )
 
 
@@ -97,6 +97,8 @@ def lib():
     L.rg_spec_policy_uniform_action.argtypes = [u64, u64, u32, i32]
     L.rg_spec_eval_device.restype = C.c_int
     L.rg_spec_eval_device.argtypes = [C.c_int, i64, vp, vp, vp]
+    L.rg_tc_logits_device.restype = C.c_int
+    L.rg_tc_logits_device.argtypes = [vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "rg_host.h"
+#include "rg_tensor.cuh"
 
 namespace {
 
@@ -39,7 +40,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_env(rg_env_impl &e) {
     cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
-    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.diag);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.diag);
 }
 
 rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
@@ -151,7 +152,30 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
         }
     }
 
+    // tf32 hi/lo UMMA tiles of the tensor-core sampler (layout: rg_tensor.cuh)
+    const int KC = rg::tc::kt_chunks(K);
+    const size_t tile_floats = (size_t)2 * KC * (rg::tc::CHUNK_BYTES / 4);
+    std::vector<float> GTC((size_t)nsub * tile_floats, 0.f);
+    for (int p = 0; p < nsub * 128; ++p) {
+        float *tile = GTC.data() + (size_t)(p / 128) * tile_floats;
+        const int row = p % 128;
+        for (int k = 0; k < KC * 4; ++k) {
+            float x = 0.f;
+            if (p < P) {
+                if (k < K) x = (float)(d->Gamma[(size_t)p * K + k] * kLog2e);
+                else if (k == K) x = (float)(d->mu_organic[p] * kLog2e);
+                else if (k == K + 1) x = 1.f;
+            } else if (k == K) {
+                x = -1e30f;
+            }
+            const float hi = rg::tc::tf32_hi(x);
+            tile[rg::tc::tile_index(0, KC, row, k)] = hi;
+            tile[rg::tc::tile_index(1, KC, row, k)] = rg::tc::tf32_hi(x - hi);
+        }
+    }
+
     cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = upload(&e.d_GTC, GTC);
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT, GT);
     if (ce == cudaSuccess) ce = upload(&e.d_mu_o, mu);
     if (ce == cudaSuccess) ce = upload(&e.d_beta, beta);
@@ -332,6 +356,14 @@ int rg_batch_continue_device(rg_env *env, int64_t N, const int64_t *user_id, int
 int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *out_device, void *stream) {
     if (kind < 0 || kind > 6 || n < 0 || !in_device || !out_device) return fail(RG_EINVAL, "bad spec_eval argument");
     RG_CUDA(rg::launch_spec_eval(kind, n, in_device, out_device, (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *shift_device, float *out_device,
+                        void *stream) {
+    if (!env || !omega_device || !shift_device || !out_device) return fail(RG_EINVAL, "null argument");
+    RG_CUDA(cudaSetDevice(env->impl.device));
+    RG_CUDA(rg::launch_tc_logits(env->impl, omega_device, shift_device, out_device, (cudaStream_t)stream));
     return RG_OK;
 }
 

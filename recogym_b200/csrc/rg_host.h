@@ -11,7 +11,8 @@ struct rg_env_impl {
     // owned device allocations
     double *d_GammaT = nullptr, *d_mu_o = nullptr, *d_beta = nullptr, *d_mu_b = nullptr;
     float *d_GammaT32 = nullptr, *d_mu_o32 = nullptr;
-    float *d_Gamma32 = nullptr;          // [Ppad][Kpad4] row-major fp32 (fast-path tiles)
+    float *d_Gamma32 = nullptr;          // [nsub][K+1][128] fp32 tiles (fast path)
+    float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
     unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
 };
 
@@ -30,5 +31,7 @@ cudaError_t launch_batch(const rg_env_impl &e, int mode, long long N, const long
                          const int32_t *action, int32_t *state, int32_t *t, int32_t *last_view, double *omega,
                          int32_t *reward, int32_t *sess_v, int32_t *sess_len, int sess_cap, int32_t *n_unfinished,
                          cudaStream_t stream);
+cudaError_t launch_tc_logits(const rg_env_impl &e, const double *omega, const float *shift, float *out,
+                             cudaStream_t stream);
 cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);
 }  // namespace rg

@@ -1,0 +1,105 @@
+// rg_tensor.cuh -- tcgen05 / TMEM primitives (inline PTX) and the operand layout of the tensor-core
+// contraction used by the organic-view sampler.
+//
+// Logits of 128 users x 128 products are one UMMA tile:  D[u][p] = sum_k A[u][k] * B[p][k]  with
+//   A = omega tile   (128 x KT tf32, K-major), rebuilt by the CTA every round,
+//   B = Gamma tile   (128 x KT tf32, K-major), precomputed on the host (GTC array),
+// both in the canonical no-swizzle K-major layout of the UMMA shared-memory descriptor:
+//   element (row r, column k) -> chunk kc = k/4 (16 bytes), row group g = r/8:
+//   byte offset = kc * 2048 + g * 128 + (r % 8) * 16 + (k % 4) * 4        (2048 = 16 row groups x 128 B)
+// so LBO (between the two 16-byte K chunks of one K=8 MMA step) = 2048 B and SBO (between 8-row groups) = 128 B.
+// fp32 accuracy comes from a two-term tf32 split of both operands, x = hi + lo (hi = top 19 bits):
+//   D = A_hi B_hi + A_hi B_lo + A_lo B_hi   (the dropped lo*lo term is ~2^-22 relative)
+// Columns: k < K: log2e-scaled Gamma / omega;  k = K: mu' / 1;  k = K+1: 1 / -shift_u;  rest 0.
+#pragma once
+#include <cstdint>
+
+namespace rg {
+namespace tc {
+
+constexpr int TILE = 128;            // users per tile (UMMA M) and products per tile (UMMA N)
+constexpr int CHUNK_BYTES = 2048;    // one 16-byte K chunk of all 128 rows
+
+__host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks (even: one MMA eats two)
+    int kc = (K + 2 + 3) / 4;
+    return (kc + 1) & ~1;
+}
+
+__host__ __device__ inline float tf32_hi(float x) {
+    union { float f; uint32_t u; } v;
+    v.f = x;
+    v.u &= 0xFFFFE000u;
+    return v.f;
+}
+
+// float index of element (row, k) of term t inside one operand tile [2 terms][KC][16][8][4]
+__host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {
+    return ((((size_t)t * KC + (k >> 2)) * 16 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(CHUNK_BYTES >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdescTf32M128N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp as the alloc
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 tf32 step; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    // the wait names every destination register as in/out so that no consumer can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+#endif
+
+}  // namespace tc
+}  // namespace rg

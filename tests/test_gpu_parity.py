@@ -316,3 +316,39 @@ def test_drivers_test_agent_and_verify_agents():
     df = rg.verify_agents(env, 3000, {"random": ra, "organic": oc})
     assert list(df.columns) == ["Agent", "0.025", "0.500", "0.975"] and len(df) == 2
     assert ((df["0.025"] < df["0.500"]) & (df["0.500"] < df["0.975"])).all()
+
+
+def test_tensor_core_logits_match_binary64():
+    """tcgen05 contraction (tf32 hi/lo split, three UMMA terms) against binary64 logits: validates the
+    UMMA descriptors / operand layout / TMEM read-back and measures the error the tensor-core sampler's
+    filter has to cover."""
+    import ctypes as C
+    import torch
+    from recogym_b200 import DeviceEnv, _lib as L
+    for P, K in ((1000, 20), (10000, 20), (300, 5), (700, 64)):
+        cfg, sp = synthetic_env(P, K, 7 + P)
+        de = DeviceEnv(sp, 1, 0.1, 1)
+        rs = np.random.RandomState(P)
+        omega = rs.normal(size=(128, K))
+        omega[0] = 0.0
+        omega[1] *= 3.0
+        G, mu = sp["Gamma"], sp["mu_organic"].ravel()
+        log2e = 1.4426950408889634
+        logits = (omega @ G.T + mu[None, :]) * log2e
+        shift = (np.linalg.norm(omega, axis=1) * np.linalg.norm(G, axis=1).max() + mu.max()) * log2e - 100.0
+        shift = shift.astype(np.float32)
+        nsub = (P + 127) // 128
+        om_d = torch.as_tensor(omega, device="cuda")
+        sh_d = torch.as_tensor(shift, device="cuda")
+        out = torch.zeros((128, nsub * 128), dtype=torch.float32, device="cuda")
+        L.check(L.lib().rg_tc_logits_device(de._h, C.c_void_p(om_d.data_ptr()), C.c_void_p(sh_d.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.float64)
+        ref = logits - shift.astype(np.float64)[:, None]
+        err = np.abs(got[:, :P] - ref)
+        scale = np.abs(ref).max()
+        print("tc logits P=%d K=%d: max abs err %.3e (log2 units), max |ref| %.1f" % (P, K, err.max(), scale))
+        assert err.max() < 2e-4, (P, K, err.max())
+        assert (got[:, P:] < -1e29).all()          # padded products carry no mass
+        de.close()
