@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--users", type=int, default=0, help="users per GPU per step (default: workload's)")
-    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--math", default="fast", choices=["fast", "exact", "tensor"])
     ap.add_argument("--train-users", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -225,7 +225,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    math_mode = L.MATH_FAST if args.math == "fast" else L.MATH_EXACT
+    math_mode = {"fast": L.MATH_FAST, "exact": L.MATH_EXACT, "tensor": L.MATH_TENSOR}[args.math]
     P, K, U = wl["P"], wl["K"], wl["users"]
 
     cfg, sp = static_params(P, K)

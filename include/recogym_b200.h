@@ -46,6 +46,8 @@ extern "C" {
 #define RG_MATH_EXACT 0 /* every view sampled in binary64 (reference arithmetic) */
 #define RG_MATH_FAST 1  /* fp32 CUDA-core contraction with a rigorous ambiguity filter; ambiguous
                            events are re-sampled in binary64, so discrete results equal RG_MATH_EXACT */
+#define RG_MATH_TENSOR 2 /* as RG_MATH_FAST with the contraction on the tensor cores (tcgen05, tf32 hi/lo split,
+                            accumulators in TMEM); the filter bound for the tensor-core sums is empirical */
 
 /* Static parameters of one environment == what RecoEnv1.set_static_params() builds
  * (recogym/envs/reco_env_v1.py:51-75) plus the config scalars update_state()/reset() read. */

@@ -10,7 +10,7 @@ from .constants import AgentStats, AgentInit, EvolutionCase, TrainingApproach, R
 from .bench_agents import test_agent
 from .evaluate_agent import evaluate_agent, build_agent_init, verify_agents
 from . import agents
-from ._lib import MATH_EXACT, MATH_FAST, RecoGymB200Error
+from ._lib import MATH_EXACT, MATH_FAST, MATH_TENSOR, RecoGymB200Error
 
 _REGISTRY = {"reco-gym-v1": RecoEnv1}
 

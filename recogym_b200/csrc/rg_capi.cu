@@ -40,7 +40,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_env(rg_env_impl &e) {
     cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
-    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.diag);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.diag);
 }
 
 rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
@@ -61,7 +61,7 @@ int check_rollout_args(const rg_env *env, const rg_policy *policy, int64_t n_org
     if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE)
         return fail(RG_EINVAL, "unknown policy kind %d", policy->kind);
     if (policy->kind == RG_POLICY_TABLE && !policy->table) return fail(RG_EINVAL, "table policy without table");
-    if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST)
+    if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST && math_mode != RG_MATH_TENSOR)
         return fail(RG_EINVAL, "unknown math mode %d", math_mode);
     return RG_OK;
 }
@@ -211,6 +211,8 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     v.muabsmax = muabsmax;
     v.G32 = e.d_Gamma32;
     v.nsub = nsub;
+    v.GTC = e.d_GTC;
+    v.KC = KC;
     v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
     v.seed = d->seed;
     *out = env;
@@ -238,9 +240,9 @@ int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, 
     RG_CUDA(cudaSetDevice(env->impl.device));
     rg::PolicyDev pol{policy->kind, policy->table};
     const rg::RolloutOutDev od = to_dev(*out);
-    if (math_mode == RG_MATH_FAST)
+    if (math_mode == RG_MATH_FAST || math_mode == RG_MATH_TENSOR)
         RG_CUDA(rg::launch_rollout_fast(env->impl, pol, user_begin, n_organic_users, n_organic_users + n_users, od,
-                                        (cudaStream_t)stream));
+                                        (cudaStream_t)stream, math_mode == RG_MATH_TENSOR));
     else
         RG_CUDA(rg::launch_rollout_exact(env->impl, pol, user_begin, n_organic_users, n_organic_users + n_users, od,
                                          (cudaStream_t)stream));

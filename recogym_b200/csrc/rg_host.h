@@ -13,6 +13,8 @@ struct rg_env_impl {
     float *d_GammaT32 = nullptr, *d_mu_o32 = nullptr;
     float *d_Gamma32 = nullptr;          // [nsub][K+1][128] fp32 tiles (fast path)
     float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
+    double *d_om_scratch = nullptr;      // RG_MATH_TENSOR: omega rows of the resident slots
+    size_t om_scratch_bytes = 0;
     unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
 };
 
@@ -24,9 +26,9 @@ namespace rg {
 cudaError_t launch_rollout_exact(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
                                  long long n_organic_users, long long n_total, const RolloutOutDev &out,
                                  cudaStream_t stream);
-cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
+cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long user_begin,
                                 long long n_organic_users, long long n_total, const RolloutOutDev &out,
-                                cudaStream_t stream);
+                                cudaStream_t stream, bool tensor);
 cudaError_t launch_batch(const rg_env_impl &e, int mode, long long N, const long long *user_id,
                          const int32_t *action, int32_t *state, int32_t *t, int32_t *last_view, double *omega,
                          int32_t *reward, int32_t *sess_v, int32_t *sess_len, int sess_cap, int32_t *n_unfinished,

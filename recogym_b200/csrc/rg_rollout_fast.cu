@@ -24,6 +24,7 @@
 // All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
 #include "rg_device.cuh"
 #include "rg_host.h"
+#include "rg_tensor.cuh"
 
 namespace rg {
 namespace fast {
@@ -37,7 +38,8 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pend, pend_list, misc, om32, tilesum, gtile, total;
+        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        total;
 };
 
 struct Params {
@@ -47,6 +49,8 @@ struct Params {
     RolloutOutDev out;
     unsigned long long *queue;
     int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
+    int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
+    double *om_scratch;     // tc: the binary64 omega rows live in global memory, [grid][TU][kp]
     Layout L;
 };
 
@@ -56,9 +60,11 @@ __host__ inline void make_layout(Params &p) {
     const int K = p.env.K, K1 = K + 1;
     Layout &L = p.L;
     int o = 0;
-    L.mbar = o; o += 8 * kMaxStages;
-    L.om64 = o; o += 8 * TU * p.kp;
-    L.csum = o; o += 8 * p.ncs * FB * 2;
+    const int KC = tc::kt_chunks(K);
+    const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES;
+    L.mbar = o; o += 8 * (kMaxStages + 4);  // ring barriers, then [kMaxStages..+1] TMEM-full, [+2] TMEM address word
+    L.om64 = o; if (!p.tc) o += 8 * TU * p.kp;
+    L.csum = o; if (!p.tc) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
     L.lse = o; o += 8 * TU;
@@ -83,10 +89,24 @@ __host__ inline void make_layout(Params &p) {
     L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
     o = align_up(o, 16);
-    L.om32 = o; o += 4 * K1 * TU;
+    L.om32 = o; if (!p.tc) o += 4 * K1 * TU;
     L.tilesum = o; o += 4 * TU * p.nrec_pad;
     o = align_up(o, 128);
-    L.gtile = o; o += 4 * p.nstage * K1 * SUB;
+    L.gtile = o;
+    if (!p.tc) {
+        o += 4 * p.nstage * K1 * SUB;
+        L.atile = o;
+    } else {
+        // the B ring is idle between pass 1 and the next round's first load: the fp32 omega tile of pass 2 and
+        // the partial sums of the re-sampling sweeps live in the same bytes
+        int ring = p.nstage * tc_tile_bytes;
+        const int alias = align_up(4 * K1 * TU, 16) + 8 * p.ncs * FB * 2;
+        if (alias > ring) ring = align_up(alias, 128);
+        L.om32 = o;
+        L.csum = o + align_up(4 * K1 * TU, 16);
+        o += ring;
+        L.atile = o; o += tc_tile_bytes;
+    }
     L.total = o;
 }
 
@@ -338,6 +358,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
     __syncthreads();
 }
 
+template <bool TC>
 __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const EnvDev &env = p.env;
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     uint64_t *mbar = (uint64_t *)(smem + L.mbar);
-    double *om64 = (double *)(smem + L.om64);
+    double *om64 = TC ? p.om_scratch + (size_t)blockIdx.x * TU * p.kp : (double *)(smem + L.om64);
     double *csum = (double *)(smem + L.csum);
     uint64_t *s_user = (uint64_t *)(smem + L.user);
     uint64_t *s_hash = (uint64_t *)(smem + L.hash);
@@ -374,16 +395,23 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *om32 = (float *)(smem + L.om32);
     float *tilesum = (float *)(smem + L.tilesum);
     float *gtile = (float *)(smem + L.gtile);
+    float *a_tile = (float *)(smem + L.atile);
+    uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
+    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + 2);
+    const int KC = env.KC;
+    const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES;
 
-    const unsigned tile_bytes = (unsigned)(4 * K1 * SUB);
+    const unsigned tile_bytes = TC ? tc_tile_bytes : (unsigned)(4 * K1 * SUB);
     const int nsub = env.nsub, nstage = p.nstage;
 
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+        if (TC) { mbar_init(&dfull[0], 1); mbar_init(&dfull[1], 1); }
         fence_barrier_init();
         misc[1] = 0;
     }
+    if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // two 128-column accumulator tiles
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
     unsigned long long n_fallback = 0, n_tier3 = 0;
     unsigned ambig64 = 0;
@@ -446,10 +474,26 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         const int stage = (int)(seq % (unsigned)nstage);
         const int sub = (int)(seq % (unsigned)nsub);
         mbar_expect_tx(&mbar[stage], tile_bytes);
-        tma_bulk_g2s(gtile + (size_t)stage * K1 * SUB, env.G32 + (size_t)sub * K1 * SUB, tile_bytes, &mbar[stage]);
+        if (TC)
+            tma_bulk_g2s((unsigned char *)gtile + (size_t)stage * tile_bytes, env.GTC + (size_t)sub * (tile_bytes / 4),
+                         tile_bytes, &mbar[stage]);
+        else
+            tma_bulk_g2s(gtile + (size_t)stage * K1 * SUB, env.G32 + (size_t)sub * K1 * SUB, tile_bytes, &mbar[stage]);
     };
-    if (tid == 0)
-        for (int s = 0; s < nstage - 1; ++s) issue_load((unsigned)s);
+    // non-TC: the ring is always nstage-1 tiles ahead, across rounds.  TC: the ring bytes are reused between
+    // pass 1 and the next round, so each round starts with its own prologue of min(nstage, nsub) loads.
+    const int tc_prologue = nstage < nsub ? nstage : nsub;
+    if (tid == 0) {
+        if (TC) for (int s = 0; s < tc_prologue; ++s) issue_load((unsigned)s);
+        else for (int s = 0; s < nstage - 1; ++s) issue_load((unsigned)s);
+    }
+    uint32_t tmem_base = 0;
+    if (TC) {
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        tmem_base = *tmem_slot;
+    }
 
     const int tx = tid & 15, ty = tid >> 4;
 
@@ -471,13 +515,17 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         if (nlive == 0) break;
 
         // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
-        // error bound.  Dead positions get zeros.
-        for (int idx = tid; idx < K1 * TU; idx += NT) {
-            const int k = idx / TU, i = idx - k * TU;
-            float v = 0.f;
-            if (i < nlive) v = (k < K) ? (float)om64[(size_t)pos2slot[i] * KP + k] : 1.f;
-            om32[idx] = v;
-        }
+        // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
+        // bytes with the B ring, so it is built after pass 1.)
+        auto build_om32 = [&]() {
+            for (int idx = tid; idx < K1 * TU; idx += NT) {
+                const int k = idx / TU, i = idx - k * TU;
+                float v = 0.f;
+                if (i < nlive) v = (k < K) ? (float)om64[(size_t)pos2slot[i] * KP + k] : 1.f;
+                om32[idx] = v;
+            }
+        };
+        if (!TC) build_om32();
         if (tid < TU) {
             float sh = 0.f, ep = 1.f;
             if (tid < nlive) {
@@ -491,7 +539,14 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const double aub = (nrm * env.gmax + env.muabsmax) * kLog2e;  // >= sum_k |G'_pk w_k| + |mu'_p|
                 const double u24 = 5.9604644775390625e-08;                    // 2^-24
                 // log2-logit error: input rounding + K+1 fma roundings + the shift subtraction
-                const double dl2 = (K + 4) * u24 * aub + u24 * (aub + fabs(shift)) + u24 * fabs(shift);
+                double dl2 = (K + 4) * u24 * aub + u24 * (aub + fabs(shift)) + u24 * fabs(shift);
+                if (TC) {
+                    // tensor-core tile sums: dropped lo*lo term (2^-22 per product term, doubled) and the fp32
+                    // accumulation of the UMMA, whose rounding is undocumented: 8 roundings at the largest
+                    // magnitude.  Measured (tests): <= 0.5 of this bound for K = 5..64.
+                    const double dtc = aub * 4.76837158203125e-07 + 8.0 * u24 * (aub + fabs(shift));
+                    dl2 = fmax(dl2, dtc);
+                }
                 // relative mass error: exp of that, ex2.approx (2^-21 covers its 2 ulp), fp32 partial sums of pass 1
                 const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 +
                                      (8.0 * p.rec_sub + 6.0) * u24;
@@ -504,7 +559,78 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         __syncthreads();
 
         // ---- B: pass 1, dense contraction + exponentials + per-record-tile partial sums
-        {
+        if constexpr (TC) {
+            // Tensor-core form.  A = omega tile (tf32 hi/lo, UMMA K-major layout) written by the CTA, B = Gamma
+            // tiles streamed by TMA, D = shifted log2-logits of 128 users x 128 products in TMEM (two buffers).
+            // Thread 0 issues the three-term MMA of tile s+1 before the CTA runs the epilogue of tile s:
+            // thread (lane quarter q, column half h) owns user 32q+lane and 64 columns; per logit the epilogue is
+            // one ex2 and one add.
+            for (int idx = tid; idx < TU * p.nrec_pad; idx += NT) tilesum[idx] = 0.f;
+            const int KT = KC * 4;
+            for (int idx = tid; idx < TU * KT; idx += NT) {
+                const int row = idx / KT, k = idx - row * KT;
+                float x = 0.f;
+                if (row < nlive) {
+                    if (k < K) x = (float)om64[(size_t)pos2slot[row] * KP + k];
+                    else if (k == K) x = 1.f;
+                    else if (k == K + 1) x = -s_shift[row];
+                }
+                const float hi = tc::tf32_hi(x);
+                a_tile[tc::tile_index(0, KC, row, k)] = hi;
+                a_tile[tc::tile_index(1, KC, row, k)] = tc::tf32_hi(x - hi);
+            }
+            tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+
+            const uint32_t a_saddr = tc::smem_addr(a_tile);
+            const uint32_t ring_saddr = tc::smem_addr(gtile);
+            auto issue_mma = [&](unsigned gs) {  // thread 0: tile gs -> TMEM buffer gs & 1
+                const unsigned st = gs % (unsigned)nstage;
+                mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
+                tc::tc_fence_after();
+                tc::issue_tile_mmas(tmem_base + (gs & 1u) * 128u, a_saddr, ring_saddr + st * tile_bytes, KC);
+                tc::umma_commit(&dfull[gs & 1u]);
+            };
+            const int q = warp & 3, h = warp >> 2;
+            const int pos = q * 32 + lane;
+            const bool act = pos < nlive;
+            float part = 0.f;
+            int rec = 0, sub_in_rec = 0;
+            if (tid == 0) issue_mma(seq_use);
+            for (int sub = 0; sub < nsub; ++sub) {
+                const unsigned gs = seq_use + (unsigned)sub;
+                if (tid == 0 && sub + 1 < nsub) issue_mma(gs + 1u);
+                mbar_wait(&dfull[gs & 1u], (gs >> 1) & 1u);
+                tc::tc_fence_after();
+                // MMA(gs) is complete: its ring stage is free for tile gs + nstage of this round
+                if (tid == 0 && sub + nstage < nsub) issue_load(gs + (unsigned)nstage);
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float v[32];
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (gs & 1u) * 128u + (uint32_t)(h * 64 + c * 32), v);
+                    if (act) {
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) { s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]); }
+                        part += s0 + s1;
+                    }
+                }
+                if (++sub_in_rec == p.rec_sub || sub == nsub - 1) {
+                    if (act) atomicAdd(&tilesum[(size_t)pos * p.nrec_pad + rec], part);
+                    part = 0.f;
+                    ++rec;
+                    sub_in_rec = 0;
+                }
+                tc::tc_fence_before();
+                __syncthreads();  // TMEM buffer gs & 1 may be overwritten by MMA(gs + 2)
+            }
+            seq_use += (unsigned)nsub;
+            build_om32();     // pass 2 operand, in the (now idle) ring bytes
+            __syncthreads();
+        } else {
             const bool warp_active = warp * 16 < nlive;
             float sh[8], part[8];
 #pragma unroll
@@ -707,6 +833,12 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             __syncthreads();
         }
 
+        if (TC && tid == 0) {
+            // pass 2 and the re-sampling sweeps are done with the bytes they share with the ring:
+            // start streaming the first tiles of the next round while the users are advanced
+            for (int s2 = 0; s2 < tc_prologue; ++s2) issue_load(seq_use + (unsigned)s2);
+        }
+
         // ---- D: one thread per slot: finish the organic event, run the bandit events, recycle the slot.
         // omega updates that precede an ORGANIC event are deferred to omega_phase() (whole CTA); the ones
         // that precede a bandit event (change_omega_for_bandits only) are done inline.
@@ -779,9 +911,14 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     }
 
     // ---- drain the prefetched tiles (a CTA must not exit with bulk copies in flight)
-    for (int s = 0; s < nstage - 1; ++s) {
+    for (int s = 0; s < (TC ? tc_prologue : nstage - 1); ++s) {
         const unsigned seq = seq_use + (unsigned)s;
         mbar_wait(&mbar[seq % (unsigned)nstage], (seq / (unsigned)nstage) & 1u);
+    }
+    if (TC) {
+        tc::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
     }
 
     // ---- hand the user queue back clean: the last CTA to get here zeroes the ticket and the arrival counter
@@ -811,9 +948,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
 }  // namespace fast
 
-cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long long user_begin,
+cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long user_begin,
                                 long long n_organic_users, long long n_total, const RolloutOutDev &out,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, bool tensor) {
     using namespace fast;
     if (n_total <= 0) return cudaSuccess;
     Params p;
@@ -823,6 +960,8 @@ cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long
     p.n_organic_users = n_organic_users;
     p.n_total = n_total;
     p.out = out;
+    p.tc = tensor ? 1 : 0;
+    p.om_scratch = nullptr;
     const int K1 = e.dev.K + 1;
     p.kp = e.dev.K | 1;  // odd row stride of the binary64 omega rows: conflict-free per-slot access
     p.ncs = (e.dev.Ppad + CHUNK - 1) / CHUNK + 1;
@@ -857,13 +996,28 @@ cudaError_t launch_rollout_fast(const rg_env_impl &e, const PolicyDev &pol, long
     // launch never needs a memset (and profiler kernel replays see a clean queue).  30 pairs in rotation
     // keep launches on different streams apart.
     p.queue = e.diag + 4 + 2 * (launch_seq++ % 30u);
-    cudaError_t ce = cudaFuncSetAttribute(rollout_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+    cudaError_t ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
+                            : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
     if (ce != cudaSuccess) return ce;
     int ctas_per_sm = p.L.total <= 110 * 1024 ? 2 : 1;
     long long blocks = (n_total + TU - 1) / TU;
     const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
     if (blocks > max_blocks) blocks = max_blocks;
-    rollout_cta_kernel<<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+    if (tensor) {
+        const size_t need = sizeof(double) * (size_t)max_blocks * TU * p.kp;
+        if (e.om_scratch_bytes < need) {   // binary64 omega rows of every resident slot (grown once per env)
+            if (e.d_om_scratch) cudaFree(e.d_om_scratch);
+            e.d_om_scratch = nullptr;
+            e.om_scratch_bytes = 0;
+            ce = cudaMalloc((void **)&e.d_om_scratch, need);
+            if (ce != cudaSuccess) return ce;
+            e.om_scratch_bytes = need;
+        }
+        p.om_scratch = e.d_om_scratch;
+        rollout_cta_kernel<true><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+    } else {
+        rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -54,23 +54,6 @@ __device__ void build_a_tile(float *a_tile, int KC, int K, const double *omega, 
     }
 }
 
-// One thread: the three-term tf32 contraction of one 128 x 128 tile into TMEM columns [tmem_d, tmem_d+128)
-__device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int KC) {
-    const uint32_t term = (uint32_t)KC * CHUNK_BYTES;  // bytes of one term (hi or lo) of an operand tile
-    uint32_t acc = 0;
-    // small terms first: lo*hi, hi*lo, then hi*hi
-#pragma unroll 1
-    for (int pair = 0; pair < 3; ++pair) {
-        const uint32_t a0 = a_saddr + (pair == 0 ? term : 0u);
-        const uint32_t b0 = b_saddr + (pair == 1 ? term : 0u);
-        for (int s = 0; s < KC / 2; ++s) {
-            umma_tf32(tmem_d, umma_desc(a0 + (uint32_t)s * 2u * CHUNK_BYTES), umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES),
-                      kIdescTf32M128N128, acc);
-            acc = 1;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict__ GTC, int nsub, int KC, int K,
                                                         const double *__restrict__ omega,
                                                         const float *__restrict__ shift, float *__restrict__ out) {

@@ -1,3 +1,6 @@
 #!/bin/bash
+# tensor-core mode: parity tests for the mode, then a short bench in both modes
 mkdir -p gpurun_out
-timeout -k 10 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k tensor_core 2>&1 | tail -15 | tee gpurun_out/tc_test.log
+TAG=${1:-tc}
+timeout -k 10 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor or c3_shape" 2>&1 | tail -15 | tee gpurun_out/tc_test_$TAG.log
+timeout -k 10 600 python bench.py --steps 3 --warmup 3 --math tensor --no-cpu-baseline 2>&1 | tail -2 | tee gpurun_out/bench_tensor_$TAG.log

@@ -12,7 +12,7 @@ from conftest import T2_CASES, load_golden, oracle_env_from_golden
 
 pytestmark = pytest.mark.gpu
 
-MODES = {"exact": 0, "fast": 1}
+MODES = {"exact": 0, "fast": 1, "tensor": 2}
 
 
 def device_env_from_golden(g, device=0):
@@ -96,7 +96,7 @@ def test_device_math_equals_host_and_oracle(oracle):
                 assert y[i, 1] == float(oracle.philox(s, u, t, 1)[3])
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
 @pytest.mark.parametrize("case", T2_CASES)
 def test_rollout_equals_oracle_and_reference_logs(oracle, case, mode):
     """Golden cases: CUDA rollout == C oracle per user, and its counters == the T2 reference logs."""
@@ -117,7 +117,7 @@ def test_rollout_equals_oracle_and_reference_logs(oracle, case, mode):
     de.close()
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
 @pytest.mark.parametrize("P,K,n,policy", [
     (1, 1, 300, "uniform"),        # single product: view always 0
     (2, 3, 400, "table"),
@@ -136,7 +136,7 @@ def test_rollout_shapes_and_edges(oracle, P, K, n, policy, mode):
     de.close()
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
 def test_rollout_model_variants(oracle, mode):
     for over in ({"change_omega_for_bandits": True, "sigma_omega": 0.4},
                  {"flips": 15, "normalize_beta": True},
@@ -172,14 +172,14 @@ def test_empty_and_device_entry_points(oracle):
     de.close()
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
 def test_sharding_invariance_and_full_size_properties(mode):
     """BASELINE config C2 size (P=100, K=5, 1M users): results do not depend on how users are split
     over launches/ranks; counters are self-consistent; events/user follows the geometric law."""
     from recogym_b200 import DeviceEnv
     cfg, sp = synthetic_env(100, 5, 42)
     de = DeviceEnv(sp, 1, 0.1, 42)
-    N = 1_000_000 if mode == "fast" else 100_000
+    N = 1_000_000 if mode != "exact" else 100_000
     full = de.rollout_host(N, "uniform", None, 0, 0, MODES[mode], per_user=True, hist=True)
     parts = [de.rollout_host(N // 4, "uniform", None, r * (N // 4), 0, MODES[mode], per_user=True, hist=True)
              for r in range(4)]
@@ -208,11 +208,13 @@ def test_c3_shape_fast_equals_exact_on_device():
     de = DeviceEnv(sp, 1, 0.1, 42)
     table = np.random.RandomState(1).randint(0, 10000, 10000).astype(np.int32)
     a = de.rollout_host(3000, "table", table, 0, 0, 0, per_user=True, hist=True, omega=True)
-    b = de.rollout_host(3000, "table", table, 0, 0, 1, per_user=True, hist=True, omega=True)
-    for k in PER_USER + ("hash", "view_hist", "action_hist", "click_hist", "omega"):
-        assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(a["totals"][:6], b["totals"][:6])
-    assert a["totals"][7] == 0 and b["totals"][7] == 0
+    for mode in (1, 2):
+        b = de.rollout_host(3000, "table", table, 0, 0, mode, per_user=True, hist=True, omega=True)
+        for k in PER_USER + ("hash", "view_hist", "action_hist", "click_hist", "omega"):
+            assert np.array_equal(a[k], b[k]), (mode, k)
+        assert np.array_equal(a["totals"][:6], b["totals"][:6])
+        assert a["totals"][7] == 0 and b["totals"][7] == 0
+        assert 0 < b["totals"][8] <= b["totals"][6] < 0.2 * b["totals"][2]   # tier 3 << tier 2 << organic draws
     de.close()
 
 
