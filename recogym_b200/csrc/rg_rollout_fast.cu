@@ -38,7 +38,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pz, ptau, pcum, prsel, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
 
@@ -68,6 +68,9 @@ __host__ inline void make_layout(Params &p) {
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
     L.lse = o; o += 8 * TU;
+    L.pz = o; o += 8 * TU;
+    L.ptau = o; o += 8 * TU;
+    L.pcum = o; o += 8 * TU;
     L.user = o; o += 8 * TU;
     L.hash = o; o += 8 * TU;
     L.t = o; o += 4 * TU;
@@ -85,6 +88,7 @@ __host__ inline void make_layout(Params &p) {
     L.fb_slot = o; o += 4 * FB;
     L.fb_pos = o; o += 4 * FB;
     L.fb_unres = o; o += 4 * FB;
+    L.prsel = o; o += 4 * TU;
     L.pend = o; o += 4 * TU;
     L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
@@ -387,6 +391,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     double *fb_u = (double *)(smem + L.fb_u);
     double *fb_lse = (double *)(smem + L.fb_lse);
     double *s_lse = (double *)(smem + L.lse);  // log2-sum-exp of the fp32 pass, per position (ambiguous draws)
+    double *s_Z = (double *)(smem + L.pz);
+    double *s_tau = (double *)(smem + L.ptau);
+    double *s_cum = (double *)(smem + L.pcum);
+    int *s_rsel = (int *)(smem + L.prsel);
     int *fb_pos = (int *)(smem + L.fb_pos);
     int *fb_unres = (int *)(smem + L.fb_unres);
     int *s_pend = (int *)(smem + L.pend);      // 0 none, 1 drift into s_t, 2 init of a fresh user
@@ -687,38 +695,33 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             seq_use += (unsigned)nsub;
         }
 
-        // ---- C: pass 2, one warp per live user: total mass, locate, recompute one record tile, margins
-        for (int i = warp; i < nlive; i += NT / 32) {
-            const int slot = pos2slot[i];
-            const uint64_t user = s_user[slot];
-            const u32x4 w = draw(env.seed, user, s_t[slot], SLOT_EVENT);
+        // ---- C: pass 2a, one thread per live user: view uniform, total mass, tau = u*Z, the record tile that
+        // contains tau and the mass before it (sequential binary64 sums of the fp32 tile sums)
+        if (tid < nlive) {
+            const int i = tid, slot = pos2slot[i];
+            const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
             const double u = uniform53(w.x, w.y);
             const float *ts = tilesum + (size_t)i * p.nrec_pad;
-            double zl = 0.0;
-            for (int r = lane; r < p.nrec; r += 32) zl += (double)ts[r];
-            const double Z = warp_sum(zl);
+            double Z = 0.0;
+            for (int r = 0; r < p.nrec; ++r) Z += (double)ts[r];
             const double tau = u * Z;
             double cum = 0.0;
             int rsel = -1;
-            for (int r0 = 0; r0 < p.nrec && rsel < 0; r0 += 32) {
-                const int r = r0 + lane;
-                double x = r < p.nrec ? (double)ts[r] : 0.0;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const double y = __shfl_up_sync(0xffffffffu, x, d);
-                    if (lane >= d) x += y;
-                }
-                const double pre = cum + x;
-                const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (r < p.nrec));
-                if (m) {
-                    const int fl = __ffs(m) - 1;
-                    rsel = r0 + fl;
-                    const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
-                    cum = fl > 0 ? below : cum;
-                } else {
-                    cum = __shfl_sync(0xffffffffu, pre, 31);
-                }
+            for (int r = 0; r < p.nrec; ++r) {
+                const double nx = cum + (double)ts[r];
+                if (nx > tau) { rsel = r; break; }
+                cum = nx;
             }
+            s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel;
+        }
+        __syncthreads();
+
+        // ---- C: pass 2b, one warp per live user: recompute the located record tile, index and margins
+        for (int i = warp; i < nlive; i += NT / 32) {
+            const int slot = pos2slot[i];
+            const double Z = s_Z[i], tau = s_tau[i];
+            double cum = s_cum[i];
+            const int rsel = s_rsel[i];
             int found = -1;
             bool amb = false;
             double lower = 0.0, upper = 0.0;
@@ -986,6 +989,11 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             make_layout(p);
             if (p.L.total <= 227 * 1024) best_stage = nstage;
         }
+    }
+    if (!best_stage && tensor) {
+        // the UMMA operand tiles (2 x 2 x KC x 2 KB per stage + the A tile) do not fit for this K:
+        // same kernel with the CUDA-core contraction (identical discrete results)
+        return launch_rollout_fast(e, pol, user_begin, n_organic_users, n_total, out, stream, false);
     }
     if (!best_stage) return cudaErrorInvalidConfiguration;  // K/P too large for the CTA-batched kernel
     p.nstage = best_stage;
