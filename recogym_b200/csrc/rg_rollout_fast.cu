@@ -38,7 +38,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, lse, pz, ptau, pcum, prsel, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, ptau, pcum, prsel, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
 
@@ -67,6 +67,7 @@ __host__ inline void make_layout(Params &p) {
     L.csum = o; if (!p.tc) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
+    L.fb_om = o; o += 8 * FB * p.kp;
     L.lse = o; o += 8 * TU;
     L.pz = o; o += 8 * TU;
     L.ptau = o; o += 8 * TU;
@@ -176,14 +177,13 @@ __device__ __forceinline__ void thread_omega_update(double *omega, int K, double
 //     E = sum_p m_p*(c1*|x_p| + c2), accumulated alongside in esum[f][c] (an a-posteriori bound, about
 //     6e-7 of the total: ~250x tighter than the fp32 pass).  A draw whose margins exceed 2E is final.
 //   TIER 3 (T2 = false): everything in binary64 (exp64), the reference arithmetic; final.
-template <int NB, bool T2>
-__device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const double *om64, int KP, double *csum,
-                                                   double *esum, int ncs, const int *slots, int nb,
-                                                   const double *shiftv, int lane, int warp) {
+template <int NB, int PP, bool T2>
+__device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const double *om_s, int KP, double *csum,
+                                                   double *esum, int ncs, int nb, const double *shiftv, int lane,
+                                                   int warp) {
+    // om_s: the omega rows of the batch staged in shared memory, [FB][KP].  Each lane carries PP products x NB
+    // users = PP*NB independent fma chains and PP loads in flight per k (the sweep is latency bound otherwise).
     const int K = env.K, P = env.P, Ppad = env.Ppad;
-    const double *om[NB];
-#pragma unroll
-    for (int f = 0; f < NB; ++f) om[f] = om64 + (size_t)slots[f < nb ? f : nb - 1] * KP;
     double sv[NB];
 #pragma unroll
     for (int f = 0; f < NB; ++f) sv[f] = shiftv[f < nb ? f : nb - 1];
@@ -192,28 +192,43 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
         double part[NB], perr[NB];
 #pragma unroll
         for (int f = 0; f < NB; ++f) { part[f] = 0.0; perr[f] = 0.0; }
-        for (int g = 0; g < CHUNK / 32; ++g) {
-            const int j = c * CHUNK + g * 32 + lane;
-            if (j < P) {
-                double acc[NB];
+        for (int g0 = 0; g0 < CHUNK / 32; g0 += PP) {
+            double acc[PP][NB];
+            const double *gp[PP];
 #pragma unroll
-                for (int f = 0; f < NB; ++f) acc[f] = 0.0;
-                const double *gp = env.GammaT + j;
-                for (int k = 0; k < K; ++k) {
-                    const double gk = __ldg(gp + (size_t)k * Ppad);
+            for (int q = 0; q < PP; ++q) {
+                const int j = c * CHUNK + (g0 + q) * 32 + lane;
+                gp[q] = env.GammaT + (j < Ppad ? j : Ppad - 1);
 #pragma unroll
-                    for (int f = 0; f < NB; ++f) acc[f] = fma(gk, om[f][k], acc[f]);
-                }
-                const double mu = __ldg(env.mu_o + j);
+                for (int f = 0; f < NB; ++f) acc[q][f] = 0.0;
+            }
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                double gk[PP];
+#pragma unroll
+                for (int q = 0; q < PP; ++q) gk[q] = __ldg(gp[q] + (size_t)k * Ppad);
 #pragma unroll
                 for (int f = 0; f < NB; ++f) {
-                    if (T2) {
-                        const double x = (acc[f] + mu) * 1.4426950408889634074 - sv[f];
-                        const double m = (double)ex2_approx((float)x);
-                        part[f] += m;
-                        perr[f] = fma(m, fma(fabs(x), 4.14e-8, 4.8e-7), perr[f]);
-                    } else {
-                        part[f] += exp64(acc[f] + mu - sv[f]);
+                    const double w = om_s[f * KP + k];
+#pragma unroll
+                    for (int q = 0; q < PP; ++q) acc[q][f] = fma(gk[q], w, acc[q][f]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PP; ++q) {
+                const int j = c * CHUNK + (g0 + q) * 32 + lane;
+                if (j < P) {
+                    const double mu = __ldg(env.mu_o + j);
+#pragma unroll
+                    for (int f = 0; f < NB; ++f) {
+                        if (T2) {
+                            const double x = (acc[q][f] + mu) * 1.4426950408889634074 - sv[f];
+                            const double m = (double)ex2_approx((float)x);
+                            part[f] += m;
+                            perr[f] = fma(m, fma(fabs(x), 4.14e-8, 4.8e-7), perr[f]);
+                        } else {
+                            part[f] += exp64(acc[q][f] + mu - sv[f]);
+                        }
                     }
                 }
             }
@@ -235,7 +250,8 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
 template <bool T2>
 __device__ __noinline__ void block_sample_views(const EnvDev &env, const double *om64, int KP, double *csum, int ncs,
                                                 const int *slots, const double *us, const double *lse, int nb,
-                                                int *s_view, int *unresolved, int tid, unsigned &ambig) {
+                                                int *s_view, int *unresolved, double *om_s, int tid,
+                                                unsigned &ambig) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
     const int lane = tid & 31, warp = tid >> 5;
     double *esum = csum + (size_t)FB * ncs;
@@ -254,32 +270,27 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         }
         sh_shift[tid] = v;
     }
+    for (int idx = tid; idx < FB * KP; idx += NT) {  // stage the omega rows of the batch (rows >= nb repeat the last)
+        const int f = idx / KP, k = idx - f * KP;
+        om_s[idx] = k < K ? om64[(size_t)slots[f < nb ? f : nb - 1] * KP + k] : 0.0;
+    }
     __syncthreads();
     switch (nb) {
-        case 1: batch_partial_sums<1, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 2: batch_partial_sums<2, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 3: batch_partial_sums<3, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 4: batch_partial_sums<4, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 5: batch_partial_sums<5, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 6: batch_partial_sums<6, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        case 7: batch_partial_sums<7, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
-        default: batch_partial_sums<8, T2>(env, om64, KP, csum, esum, ncs, slots, nb, sh_shift, lane, warp); break;
+        case 1: batch_partial_sums<1, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 2: batch_partial_sums<2, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 3: batch_partial_sums<3, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 4: batch_partial_sums<4, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 5: batch_partial_sums<5, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 6: batch_partial_sums<6, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 7: batch_partial_sums<7, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        default: batch_partial_sums<8, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
     }
     __syncthreads();
     if (warp < nb) {
         const int f = warp;
-        const double *omega = om64 + (size_t)slots[f] * KP;
+        const double *omega = om_s + (size_t)f * KP;
         const double *cs = csum + (size_t)f * ncs;
         const double sf = sh_shift[f];
-        auto mass = [&](int j) -> double {
-            if (j >= P) return 0.0;
-            const double *g = env.GammaT + j;
-            double acc = 0.0;
-            for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
-            const double l = acc + __ldg(env.mu_o + j);
-            if (T2) return (double)ex2_approx((float)(l * 1.4426950408889634074 - sf));
-            return exp64(l - sf);
-        };
         const int nch = (Ppad + CHUNK - 1) / CHUNK;
         double zl = 0.0, el = 0.0;
         for (int c = lane; c < nch; c += 32) {
@@ -321,24 +332,64 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         int found = -1;
         double lower = 0.0, upper = 0.0;
         const int end = min((csel + 1) * CHUNK, Ppad);
-        for (int base = csel * CHUNK; base < end; base += 32) {
-            double x = mass(base + lane);
+        {   // the whole chunk at once: 8 masses per lane (8 independent chains), 8 butterfly totals, one scan
+            constexpr int G = CHUNK / 32;
+            double acc[G], xs[G], tq[G];
+            const double *gp[G];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double y = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += y;
+            for (int q = 0; q < G; ++q) {
+                const int j = csel * CHUNK + q * 32 + lane;
+                gp[q] = env.GammaT + (j < Ppad ? j : Ppad - 1);
+                acc[q] = 0.0;
             }
-            const double pre = cum + x;
-            const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (base + lane < P));
-            if (m) {
-                const int fl = __ffs(m) - 1;
-                found = base + fl;
-                upper = __shfl_sync(0xffffffffu, pre, fl);
-                const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
-                lower = fl > 0 ? below : cum;
-                break;
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const double w = omega[k];
+#pragma unroll
+                for (int q = 0; q < G; ++q) acc[q] = fma(__ldg(gp[q] + (size_t)k * Ppad), w, acc[q]);
             }
-            cum = __shfl_sync(0xffffffffu, pre, 31);
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                const int j = csel * CHUNK + q * 32 + lane;
+                double m = 0.0;
+                if (j < P) {
+                    const double l = acc[q] + __ldg(env.mu_o + j);
+                    m = T2 ? (double)ex2_approx((float)(l * 1.4426950408889634074 - sf)) : exp64(l - sf);
+                }
+                xs[q] = m;
+                tq[q] = m;
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+                for (int q = 0; q < G; ++q) tq[q] += __shfl_xor_sync(0xffffffffu, tq[q], d);
+            }
+            bool done = false;
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                if (done) break;
+                if (cum + tq[q] > tau || q == G - 1) {
+                    double x = xs[q];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= d) x += y;
+                    }
+                    const double pre = cum + x;
+                    const int base = csel * CHUNK + q * 32;
+                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (base + lane < P));
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        found = base + fl;
+                        upper = __shfl_sync(0xffffffffu, pre, fl);
+                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                        lower = fl > 0 ? below : cum;
+                    }
+                    done = true;
+                } else {
+                    cum += tq[q];
+                }
+            }
         }
         bool amb = false;
         if (found < 0) {
@@ -390,6 +441,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     int *fb_slot = (int *)(smem + L.fb_slot);
     double *fb_u = (double *)(smem + L.fb_u);
     double *fb_lse = (double *)(smem + L.fb_lse);
+    double *fb_om = (double *)(smem + L.fb_om);
     double *s_lse = (double *)(smem + L.lse);  // log2-sum-exp of the fp32 pass, per position (ambiguous draws)
     double *s_Z = (double *)(smem + L.pz);
     double *s_tau = (double *)(smem + L.ptau);
@@ -556,8 +608,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     dl2 = fmax(dl2, dtc);
                 }
                 // relative mass error: exp of that, ex2.approx (2^-21 covers its 2 ulp), fp32 partial sums of pass 1
-                const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 +
-                                     (8.0 * p.rec_sub + 6.0) * u24;
+                // fp32 partial sums of pass 1: longest chain of additions behind one record-tile sum
+                const double nadd = TC ? fmax(8.0 * p.rec_sub + 6.0, 2.0 * p.rec_sub + 20.0) : 8.0 * p.rec_sub + 6.0;
+                const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 + nadd * u24;
                 sh = (float)shift;
                 ep = (float)(2.0 * delta * 1.05 + 1e-7);
             }
@@ -819,11 +872,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     __syncthreads();
                     if (tier == 2) {
                         block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
-                                                 tid, ambig64);
+                                                 fb_om, tid, ambig64);
                         if (tid < nb && fb_unres[tid]) pend_list[atomicAdd(&misc[4], 1)] = fb_pos[tid];
                     } else {
                         block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view,
-                                                  fb_unres, tid, ambig64);
+                                                  fb_unres, fb_om, tid, ambig64);
                     }
                     __syncthreads();
                 }
@@ -842,9 +895,30 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             for (int s2 = 0; s2 < tc_prologue; ++s2) issue_load(seq_use + (unsigned)s2);
         }
 
-        // ---- D: one thread per slot: finish the organic event, run the bandit events, recycle the slot.
-        // omega updates that precede an ORGANIC event are deferred to omega_phase() (whole CTA); the ones
-        // that precede a bandit event (change_omega_for_bandits only) are done inline.
+        // ---- D: advance the users.  D1 (one thread per slot) finishes the organic event: bookkeeping of the
+        // view, transition.  D2 (one warp per user) runs the bandit events: the draws of an event depend only
+        // on (user, t), so lane j evaluates the event at time t+j assuming the run is still alive; the run ends
+        // at the first lane whose transition leaves the bandit state or whose click fires.  omega updates that
+        // precede an ORGANIC event are deferred to omega_phase(); with change_omega_for_bandits every event
+        // changes omega, so that configuration keeps the serial per-thread loop.
+        auto finish_user = [&](int slot, uint64_t user, uint64_t h, uint32_t t, int last_view, int n_org, int n_ban,
+                               int n_clk) {  // episode over: write the user out, claim the next one
+            const long long idx = (long long)user - p.user_begin;
+            const double *om = om64 + (size_t)slot * KP;
+            h = hash_fold(h, ((uint64_t)t << 2) | 3u);
+            if (p.out.n_events) p.out.n_events[idx] = (int32_t)t;
+            if (p.out.n_organic) p.out.n_organic[idx] = n_org;
+            if (p.out.n_bandit) p.out.n_bandit[idx] = n_ban;
+            if (p.out.n_clicks) p.out.n_clicks[idx] = n_clk;
+            if (p.out.last_view) p.out.last_view[idx] = last_view;
+            if (p.out.hash) p.out.hash[idx] = h;
+            if (p.out.omega)
+                for (int k = 0; k < K; ++k) p.out.omega[(size_t)idx * K + k] = om[k];
+            tot_users += 1; tot_events += t; tot_org += n_org; tot_ban += n_ban; tot_clk += n_clk;
+            tot_ph += idx < p.n_organic_users ? 0 : 1;
+            claim(slot);
+        };
+        const bool serial_bandit = env.change_omega_for_bandits != 0;
         if (tid < TU && s_live[tid]) {
             const int slot = tid;
             double *om = om64 + (size_t)slot * KP;
@@ -852,8 +926,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             uint64_t h = s_hash[slot];
             uint32_t t = s_t[slot];
             int last_view, n_org = s_n_org[slot], n_ban = s_n_ban[slot], n_clk = s_n_clk[slot];
-            const long long idx = (long long)user - p.user_begin;
-            const bool organic_only = idx < p.n_organic_users;
+            const bool organic_only = (long long)user - p.user_begin < p.n_organic_users;
             {   // abstract.py:110-119: the view was drawn above; now update_state
                 const int v = s_view[slot];
                 last_view = v;
@@ -867,21 +940,18 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             int pend = 0;
             if (st == RG_ORGANIC) pend = 1;
             else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
-            while (st == RG_BANDIT && !organic_only) {  // abstract.py:174-181
+            while (serial_bandit && st == RG_BANDIT && !organic_only) {  // abstract.py:174-181, one event per turn
                 int a;
                 if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
                 else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
                 const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
                 const double uc = uniform53(wb.x, wb.y);
-                // ff() never exceeds sig(5*0.5-6) = 0.02931, so the click threshold (1-ctr)/((1-ctr)+ctr)
-                // is above 0.9706: below that the click is 0 whatever omega is (97% of the bandit events).
                 int c = 0;
                 if (uc >= 0.9706) c = click_from_uniform(ctr_of_action(env, om, a), uc);
                 st = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
                 t += 1;
                 if (st == RG_ORGANIC) pend = 1;  // the loop ends here: deferred
-                else if (env.change_omega_for_bandits)
-                    thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+                else thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
                 if (c) st = RG_ORGANIC;
                 n_ban += 1;
                 n_clk += c;
@@ -889,23 +959,79 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 if (p.out.action_hist) atomicAdd(p.out.action_hist + a, 1ull);
                 if (c && p.out.click_hist) atomicAdd(p.out.click_hist + a, 1ull);
             }
-            if (st != RG_ORGANIC) {  // episode over: write the user out, claim the next one
-                h = hash_fold(h, ((uint64_t)t << 2) | 3u);
-                if (p.out.n_events) p.out.n_events[idx] = (int32_t)t;
-                if (p.out.n_organic) p.out.n_organic[idx] = n_org;
-                if (p.out.n_bandit) p.out.n_bandit[idx] = n_ban;
-                if (p.out.n_clicks) p.out.n_clicks[idx] = n_clk;
-                if (p.out.last_view) p.out.last_view[idx] = last_view;
-                if (p.out.hash) p.out.hash[idx] = h;
-                if (p.out.omega)
-                    for (int k = 0; k < K; ++k) p.out.omega[(size_t)idx * K + k] = om[k];
-                tot_users += 1; tot_events += t; tot_org += n_org; tot_ban += n_ban; tot_clk += n_clk;
-                tot_ph += organic_only ? 0 : 1;
-                claim(slot);
+            if (st == RG_STOP || (st == RG_BANDIT && organic_only)) {
+                finish_user(slot, user, h, t, last_view, n_org, n_ban, n_clk);
             } else {
                 s_hash[slot] = h; s_t[slot] = t; s_last_view[slot] = last_view;
                 s_n_org[slot] = n_org; s_n_ban[slot] = n_ban; s_n_clk[slot] = n_clk;
                 s_pend[slot] = pend;
+                s_state[slot] = st;  // ORGANIC, or BANDIT: the run is played by D2
+            }
+        }
+        __syncthreads();
+        if (!serial_bandit) {
+            if (warp == 0) {  // list of the slots that enter a bandit run (amb_list is free at this point)
+                int base = 0;
+                for (int c = 0; c < TU / 32; ++c) {
+                    const int slot = c * 32 + lane;
+                    const bool bd = s_live[slot] != 0 && s_state[slot] == RG_BANDIT;
+                    const unsigned m = __ballot_sync(0xffffffffu, bd);
+                    if (bd) amb_list[base + __popc(m & ((1u << lane) - 1u))] = slot;
+                    base += __popc(m);
+                }
+                if (lane == 0) misc[5] = base;
+            }
+            __syncthreads();
+            const int nban = misc[5];
+            for (int b = warp; b < nban; b += NT / 32) {
+                const int slot = amb_list[b];
+                const double *om = om64 + (size_t)slot * KP;
+                const uint64_t user = s_user[slot];
+                uint64_t h = s_hash[slot];
+                uint32_t t = s_t[slot];
+                const int last_view = s_last_view[slot];
+                int n_ban = s_n_ban[slot], n_clk = s_n_clk[slot];
+                int st = RG_BANDIT, pend = 0;
+                while (st == RG_BANDIT) {  // 32 candidate events per turn (a run is ~14 events on average)
+                    const uint32_t tt = t + (uint32_t)lane;
+                    int a;
+                    if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
+                    else a = uniform_action(draw(env.seed, user, tt, SLOT_POLICY).x, P);
+                    const u32x4 wb = draw(env.seed, user, tt, SLOT_EVENT);
+                    const double uc = uniform53(wb.x, wb.y);
+                    // ff() never exceeds sig(5*0.5-6) = 0.02931, so the click threshold (1-ctr)/((1-ctr)+ctr) is
+                    // above 0.9706: below that the click is 0 whatever omega is (97% of the bandit events)
+                    int c = 0;
+                    if (uc >= 0.9706) c = click_from_uniform(ctr_of_action(env, om, a), uc);
+                    const int nst = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
+                    const unsigned m = __ballot_sync(0xffffffffu, nst != RG_BANDIT || c != 0);
+                    const int nev = m ? __ffs(m) : 32;  // events of this turn that really happen
+                    const uint64_t rec = ((uint64_t)(uint32_t)a << 2) | ((uint64_t)c << 1) | 1u;
+                    for (int j = 0; j < nev; ++j) h = hash_fold(h, __shfl_sync(0xffffffffu, rec, j));
+                    if (lane < nev) {
+                        if (p.out.action_hist) atomicAdd(p.out.action_hist + a, 1ull);
+                        if (c && p.out.click_hist) atomicAdd(p.out.click_hist + a, 1ull);
+                    }
+                    n_ban += nev;
+                    t += (uint32_t)nev;
+                    if (m) {
+                        const int cf = __shfl_sync(0xffffffffu, c, nev - 1);
+                        const int nstf = __shfl_sync(0xffffffffu, nst, nev - 1);
+                        n_clk += cf;
+                        pend = nstf == RG_ORGANIC ? 1 : 0;   // drift only if the TRANSITION said organic
+                        st = cf ? RG_ORGANIC : nstf;          // abstract.py:180-181: a click overrides it
+                    }
+                }
+                if (lane == 0) {
+                    if (st == RG_ORGANIC) {
+                        s_hash[slot] = h; s_t[slot] = t; s_n_ban[slot] = n_ban; s_n_clk[slot] = n_clk;
+                        s_pend[slot] = pend;
+                        s_state[slot] = RG_ORGANIC;
+                    } else {
+                        finish_user(slot, user, h, t, last_view, s_n_org[slot], n_ban, n_clk);
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
