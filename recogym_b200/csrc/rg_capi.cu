@@ -154,11 +154,11 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
 
     // tf32 hi/lo UMMA tiles of the tensor-core sampler (layout: rg_tensor.cuh)
     const int KC = rg::tc::kt_chunks(K);
-    const size_t tile_floats = (size_t)2 * KC * (rg::tc::CHUNK_BYTES / 4);
-    std::vector<float> GTC((size_t)nsub * tile_floats, 0.f);
+    const size_t tile_floats = (size_t)2 * KC * (rg::tc::CHUNK_BYTES_B / 4);   // one 64-product tile, hi + lo
+    std::vector<float> GTC((size_t)nsub * 2 * tile_floats, 0.f);
     for (int p = 0; p < nsub * 128; ++p) {
-        float *tile = GTC.data() + (size_t)(p / 128) * tile_floats;
-        const int row = p % 128;
+        float *tile = GTC.data() + (size_t)(p / 64) * tile_floats;
+        const int row = p % 64;
         for (int k = 0; k < KC * 4; ++k) {
             float x = 0.f;
             if (p < P) {
@@ -169,8 +169,8 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
                 x = -1e30f;
             }
             const float hi = rg::tc::tf32_hi(x);
-            tile[rg::tc::tile_index(0, KC, row, k)] = hi;
-            tile[rg::tc::tile_index(1, KC, row, k)] = rg::tc::tf32_hi(x - hi);
+            tile[rg::tc::tile_index_b(0, KC, row, k)] = hi;
+            tile[rg::tc::tile_index_b(1, KC, row, k)] = rg::tc::tf32_hi(x - hi);
         }
     }
 

@@ -33,7 +33,8 @@ constexpr int TU = 128;     // user slots per CTA
 constexpr int SUB = 128;    // products per shared-memory tile
 constexpr int NT = 256;     // threads per CTA
 constexpr int CHUNK = 256;  // products per partial sum of the cooperative binary64 sampler
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
+constexpr int NBUF = 3;      // tensor mode: accumulator tiles (64 TMEM columns each) in flight
 constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampler
 
 struct Layout {  // byte offsets into dynamic shared memory
@@ -61,8 +62,9 @@ __host__ inline void make_layout(Params &p) {
     Layout &L = p.L;
     int o = 0;
     const int KC = tc::kt_chunks(K);
-    const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES;
-    L.mbar = o; o += 8 * (kMaxStages + 4);  // ring barriers, then [kMaxStages..+1] TMEM-full, [+2] TMEM address word
+    const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES_B;  // one 64-product B tile (hi + lo)
+    const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
+    L.mbar = o; o += 8 * (kMaxStages + NBUF + 1);  // ring barriers, NBUF TMEM-full barriers, TMEM address word
     L.om64 = o; if (!p.tc) o += 8 * TU * p.kp;
     L.csum = o; if (!p.tc) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
@@ -110,7 +112,7 @@ __host__ inline void make_layout(Params &p) {
         L.om32 = o;
         L.csum = o + align_up(4 * K1 * TU, 16);
         o += ring;
-        L.atile = o; o += tc_tile_bytes;
+        L.atile = o; o += tc_a_bytes;
     }
     L.total = o;
 }
@@ -457,21 +459,22 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *gtile = (float *)(smem + L.gtile);
     float *a_tile = (float *)(smem + L.atile);
     uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
-    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + 2);
+    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + NBUF);
     const int KC = env.KC;
-    const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES;
+    const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES_B;
 
     const unsigned tile_bytes = TC ? tc_tile_bytes : (unsigned)(4 * K1 * SUB);
     const int nsub = env.nsub, nstage = p.nstage;
+    const int ntile = TC ? 2 * nsub : nsub;  // tiles streamed per round: 64 products (TC) or 128 (CUDA cores)
 
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
-        if (TC) { mbar_init(&dfull[0], 1); mbar_init(&dfull[1], 1); }
+        if (TC) for (int b = 0; b < NBUF; ++b) mbar_init(&dfull[b], 1);
         fence_barrier_init();
         misc[1] = 0;
     }
-    if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // two 128-column accumulator tiles
+    if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // NBUF 64-column accumulator tiles
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
     unsigned long long n_fallback = 0, n_tier3 = 0;
     unsigned ambig64 = 0;
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     unsigned seq_use = 0;  // sequence number of the next tile to consume (same in every thread)
     auto issue_load = [&](unsigned seq) {  // thread 0 only: tile (seq % nsub) -> ring stage (seq % nstage)
         const int stage = (int)(seq % (unsigned)nstage);
-        const int sub = (int)(seq % (unsigned)nsub);
+        const int sub = (int)(seq % (unsigned)ntile);
         mbar_expect_tx(&mbar[stage], tile_bytes);
         if (TC)
             tma_bulk_g2s((unsigned char *)gtile + (size_t)stage * tile_bytes, env.GTC + (size_t)sub * (tile_bytes / 4),
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     };
     // non-TC: the ring is always nstage-1 tiles ahead, across rounds.  TC: the ring bytes are reused between
     // pass 1 and the next round, so each round starts with its own prologue of min(nstage, nsub) loads.
-    const int tc_prologue = nstage < nsub ? nstage : nsub;
+    const int tc_prologue = nstage < ntile ? nstage : ntile;
     if (tid == 0) {
         if (TC) for (int s = 0; s < tc_prologue; ++s) issue_load((unsigned)s);
         else for (int s = 0; s < nstage - 1; ++s) issue_load((unsigned)s);
@@ -647,48 +650,50 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
             const uint32_t a_saddr = tc::smem_addr(a_tile);
             const uint32_t ring_saddr = tc::smem_addr(gtile);
-            auto issue_mma = [&](unsigned gs) {  // thread 0: tile gs -> TMEM buffer gs & 1
+            auto issue_mma = [&](unsigned gs) {  // thread 0: 64-product tile gs -> TMEM buffer gs % NBUF
                 const unsigned st = gs % (unsigned)nstage;
                 mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
                 tc::tc_fence_after();
-                tc::issue_tile_mmas(tmem_base + (gs & 1u) * 128u, a_saddr, ring_saddr + st * tile_bytes, KC);
-                tc::umma_commit(&dfull[gs & 1u]);
+                tc::issue_tile_mmas(tmem_base + (gs % NBUF) * 64u, a_saddr, ring_saddr + st * tile_bytes, KC);
+                tc::umma_commit(&dfull[gs % NBUF]);
             };
             const int q = warp & 3, h = warp >> 2;
             const int pos = q * 32 + lane;
             const bool act = pos < nlive;
             float part = 0.f;
-            int rec = 0, sub_in_rec = 0;
-            if (tid == 0) issue_mma(seq_use);
-            for (int sub = 0; sub < nsub; ++sub) {
-                const unsigned gs = seq_use + (unsigned)sub;
-                if (tid == 0 && sub + 1 < nsub) issue_mma(gs + 1u);
-                mbar_wait(&dfull[gs & 1u], (gs >> 1) & 1u);
+            int rec = 0;
+            if (tid == 0)
+                for (int j = 0; j < NBUF - 1 && j < ntile; ++j) issue_mma(seq_use + (unsigned)j);
+            for (int tt = 0; tt < ntile; ++tt) {
+                const unsigned gs = seq_use + (unsigned)tt;
+                if (tid == 0 && tt + NBUF - 1 < ntile) issue_mma(gs + (unsigned)(NBUF - 1));
+                mbar_wait(&dfull[gs % NBUF], (gs / NBUF) & 1u);
                 tc::tc_fence_after();
                 // MMA(gs) is complete: its ring stage is free for tile gs + nstage of this round
-                if (tid == 0 && sub + nstage < nsub) issue_load(gs + (unsigned)nstage);
+                if (tid == 0 && tt + nstage < ntile) issue_load(gs + (unsigned)nstage);
                 __syncwarp();
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                {
                     float v[32];
-                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (gs & 1u) * 128u + (uint32_t)(h * 64 + c * 32), v);
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (gs % NBUF) * 64u + (uint32_t)(h * 32), v);
                     if (act) {
-                        float s0 = 0.f, s1 = 0.f;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) { s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]); }
-                        part += s0 + s1;
+                        for (int i = 0; i < 32; i += 4) {
+                            s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]);
+                            s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
+                        }
+                        part += (s0 + s1) + (s2 + s3);
                     }
                 }
-                if (++sub_in_rec == p.rec_sub || sub == nsub - 1) {
+                if ((tt + 1) % (2 * p.rec_sub) == 0 || tt == ntile - 1) {
                     if (act) atomicAdd(&tilesum[(size_t)pos * p.nrec_pad + rec], part);
                     part = 0.f;
                     ++rec;
-                    sub_in_rec = 0;
                 }
                 tc::tc_fence_before();
-                __syncthreads();  // TMEM buffer gs & 1 may be overwritten by MMA(gs + 2)
+                __syncthreads();  // TMEM buffer gs % NBUF may be overwritten by MMA(gs + NBUF)
             }
-            seq_use += (unsigned)nsub;
+            seq_use += (unsigned)ntile;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
         } else {
@@ -784,29 +789,39 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const float shf = s_shift[i];
                 const int p0 = rsel * p.rec_sub * SUB;
                 const int p1 = min(p0 + p.rec_sub * SUB, nsub * SUB);
-                // one 128-product tile per step: 4 masses per lane (4 independent FFMA chains keep 4 x K1 L2
-                // loads in flight), the 4 group totals by butterfly sums, a scan only in the crossing group
+                // two 128-product tiles per step: 8 masses per lane (8 independent FFMA chains keep 8 x K1 L2 loads
+                // in flight), the 8 group totals by butterfly sums, a scan only in the crossing group
                 bool done = false;
-                for (int base = p0; base < p1 && !done; base += SUB) {
+                for (int base = p0; base < p1 && !done; base += 2 * SUB) {
+                    const bool two = base + SUB < p1;
                     const float *g0 = env.G32 + (size_t)(base >> 7) * K1 * SUB + lane;
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+                    const float *g1 = two ? g0 + (size_t)K1 * SUB : g0;
+                    float a[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+#pragma unroll 3
                     for (int k = 0; k < K1; ++k) {
                         const float wv = om32[k * TU + i];
-                        const float *gk = g0 + k * SUB;
-                        const float v0 = __ldg(gk), v1 = __ldg(gk + 32), v2 = __ldg(gk + 64), v3 = __ldg(gk + 96);
-                        a0 = fmaf(wv, v0, a0); a1 = fmaf(wv, v1, a1); a2 = fmaf(wv, v2, a2); a3 = fmaf(wv, v3, a3);
+                        const float *gk0 = g0 + k * SUB, *gk1 = g1 + k * SUB;
+                        float v[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { v[q] = __ldg(gk0 + q * 32); v[4 + q] = __ldg(gk1 + q * 32); }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = fmaf(wv, v[q], a[q]);
                     }
-                    double xs[4] = {(double)ex2_approx(a0 - shf), (double)ex2_approx(a1 - shf),
-                                    (double)ex2_approx(a2 - shf), (double)ex2_approx(a3 - shf)};
-                    double tq[4] = {xs[0], xs[1], xs[2], xs[3]};
+                    double xs[8], tq[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        xs[q] = (q < 4 || two) ? (double)ex2_approx(a[q] - shf) : 0.0;
+                        tq[q] = xs[q];
+                    }
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) tq[q] += __shfl_xor_sync(0xffffffffu, tq[q], d);
+                        for (int q = 0; q < 8; ++q) tq[q] += __shfl_xor_sync(0xffffffffu, tq[q], d);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 8; ++q) {
                         if (done) break;
                         if (cum + tq[q] > tau) {  // the crossing is in this group of 32 (or a rounding-level tie)
                             double x = xs[q];
@@ -1104,13 +1119,14 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.nrec_pad = p.nrec | 1;
     // ring depth: as deep as shared memory allows (2 CTAs/SM when possible)
     int best_stage = 0;
-    for (int nstage = 3; nstage >= 2 && !best_stage; --nstage) {
+    const int hi_stage = tensor ? kMaxStages : 3, lo_stage = tensor ? NBUF : 2;
+    for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
         p.nstage = nstage;
         make_layout(p);
         if (p.L.total <= 110 * 1024) best_stage = nstage;
     }
     if (!best_stage) {
-        for (int nstage = 3; nstage >= 2 && !best_stage; --nstage) {
+        for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
             p.nstage = nstage;
             make_layout(p);
             if (p.L.total <= 227 * 1024) best_stage = nstage;

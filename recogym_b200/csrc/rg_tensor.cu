@@ -59,10 +59,10 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
                                                         const float *__restrict__ shift, float *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned tile_bytes = 2u * (unsigned)KC * CHUNK_BYTES;
+    const unsigned a_bytes = 2u * (unsigned)KC * CHUNK_BYTES, tile_bytes = 2u * (unsigned)KC * CHUNK_BYTES_B;
     float *a_tile = (float *)smem;
-    float *b_tile = (float *)(smem + tile_bytes);
-    uint64_t *bars = (uint64_t *)(smem + 2 * tile_bytes);  // [0] TMA, [1] MMA
+    float *b_tile = (float *)(smem + a_bytes);
+    uint64_t *bars = (uint64_t *)(smem + a_bytes + tile_bytes);  // [0] TMA, [1] MMA
     uint32_t *tmem_slot = (uint32_t *)(bars + 2);
 
     if (tid == 0) {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (warp == 0) tmem_alloc(tmem_slot, 64);
     build_a_tile(a_tile, KC, K, omega, K, shift, TILE, tid, 128);
     fence_proxy_async();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    for (int sub = 0; sub < nsub; ++sub) {
+    for (int sub = 0; sub < 2 * nsub; ++sub) {  // 64-product tiles
         const unsigned parity = (unsigned)sub & 1u;
         if (tid == 0) {
             mbar_expect_tx(&bars[0], tile_bytes);
@@ -94,17 +94,17 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
         tc_fence_after();
         const int row = warp * 32 + lane;  // TMEM lane == user row
 #pragma unroll 1
-        for (int c0 = 0; c0 < TILE; c0 += 32) {
+        for (int c0 = 0; c0 < TILE_N; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) out[(size_t)row * ((size_t)nsub * TILE) + (size_t)sub * TILE + c0 + i] = v[i];
+            for (int i = 0; i < 32; ++i) out[(size_t)row * ((size_t)nsub * TILE) + (size_t)sub * TILE_N + c0 + i] = v[i];
         }
         tc_fence_before();
         __syncthreads();  // TMEM tile and B tile are free again
         tc_fence_after();
     }
-    if (warp == 0) tmem_dealloc(tmem_base, 128);
+    if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
 }  // namespace tc
@@ -113,7 +113,7 @@ cudaError_t launch_tc_logits(const rg_env_impl &e, const double *omega, const fl
                              cudaStream_t stream) {
     using namespace tc;
     const int KC = kt_chunks(e.dev.K);
-    const size_t smem = 2 * 2 * (size_t)KC * CHUNK_BYTES + 64;
+    const size_t smem = 2 * (size_t)KC * (CHUNK_BYTES + CHUNK_BYTES_B) + 64;
     cudaError_t ce = cudaFuncSetAttribute(tc_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
     tc_logits_kernel<<<1, 128, smem, stream>>>(e.d_GTC, e.dev.nsub, KC, e.dev.K, omega, shift, out);

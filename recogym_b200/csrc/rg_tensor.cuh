@@ -1,13 +1,15 @@
 // rg_tensor.cuh -- tcgen05 / TMEM primitives (inline PTX) and the operand layout of the tensor-core
 // contraction used by the organic-view sampler.
 //
-// Logits of 128 users x 128 products are one UMMA tile:  D[u][p] = sum_k A[u][k] * B[p][k]  with
+// Logits of 128 users x 64 products are one UMMA tile:  D[u][p] = sum_k A[u][k] * B[p][k]  with
 //   A = omega tile   (128 x KT tf32, K-major), rebuilt by the CTA every round,
-//   B = Gamma tile   (128 x KT tf32, K-major), precomputed on the host (GTC array),
+//   B = Gamma tile   ( 64 x KT tf32, K-major), precomputed on the host (GTC array),
 // both in the canonical no-swizzle K-major layout of the UMMA shared-memory descriptor:
 //   element (row r, column k) -> chunk kc = k/4 (16 bytes), row group g = r/8:
-//   byte offset = kc * 2048 + g * 128 + (r % 8) * 16 + (k % 4) * 4        (2048 = 16 row groups x 128 B)
-// so LBO (between the two 16-byte K chunks of one K=8 MMA step) = 2048 B and SBO (between 8-row groups) = 128 B.
+//   byte offset = kc * (rows/8 * 128) + g * 128 + (r % 8) * 16 + (k % 4) * 4
+// so LBO (between the two 16-byte K chunks of one K=8 MMA step) = 2048 B for A, 1024 B for B, and SBO (between
+// 8-row groups) = 128 B.  (64-product tiles keep four accumulator tiles in 256 TMEM columns and make the
+// L2 -> shared-memory stream of B fine grained: 12 KB per stage at K = 20.)
 // fp32 accuracy comes from a two-term tf32 split of both operands, x = hi + lo (hi = top 19 bits):
 //   D = A_hi B_hi + A_hi B_lo + A_lo B_hi   (the dropped lo*lo term is ~2^-22 relative)
 // Columns: k < K: log2e-scaled Gamma / omega;  k = K: mu' / 1;  k = K+1: 1 / -shift_u;  rest 0.
@@ -17,8 +19,10 @@
 namespace rg {
 namespace tc {
 
-constexpr int TILE = 128;            // users per tile (UMMA M) and products per tile (UMMA N)
-constexpr int CHUNK_BYTES = 2048;    // one 16-byte K chunk of all 128 rows
+constexpr int TILE = 128;            // users per tile (UMMA M)
+constexpr int TILE_N = 64;           // products per tile (UMMA N)
+constexpr int CHUNK_BYTES = 2048;    // A: one 16-byte K chunk of all 128 rows
+constexpr int CHUNK_BYTES_B = 1024;  // B: one 16-byte K chunk of all 64 rows
 
 __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks (even: one MMA eats two)
     int kc = (K + 2 + 3) / 4;
@@ -32,21 +36,24 @@ __host__ __device__ inline float tf32_hi(float x) {
     return v.f;
 }
 
-// float index of element (row, k) of term t inside one operand tile [2 terms][KC][16][8][4]
-__host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {
+// float index of element (row, k) of term t inside one operand tile [2 terms][KC][rows/8][8][4]
+__host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {  // A: 128 rows
     return ((((size_t)t * KC + (k >> 2)) * 16 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+}
+__host__ __device__ inline size_t tile_index_b(int t, int KC, int row, int k) {  // B: 64 rows
+    return ((((size_t)t * KC + (k >> 2)) * 8 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
 }
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(CHUNK_BYTES >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
            (1ull << 46);
 }
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdescTf32M128N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdescTf32M128N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
@@ -99,23 +106,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-// One thread: the three-term tf32 contraction of one 128 x 128 tile into TMEM columns [tmem_d, tmem_d+128)
+// One thread: the three-term tf32 contraction of one 128 x 64 tile into TMEM columns [tmem_d, tmem_d+64)
 __device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int KC) {
-    const uint32_t term = (uint32_t)KC * CHUNK_BYTES;  // bytes of one term (hi or lo) of an operand tile
+    const uint32_t aterm = (uint32_t)KC * CHUNK_BYTES, bterm = (uint32_t)KC * CHUNK_BYTES_B;  // hi -> lo term
     uint32_t acc = 0;
     // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll 1
     for (int pair = 0; pair < 3; ++pair) {
-        const uint32_t a0 = a_saddr + (pair == 0 ? term : 0u);
-        const uint32_t b0 = b_saddr + (pair == 1 ? term : 0u);
+        const uint32_t a0 = a_saddr + (pair == 0 ? aterm : 0u);
+        const uint32_t b0 = b_saddr + (pair == 1 ? bterm : 0u);
         for (int s = 0; s < KC / 2; ++s) {
-            umma_tf32(tmem_d, umma_desc(a0 + (uint32_t)s * 2u * CHUNK_BYTES), umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES),
-                      kIdescTf32M128N128, acc);
+            umma_tf32(tmem_d, umma_desc(a0 + (uint32_t)s * 2u * CHUNK_BYTES, CHUNK_BYTES),
+                      umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES_B, CHUNK_BYTES_B), kIdescTf32M128N64, acc);
             acc = 1;
         }
     }
 }
-
 #endif
 
 }  // namespace tc
