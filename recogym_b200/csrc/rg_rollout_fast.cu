@@ -64,7 +64,7 @@ __host__ inline void make_layout(Params &p) {
     const int KC = tc::kt_chunks(K);
     const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES_B;  // one 64-product B tile (hi + lo)
     const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
-    L.mbar = o; o += 8 * (kMaxStages + NBUF + 1);  // ring barriers, NBUF TMEM-full barriers, TMEM address word
+    L.mbar = o; o += 8 * (kMaxStages + 2 * NBUF + 1);  // ring, NBUF TMEM-full, NBUF TMEM-empty barriers, TMEM address
     L.om64 = o; if (!p.tc) o += 8 * TU * p.kp;
     L.csum = o; if (!p.tc) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
@@ -134,6 +134,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -190,7 +193,7 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
 #pragma unroll
     for (int f = 0; f < NB; ++f) sv[f] = shiftv[f < nb ? f : nb - 1];
     const int nch = (Ppad + CHUNK - 1) / CHUNK;
-    for (int c = warp; c < nch; c += NT / 32) {
+    for (int c = warp; c < nch; c += (int)(blockDim.x >> 5)) {
         double part[NB], perr[NB];
 #pragma unroll
         for (int f = 0; f < NB; ++f) { part[f] = 0.0; perr[f] = 0.0; }
@@ -272,7 +275,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         }
         sh_shift[tid] = v;
     }
-    for (int idx = tid; idx < FB * KP; idx += NT) {  // stage the omega rows of the batch (rows >= nb repeat the last)
+    for (int idx = tid; idx < FB * KP; idx += (int)blockDim.x) {  // stage the omega rows of the batch (rows >= nb repeat the last)
         const int f = idx / KP, k = idx - f * KP;
         om_s[idx] = k < K ? om64[(size_t)slots[f < nb ? f : nb - 1] * KP + k] : 0.0;
     }
@@ -416,7 +419,9 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
 }
 
 template <bool TC>
-__global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
+__global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const Params p) {
+    // TC: warp 8 is the TMA producer / MMA issuer of pass 1; it takes part in every other phase as a 9th worker
+    constexpr int NTH = TC ? NT + 32 : NT, NWARP = NTH / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const EnvDev &env = p.env;
     const Layout &L = p.L;
@@ -459,7 +464,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *gtile = (float *)(smem + L.gtile);
     float *a_tile = (float *)(smem + L.atile);
     uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
-    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + NBUF);
+    uint64_t *dempty = mbar + kMaxStages + NBUF;           // TC: accumulator tile drained by the 8 epilogue warps
+    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + 2 * NBUF);
     const int KC = env.KC;
     const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES_B;
 
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
-        if (TC) for (int b = 0; b < NBUF; ++b) mbar_init(&dfull[b], 1);
+        if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], 8); }
         fence_barrier_init();
         misc[1] = 0;
     }
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
         const int npend = misc[3], npairs = (K + 1) / 2;
-        for (int task = tid; task < npend * npairs; task += NT) {
+        for (int task = tid; task < npend * npairs; task += NTH) {
             const int slot = pend_list[task / npairs], j = task - (task / npairs) * npairs;
             const bool init = s_pend[slot] == 2;
             double *om = om64 + (size_t)slot * KP;
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
         // bytes with the B ring, so it is built after pass 1.)
         auto build_om32 = [&]() {
-            for (int idx = tid; idx < K1 * TU; idx += NT) {
+            for (int idx = tid; idx < K1 * TU; idx += NTH) {
                 const int k = idx / TU, i = idx - k * TU;
                 float v = 0.f;
                 if (i < nlive) v = (k < K) ? (float)om64[(size_t)pos2slot[i] * KP + k] : 1.f;
@@ -629,9 +635,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             // Thread 0 issues the three-term MMA of tile s+1 before the CTA runs the epilogue of tile s:
             // thread (lane quarter q, column half h) owns user 32q+lane and 64 columns; per logit the epilogue is
             // one ex2 and one add.
-            for (int idx = tid; idx < TU * p.nrec_pad; idx += NT) tilesum[idx] = 0.f;
+            for (int idx = tid; idx < TU * p.nrec_pad; idx += NTH) tilesum[idx] = 0.f;
             const int KT = KC * 4;
-            for (int idx = tid; idx < TU * KT; idx += NT) {
+            for (int idx = tid; idx < TU * KT; idx += NTH) {
                 const int row = idx / KT, k = idx - row * KT;
                 float x = 0.f;
                 if (row < nlive) {
@@ -650,31 +656,45 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
             const uint32_t a_saddr = tc::smem_addr(a_tile);
             const uint32_t ring_saddr = tc::smem_addr(gtile);
-            auto issue_mma = [&](unsigned gs) {  // thread 0: 64-product tile gs -> TMEM buffer gs % NBUF
-                const unsigned st = gs % (unsigned)nstage;
-                mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
-                tc::tc_fence_after();
-                tc::issue_tile_mmas(tmem_base + (gs % NBUF) * 64u, a_saddr, ring_saddr + st * tile_bytes, KC);
-                tc::umma_commit(&dfull[gs % NBUF]);
-            };
-            const int q = warp & 3, h = warp >> 2;
-            const int pos = q * 32 + lane;
-            const bool act = pos < nlive;
-            float part = 0.f;
-            int rec = 0;
-            if (tid == 0)
-                for (int j = 0; j < NBUF - 1 && j < ntile; ++j) issue_mma(seq_use + (unsigned)j);
-            for (int tt = 0; tt < ntile; ++tt) {
-                const unsigned gs = seq_use + (unsigned)tt;
-                if (tid == 0 && tt + NBUF - 1 < ntile) issue_mma(gs + (unsigned)(NBUF - 1));
-                mbar_wait(&dfull[gs % NBUF], (gs / NBUF) & 1u);
-                tc::tc_fence_after();
-                // MMA(gs) is complete: its ring stage is free for tile gs + nstage of this round
-                if (tid == 0 && tt + nstage < ntile) issue_load(gs + (unsigned)nstage);
+            if (warp == 8) {
+                // ---- producer / MMA issuer (one thread): B tile landed -> accumulator buffer drained -> three-term
+                // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
+                // has completed, i.e. independently of the epilogue.
+                if (lane == 0) {
+                    for (int tt = 0; tt < ntile; ++tt) {
+                        const unsigned gs = seq_use + (unsigned)tt;
+                        const unsigned st = gs % (unsigned)nstage, buf = gs % NBUF, use = gs / NBUF;
+                        mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
+                        if (use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
+                        tc::tc_fence_after();
+                        tc::issue_tile_mmas(tmem_base + buf * 64u, a_saddr, ring_saddr + st * tile_bytes, KC);
+                        tc::umma_commit(&dfull[buf]);
+                        if (tt > 0 && tt - 1 + nstage < ntile) {
+                            // MMA(gs-1) complete <=> dfull of its buffer completed its phase
+                            const unsigned gp = gs - 1u;
+                            mbar_wait(&dfull[gp % NBUF], (gp / NBUF) & 1u);
+                            issue_load(gp + (unsigned)nstage);
+                        }
+                    }
+                }
                 __syncwarp();
-                {
+            } else {
+                // ---- epilogue warps: thread (lane quarter q, column half h) owns user 32q+lane and 32 columns
+                const int q = warp & 3, h = warp >> 2;
+                const int pos = q * 32 + lane;
+                const bool act = pos < nlive;
+                float part = 0.f;
+                int rec = 0;
+                for (int tt = 0; tt < ntile; ++tt) {
+                    const unsigned gs = seq_use + (unsigned)tt;
+                    const unsigned buf = gs % NBUF;
+                    mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
+                    tc::tc_fence_after();
                     float v[32];
-                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (gs % NBUF) * 64u + (uint32_t)(h * 32), v);
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64u + (uint32_t)(h * 32), v);
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&dempty[buf]);  // this warp is done with the accumulator tile
                     if (act) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -684,15 +704,16 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         }
                         part += (s0 + s1) + (s2 + s3);
                     }
+                    if ((tt + 1) % (2 * p.rec_sub) == 0 || tt == ntile - 1) {
+                        if (act) atomicAdd(&tilesum[(size_t)pos * p.nrec_pad + rec], part);
+                        part = 0.f;
+                        ++rec;
+                    }
                 }
-                if ((tt + 1) % (2 * p.rec_sub) == 0 || tt == ntile - 1) {
-                    if (act) atomicAdd(&tilesum[(size_t)pos * p.nrec_pad + rec], part);
-                    part = 0.f;
-                    ++rec;
-                }
-                tc::tc_fence_before();
-                __syncthreads();  // TMEM buffer gs % NBUF may be overwritten by MMA(gs + NBUF)
             }
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
             seq_use += (unsigned)ntile;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
@@ -775,7 +796,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         __syncthreads();
 
         // ---- C: pass 2b, one warp per live user: recompute the located record tile, index and margins
-        for (int i = warp; i < nlive; i += NT / 32) {
+        for (int i = warp; i < nlive; i += NWARP) {
             const int slot = pos2slot[i];
             const double Z = s_Z[i], tau = s_tau[i];
             double cum = s_cum[i];
@@ -998,7 +1019,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
             __syncthreads();
             const int nban = misc[5];
-            for (int b = warp; b < nban; b += NT / 32) {
+            for (int b = warp; b < nban; b += NWARP) {
                 const int slot = amb_list[b];
                 const double *om = om64 + (size_t)slot * KP;
                 const uint64_t user = s_user[slot];
@@ -1164,7 +1185,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.om_scratch_bytes = need;
         }
         p.om_scratch = e.d_om_scratch;
-        rollout_cta_kernel<true><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+        rollout_cta_kernel<true><<<(unsigned)blocks, NT + 32, (size_t)p.L.total, stream>>>(p);
     } else {
         rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     }
