@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--users", type=int, default=0, help="users per GPU per step (default: workload's)")
-    ap.add_argument("--math", default="fast", choices=["fast", "exact", "tensor"])
+    ap.add_argument("--math", default="tensor", choices=["fast", "exact", "tensor"])
     ap.add_argument("--train-users", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -312,7 +312,7 @@ def main():
     line = {
         "metric": "simulated user-steps/sec", "value": value, "unit": "user-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tensor": "f64+tf32x2", "fast": "f64+f32", "exact": "f64"}[args.math],
         "data": "synthetic",
         "config": {"workload": wl["label"], "num_products": P, "K": K, "users_per_gpu_per_step": U,
                    "policy": wl["policy"], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
@@ -326,12 +326,24 @@ def main():
                      "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_user_step": alg_bytes,
                      "note": "fused rollout keeps user state on chip: HBM is not the physical bound (SURVEY.md 8d); "
-                             "see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32-fma", "achieved": per_gpu_steps_s * flops_per_step / 1e12,
-                          "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
-                          "frac": per_gpu_steps_s * flops_per_step / fp32_peak,
-                          "flops_per_user_step": flops_per_step},
+                             "see roofline_fp32 / roofline_mufu"},
     }
+    organic_per_s = float(ev[2]) / (total_ms * 1e-3) / world          # organic draws per second per GPU
+    if args.math == "tensor":
+        # tensor mode: the contraction is on tcgen05; the binding unit of pass 1 is the MUFU pipe
+        # (one ex2 per product per organic draw; 16 ex2/clk/SM)
+        mufu_peak = 148 * 16 * sm_max * 1e6
+        line["roofline_mufu"] = {"bound": "mufu-ex2", "achieved": organic_per_s * P / 1e12, "peak": mufu_peak / 1e12,
+                                 "unit": "Tex2/s", "frac": organic_per_s * P / mufu_peak,
+                                 "ex2_per_organic_draw": P}
+        line["roofline_tensor"] = {"bound": "tensor", "achieved": organic_per_s * 3 * 2.0 * P * (K + 2) / 1e12,
+                                   "peak": None, "unit": "TFLOP/s (tf32, three-term split)",
+                                   "note": "not the binding unit: <20% tensor-pipe active (profiles/)"}
+    else:
+        line["roofline_fp32"] = {"bound": "fp32-fma", "achieved": per_gpu_steps_s * flops_per_step / 1e12,
+                                 "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                                 "frac": per_gpu_steps_s * flops_per_step / fp32_peak,
+                                 "flops_per_user_step": flops_per_step}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],

@@ -155,10 +155,10 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     // tf32 hi/lo UMMA tiles of the tensor-core sampler (layout: rg_tensor.cuh)
     const int KC = rg::tc::kt_chunks(K);
     const size_t tile_floats = (size_t)2 * KC * (rg::tc::CHUNK_BYTES_B / 4);   // one 64-product tile, hi + lo
-    std::vector<float> GTC((size_t)nsub * 2 * tile_floats, 0.f);
+    std::vector<float> GTC((size_t)nsub * (128 / rg::tc::TILE_N) * tile_floats, 0.f);
     for (int p = 0; p < nsub * 128; ++p) {
-        float *tile = GTC.data() + (size_t)(p / 64) * tile_floats;
-        const int row = p % 64;
+        float *tile = GTC.data() + (size_t)(p / rg::tc::TILE_N) * tile_floats;
+        const int row = p % rg::tc::TILE_N;
         for (int k = 0; k < KC * 4; ++k) {
             float x = 0.f;
             if (p < P) {

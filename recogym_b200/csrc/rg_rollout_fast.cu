@@ -34,7 +34,7 @@ constexpr int SUB = 128;    // products per shared-memory tile
 constexpr int NT = 256;     // threads per CTA
 constexpr int CHUNK = 256;  // products per partial sum of the cooperative binary64 sampler
 constexpr int kMaxStages = 6;
-constexpr int NBUF = 3;      // tensor mode: accumulator tiles (64 TMEM columns each) in flight
+constexpr int NBUF = tc::TILE_N == 64 ? 3 : 2;  // tensor mode: accumulator tiles (TILE_N TMEM columns each) in flight
 constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampler
 
 struct Layout {  // byte offsets into dynamic shared memory
@@ -419,9 +419,10 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
 }
 
 template <bool TC>
-__global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const Params p) {
-    // TC: warp 8 is the TMA producer / MMA issuer of pass 1; it takes part in every other phase as a 9th worker
-    constexpr int NTH = TC ? NT + 32 : NT, NWARP = NTH / 32;
+__global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
+    // TC pass 1: warps 0-3 run the epilogue (thread = TMEM lane = user), warp 4 is the TMA producer / MMA issuer,
+    // warps 5-7 idle (288 threads would cap the kernel at 96 registers)
+    constexpr int NTH = NT, NWARP = NTH / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const EnvDev &env = p.env;
     const Layout &L = p.L;
@@ -464,23 +465,23 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
     float *gtile = (float *)(smem + L.gtile);
     float *a_tile = (float *)(smem + L.atile);
     uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
-    uint64_t *dempty = mbar + kMaxStages + NBUF;           // TC: accumulator tile drained by the 8 epilogue warps
+    uint64_t *dempty = mbar + kMaxStages + NBUF;           // TC: accumulator tile drained by the 4 epilogue warps
     uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + 2 * NBUF);
     const int KC = env.KC;
     const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES_B;
 
     const unsigned tile_bytes = TC ? tc_tile_bytes : (unsigned)(4 * K1 * SUB);
     const int nsub = env.nsub, nstage = p.nstage;
-    const int ntile = TC ? 2 * nsub : nsub;  // tiles streamed per round: 64 products (TC) or 128 (CUDA cores)
+    const int ntile = TC ? nsub * (128 / tc::TILE_N) : nsub;  // tiles streamed per round
 
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
-        if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], 8); }
+        if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], 4); }
         fence_barrier_init();
         misc[1] = 0;
     }
-    if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // NBUF 64-column accumulator tiles
+    if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // NBUF accumulator tiles of TILE_N columns
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
     unsigned long long n_fallback = 0, n_tier3 = 0;
     unsigned ambig64 = 0;
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
                 }
                 // relative mass error: exp of that, ex2.approx (2^-21 covers its 2 ulp), fp32 partial sums of pass 1
                 // fp32 partial sums of pass 1: longest chain of additions behind one record-tile sum
-                const double nadd = TC ? fmax(8.0 * p.rec_sub + 6.0, 2.0 * p.rec_sub + 20.0) : 8.0 * p.rec_sub + 6.0;
+                const double nadd = TC ? (double)(tc::TILE_N / 4 + 4 + p.rec_sub * (128 / tc::TILE_N)) : 8.0 * p.rec_sub + 6.0;
                 const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 + nadd * u24;
                 sh = (float)shift;
                 ep = (float)(2.0 * delta * 1.05 + 1e-7);
@@ -635,7 +636,6 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
             // Thread 0 issues the three-term MMA of tile s+1 before the CTA runs the epilogue of tile s:
             // thread (lane quarter q, column half h) owns user 32q+lane and 64 columns; per logit the epilogue is
             // one ex2 and one add.
-            for (int idx = tid; idx < TU * p.nrec_pad; idx += NTH) tilesum[idx] = 0.f;
             const int KT = KC * 4;
             for (int idx = tid; idx < TU * KT; idx += NTH) {
                 const int row = idx / KT, k = idx - row * KT;
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
 
             const uint32_t a_saddr = tc::smem_addr(a_tile);
             const uint32_t ring_saddr = tc::smem_addr(gtile);
-            if (warp == 8) {
+            if (warp == 4) {
                 // ---- producer / MMA issuer (one thread): B tile landed -> accumulator buffer drained -> three-term
                 // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
                 // has completed, i.e. independently of the epilogue.
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
                         mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
                         if (use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
                         tc::tc_fence_after();
-                        tc::issue_tile_mmas(tmem_base + buf * 64u, a_saddr, ring_saddr + st * tile_bytes, KC);
+                        tc::issue_tile_mmas(tmem_base + buf * (uint32_t)tc::TILE_N, a_saddr, ring_saddr + st * tile_bytes, KC);
                         tc::umma_commit(&dfull[buf]);
                         if (tt > 0 && tt - 1 + nstage < ntile) {
                             // MMA(gs-1) complete <=> dfull of its buffer completed its phase
@@ -678,9 +678,9 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
                     }
                 }
                 __syncwarp();
-            } else {
-                // ---- epilogue warps: thread (lane quarter q, column half h) owns user 32q+lane and 32 columns
-                const int q = warp & 3, h = warp >> 2;
+            } else if (warp < 4) {
+                // ---- epilogue warps: thread = TMEM lane = user 32*warp+lane, all TILE_N columns of every tile
+                const int q = warp;
                 const int pos = q * 32 + lane;
                 const bool act = pos < nlive;
                 float part = 0.f;
@@ -690,22 +690,29 @@ __global__ void __launch_bounds__(TC ? NT + 32 : NT, 2) rollout_cta_kernel(const
                     const unsigned buf = gs % NBUF;
                     mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
                     tc::tc_fence_after();
-                    float v[32];
-                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64u + (uint32_t)(h * 32), v);
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&dempty[buf]);  // this warp is done with the accumulator tile
-                    if (act) {
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    constexpr int HALF = tc::TILE_N;  // columns of this thread (the whole tile row)
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]);
-                            s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
+                    for (int c = 0; c < HALF; c += 32) {
+                        float v[32];
+                        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)tc::TILE_N +
+                                          (uint32_t)c, v);
+                        if (c + 32 >= HALF) {  // last read of this tile: hand the accumulator back before the math
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&dempty[buf]);
                         }
-                        part += (s0 + s1) + (s2 + s3);
+                        if (act) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]);
+                                s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
+                            }
+                        }
                     }
-                    if ((tt + 1) % (2 * p.rec_sub) == 0 || tt == ntile - 1) {
-                        if (act) atomicAdd(&tilesum[(size_t)pos * p.nrec_pad + rec], part);
+                    part += (s0 + s1) + (s2 + s3);
+                    if ((tt + 1) % (p.rec_sub * (128 / tc::TILE_N)) == 0 || tt == ntile - 1) {
+                        if (act) tilesum[(size_t)pos * p.nrec_pad + rec] = part;
                         part = 0.f;
                         ++rec;
                     }
@@ -1185,7 +1192,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.om_scratch_bytes = need;
         }
         p.om_scratch = e.d_om_scratch;
-        rollout_cta_kernel<true><<<(unsigned)blocks, NT + 32, (size_t)p.L.total, stream>>>(p);
+        rollout_cta_kernel<true><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     } else {
         rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     }

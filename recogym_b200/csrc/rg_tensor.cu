@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 64);
+    if (warp == 0) tmem_alloc(tmem_slot, TILE_N);
     build_a_tile(a_tile, KC, K, omega, K, shift, TILE, tid, 128);
     fence_proxy_async();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    for (int sub = 0; sub < 2 * nsub; ++sub) {  // 64-product tiles
+    for (int sub = 0; sub < nsub * (128 / TILE_N); ++sub) {  // TILE_N-product tiles
         const unsigned parity = (unsigned)sub & 1u;
         if (tid == 0) {
             mbar_expect_tx(&bars[0], tile_bytes);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
         __syncthreads();  // TMEM tile and B tile are free again
         tc_fence_after();
     }
-    if (warp == 0) tmem_dealloc(tmem_base, 64);
+    if (warp == 0) tmem_dealloc(tmem_base, TILE_N);
 }
 
 }  // namespace tc

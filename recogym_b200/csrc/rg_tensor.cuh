@@ -20,9 +20,12 @@ namespace rg {
 namespace tc {
 
 constexpr int TILE = 128;            // users per tile (UMMA M)
-constexpr int TILE_N = 64;           // products per tile (UMMA N)
+#ifndef RG_TC_TILE_N
+#define RG_TC_TILE_N 128
+#endif
+constexpr int TILE_N = RG_TC_TILE_N; // products per tile (UMMA N): 64 or 128
 constexpr int CHUNK_BYTES = 2048;    // A: one 16-byte K chunk of all 128 rows
-constexpr int CHUNK_BYTES_B = 1024;  // B: one 16-byte K chunk of all 64 rows
+constexpr int CHUNK_BYTES_B = TILE_N / 8 * 128;  // B: one 16-byte K chunk of all TILE_N rows
 
 __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks (even: one MMA eats two)
     int kc = (K + 2 + 3) / 4;
@@ -41,7 +44,7 @@ __host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {  /
     return ((((size_t)t * KC + (k >> 2)) * 16 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
 }
 __host__ __device__ inline size_t tile_index_b(int t, int KC, int row, int k) {  // B: 64 rows
-    return ((((size_t)t * KC + (k >> 2)) * 8 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+    return ((((size_t)t * KC + (k >> 2)) * (TILE_N / 8) + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
 }
 
 #if defined(__CUDACC__)
@@ -53,7 +56,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            (1ull << 46);
 }
 // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdescTf32M128N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)TILE_N >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
@@ -117,7 +120,7 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_d, uint32_t a_sadd
         const uint32_t b0 = b_saddr + (pair == 1 ? bterm : 0u);
         for (int s = 0; s < KC / 2; ++s) {
             umma_tf32(tmem_d, umma_desc(a0 + (uint32_t)s * 2u * CHUNK_BYTES, CHUNK_BYTES),
-                      umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES_B, CHUNK_BYTES_B), kIdescTf32M128N64, acc);
+                      umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES_B, CHUNK_BYTES_B), kIdescTf32, acc);
             acc = 1;
         }
     }

@@ -12,9 +12,9 @@ timeout -k 10 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpu
 echo "== smoke"
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_$TAG.log
 echo "== bench fast"
-timeout -k 10 900 python bench.py --steps 3 --warmup 3 --users $USERS --math fast 2>&1 | tail -3 | tee gpurun_out/bench_$TAG.log
+timeout -k 10 900 python bench.py --steps 3 --warmup 3 --users $USERS --math fast --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_$TAG.log
 echo "== bench tensor"
-timeout -k 10 900 python bench.py --steps 3 --warmup 3 --users $USERS --math tensor --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_tensor_$TAG.log
+timeout -k 10 900 python bench.py --steps 3 --warmup 3 --users $USERS --math tensor 2>&1 | tail -3 | tee gpurun_out/bench_tensor_$TAG.log
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rollout -c 12 --csv \
