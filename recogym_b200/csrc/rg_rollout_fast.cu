@@ -39,7 +39,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, ptau, pcum, prsel, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
 
@@ -51,6 +51,7 @@ struct Params {
     unsigned long long *queue;
     int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
     int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
+    int async2;             // tc: tier 2/3 re-sampling runs on warps 5-7 underneath the next round's pass 1
     double *om_scratch;     // tc: the binary64 omega rows live in global memory, [grid][TU][kp]
     Layout L;
 };
@@ -66,14 +67,17 @@ __host__ inline void make_layout(Params &p) {
     const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
     L.mbar = o; o += 8 * (kMaxStages + 2 * NBUF + 1);  // ring, NBUF TMEM-full, NBUF TMEM-empty barriers, TMEM address
     L.om64 = o; if (!p.tc) o += 8 * TU * p.kp;
-    L.csum = o; if (!p.tc) o += 8 * p.ncs * FB * 2;
+    L.csum = o; if (!p.tc || p.async2) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
     L.fb_om = o; o += 8 * FB * p.kp;
-    L.lse = o; o += 8 * TU;
-    L.pz = o; o += 8 * TU;
-    L.ptau = o; o += 8 * TU;
-    L.pcum = o; o += 8 * TU;
+    L.lse = o; if (!p.tc) o += 8 * TU;
+    L.pz = o; if (!p.tc) o += 8 * TU;
+    L.pu = o; if (!p.tc) o += 8 * TU;
+    L.rq_u = o; o += 8 * TU;
+    L.rq_lse = o; o += 8 * TU;
+    L.ptau = o; if (!p.tc) o += 8 * TU;
+    L.pcum = o; if (!p.tc) o += 8 * TU;
     L.user = o; o += 8 * TU;
     L.hash = o; o += 8 * TU;
     L.t = o; o += 4 * TU;
@@ -92,6 +96,8 @@ __host__ inline void make_layout(Params &p) {
     L.fb_pos = o; o += 4 * FB;
     L.fb_unres = o; o += 4 * FB;
     L.prsel = o; o += 4 * TU;
+    L.wait = o; o += 4 * TU;
+    L.rq_slot = o; o += 4 * TU;
     L.pend = o; o += 4 * TU;
     L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
@@ -107,10 +113,13 @@ __host__ inline void make_layout(Params &p) {
         // the B ring is idle between pass 1 and the next round's first load: the fp32 omega tile of pass 2 and
         // the partial sums of the re-sampling sweeps live in the same bytes
         int ring = p.nstage * tc_tile_bytes;
-        const int alias = align_up(4 * K1 * TU, 16) + 8 * p.ncs * FB * 2;
+        const int om32_bytes = align_up(4 * K1 * TU, 16);
+        const int alias = om32_bytes + 5 * 8 * TU + (p.async2 ? 0 : 8 * p.ncs * FB * 2);
         if (alias > ring) ring = align_up(alias, 128);
         L.om32 = o;
-        L.csum = o + align_up(4 * K1 * TU, 16);
+        L.lse = o + om32_bytes;
+        L.pz = L.lse + 8 * TU; L.pu = L.pz + 8 * TU; L.ptau = L.pu + 8 * TU; L.pcum = L.ptau + 8 * TU;
+        if (!p.async2) L.csum = L.pcum + 8 * TU;
         o += ring;
         L.atile = o; o += tc_a_bytes;
     }
@@ -185,7 +194,7 @@ __device__ __forceinline__ void thread_omega_update(double *omega, int K, double
 template <int NB, int PP, bool T2>
 __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const double *om_s, int KP, double *csum,
                                                    double *esum, int ncs, int nb, const double *shiftv, int lane,
-                                                   int warp) {
+                                                   int warp, int nwarps) {
     // om_s: the omega rows of the batch staged in shared memory, [FB][KP].  Each lane carries PP products x NB
     // users = PP*NB independent fma chains and PP loads in flight per k (the sweep is latency bound otherwise).
     const int K = env.K, P = env.P, Ppad = env.Ppad;
@@ -193,7 +202,7 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
 #pragma unroll
     for (int f = 0; f < NB; ++f) sv[f] = shiftv[f < nb ? f : nb - 1];
     const int nch = (Ppad + CHUNK - 1) / CHUNK;
-    for (int c = warp; c < nch; c += (int)(blockDim.x >> 5)) {
+    for (int c = warp; c < nch; c += nwarps) {
         double part[NB], perr[NB];
 #pragma unroll
         for (int f = 0; f < NB; ++f) { part[f] = 0.0; perr[f] = 0.0; }
@@ -255,10 +264,16 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
 template <bool T2>
 __device__ __noinline__ void block_sample_views(const EnvDev &env, const double *om64, int KP, double *csum, int ncs,
                                                 const int *slots, const double *us, const double *lse, int nb,
-                                                int *s_view, int *unresolved, double *om_s, int tid,
-                                                unsigned &ambig) {
+                                                int *s_view, int *unresolved, double *om_s, int tid, int gn,
+                                                int bar_id, unsigned &ambig) {
+    // Called by a GROUP of gn threads (tid = index inside the group): the whole CTA (bar_id 0, __syncthreads)
+    // or the three idle warps of the tensor-core pass 1 (named barrier bar_id).
     const int K = env.K, P = env.P, Ppad = env.Ppad;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = gn >> 5;
+    auto gsync = [&]() {
+        if (bar_id == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gn) : "memory");
+    };
     double *esum = csum + (size_t)FB * ncs;
     __shared__ double sh_shift[FB];
     if (tid < FB) {
@@ -275,24 +290,23 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         }
         sh_shift[tid] = v;
     }
-    for (int idx = tid; idx < FB * KP; idx += (int)blockDim.x) {  // stage the omega rows of the batch (rows >= nb repeat the last)
+    for (int idx = tid; idx < FB * KP; idx += gn) {  // stage the omega rows of the batch (rows >= nb repeat the last)
         const int f = idx / KP, k = idx - f * KP;
         om_s[idx] = k < K ? om64[(size_t)slots[f < nb ? f : nb - 1] * KP + k] : 0.0;
     }
-    __syncthreads();
+    gsync();
     switch (nb) {
-        case 1: batch_partial_sums<1, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 2: batch_partial_sums<2, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 3: batch_partial_sums<3, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 4: batch_partial_sums<4, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 5: batch_partial_sums<5, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 6: batch_partial_sums<6, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        case 7: batch_partial_sums<7, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
-        default: batch_partial_sums<8, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp); break;
+        case 1: batch_partial_sums<1, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 2: batch_partial_sums<2, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 3: batch_partial_sums<3, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 4: batch_partial_sums<4, 4, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 5: batch_partial_sums<5, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 6: batch_partial_sums<6, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        case 7: batch_partial_sums<7, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
+        default: batch_partial_sums<8, 2, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
     }
-    __syncthreads();
-    if (warp < nb) {
-        const int f = warp;
+    gsync();
+    for (int f = warp; f < nb; f += nwarps) {
         const double *omega = om_s + (size_t)f * KP;
         const double *cs = csum + (size_t)f * ncs;
         const double sf = sh_shift[f];
@@ -415,7 +429,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
             }
         }
     }
-    __syncthreads();
+    gsync();
 }
 
 template <bool TC>
@@ -452,6 +466,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     double *fb_om = (double *)(smem + L.fb_om);
     double *s_lse = (double *)(smem + L.lse);  // log2-sum-exp of the fp32 pass, per position (ambiguous draws)
     double *s_Z = (double *)(smem + L.pz);
+    double *s_u = (double *)(smem + L.pu);
+    double *rq_u = (double *)(smem + L.rq_u);       // re-sampling queues [2][TU] (double-buffered by round parity)
+    double *rq_lse = (double *)(smem + L.rq_lse);
+    int *rq_slot = (int *)(smem + L.rq_slot);
+    int *s_wait = (int *)(smem + L.wait);           // 0 none, 2 queued this round, 1 being re-sampled this round
     double *s_tau = (double *)(smem + L.ptau);
     double *s_cum = (double *)(smem + L.pcum);
     int *s_rsel = (int *)(smem + L.prsel);
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         s_last_view[slot] = -1;
         s_n_org[slot] = 0; s_n_ban[slot] = 0; s_n_clk[slot] = 0;
         s_live[slot] = 1;
+        s_wait[slot] = 0;
         s_pend[slot] = 2;  // omega = sigma0 * z(user, 0) (reco_env_v1.py:80-82), done by omega_phase()
         return true;
     };
@@ -534,7 +554,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         __syncthreads();
         if (tid < TU) s_pend[tid] = 0;
     };
-    if (tid < TU) { s_pend[tid] = 0; claim(tid); }
+    if (tid < TU) { s_pend[tid] = 0; s_wait[tid] = 0; claim(tid); }
+    if (tid == 0) misc[6] = 0;
+    const bool ASYNC = TC && p.async2 != 0;
     __syncthreads();
     omega_phase();
     __syncthreads();
@@ -573,7 +595,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             int base = 0;
             for (int c = 0; c < TU / 32; ++c) {
                 const int slot = c * 32 + lane;
-                const bool lv = s_live[slot] != 0;
+                if (s_wait[slot] == 2) s_wait[slot] = 1;  // queued last round: re-sampled during this pass 1
+                const bool lv = s_live[slot] != 0 && s_wait[slot] == 0;
                 const unsigned m = __ballot_sync(0xffffffffu, lv);
                 if (lv) pos2slot[base + __popc(m & ((1u << lane) - 1u))] = slot;
                 base += __popc(m);
@@ -582,7 +605,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
         const int nlive = misc[0];
-        if (nlive == 0) break;
+        const int nq = misc[6];  // draws queued in the previous round
+        if (nlive == 0 && nq == 0) break;
 
         // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
         // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
@@ -678,6 +702,41 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     }
                 }
                 __syncwarp();
+            } else if (warp >= 5) {
+                // ---- re-sampling warps: the draws queued in the previous round, tier 2 then tier 3, on the
+                // (otherwise idle) FP64 pipe while warps 0-4 stream the contraction of this round
+                if (ASYNC) {
+                    const int gtid = tid - 5 * 32, gn = 3 * 32;
+                    const int *qs = rq_slot;
+                    const double *qu = rq_u, *ql = rq_lse;
+                    for (int b0 = 0; b0 < nq; b0 += FB) {
+                        int nb = min(FB, nq - b0);
+                        if (gtid < nb) {
+                            fb_slot[gtid] = qs[b0 + gtid];
+                            fb_u[gtid] = qu[b0 + gtid];
+                            fb_lse[gtid] = ql[b0 + gtid];
+                            fb_unres[gtid] = 0;
+                        }
+                        asm volatile("bar.sync 1, 96;" ::: "memory");
+                        block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
+                                                 fb_om, gtid, gn, 1, ambig64);
+                        if (gtid == 0) {  // compact the draws tier 2 left open (serial: at most FB entries)
+                            int n3 = 0;
+                            for (int f = 0; f < nb; ++f)
+                                if (fb_unres[f]) { fb_slot[n3] = fb_slot[f]; fb_u[n3] = fb_u[f]; ++n3; }
+                            misc[8] = n3;
+                            n_fallback += (unsigned long long)nb;
+                            n_tier3 += (unsigned long long)n3;
+                        }
+                        asm volatile("bar.sync 1, 96;" ::: "memory");
+                        const int n3 = misc[8];
+                        if (n3 > 0)
+                            block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, n3, s_view,
+                                                      fb_unres, fb_om, gtid, gn, 1, ambig64);
+                        asm volatile("bar.sync 1, 96;" ::: "memory");
+                    }
+                    for (int e = gtid; e < nq; e += gn) s_wait[qs[e]] = 0;  // their views are in s_view: advance in D
+                }
             } else if (warp < 4) {
                 // ---- epilogue warps: thread = TMEM lane = user 32*warp+lane, all TILE_N columns of every tile
                 const int q = warp;
@@ -721,6 +780,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             tc::tc_fence_before();
             __syncthreads();
             tc::tc_fence_after();
+            if (tid == 0) misc[6] = 0;  // the queue has been consumed; pass 2b refills it (after the next barrier)
             seq_use += (unsigned)ntile;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
@@ -798,7 +858,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 if (nx > tau) { rsel = r; break; }
                 cum = nx;
             }
-            s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel;
+            s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel; s_u[i] = u;
         }
         __syncthreads();
 
@@ -884,8 +944,15 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             if (lane == 0) {
                 s_view[slot] = found;
                 if (amb) {
-                    amb_list[atomicAdd(&misc[1], 1)] = i;
-                    s_lse[i] = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
+                    const double lse = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
+                    if (ASYNC) {  // re-sampled underneath the next round's pass 1; the slot sits that round out
+                        const int e = atomicAdd(&misc[6], 1);
+                        rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
+                        s_wait[slot] = 2;
+                    } else {
+                        amb_list[atomicAdd(&misc[1], 1)] = i;
+                        s_lse[i] = lse;
+                    }
                 }
             }
         }
@@ -915,11 +982,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     __syncthreads();
                     if (tier == 2) {
                         block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
-                                                 fb_om, tid, ambig64);
+                                                 fb_om, tid, NTH, 0, ambig64);
                         if (tid < nb && fb_unres[tid]) pend_list[atomicAdd(&misc[4], 1)] = fb_pos[tid];
                     } else {
                         block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view,
-                                                  fb_unres, fb_om, tid, ambig64);
+                                                  fb_unres, fb_om, tid, NTH, 0, ambig64);
                     }
                     __syncthreads();
                 }
@@ -962,7 +1029,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             claim(slot);
         };
         const bool serial_bandit = env.change_omega_for_bandits != 0;
-        if (tid < TU && s_live[tid]) {
+        if (tid < TU && s_live[tid] && s_wait[tid] == 0) {
             const int slot = tid;
             double *om = om64 + (size_t)slot * KP;
             const uint64_t user = s_user[slot];
@@ -1133,6 +1200,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.n_total = n_total;
     p.out = out;
     p.tc = tensor ? 1 : 0;
+    p.async2 = tensor ? 1 : 0;
     p.om_scratch = nullptr;
     const int K1 = e.dev.K + 1;
     p.kp = e.dev.K | 1;  // odd row stride of the binary64 omega rows: conflict-free per-slot access
@@ -1146,18 +1214,18 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.nrec = (nsub + rec_sub - 1) / rec_sub;
     p.nrec_pad = p.nrec | 1;
     // ring depth: as deep as shared memory allows (2 CTAs/SM when possible)
-    int best_stage = 0;
     const int hi_stage = tensor ? kMaxStages : 3, lo_stage = tensor ? NBUF : 2;
-    for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
-        p.nstage = nstage;
-        make_layout(p);
-        if (p.L.total <= 110 * 1024) best_stage = nstage;
-    }
-    if (!best_stage) {
-        for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
-            p.nstage = nstage;
-            make_layout(p);
-            if (p.L.total <= 227 * 1024) best_stage = nstage;
+    const int two_ctas = 113 * 1024;  // (228 KB - 1 KB reserved per CTA) / 2
+    int best_stage = 0;
+    for (int pass = 0; pass < 2 && !best_stage; ++pass) {
+        const int limit = pass == 0 ? two_ctas : 227 * 1024;
+        for (int a2 = tensor ? 1 : 0; a2 >= 0 && !best_stage; --a2) {
+            p.async2 = a2;
+            for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
+                p.nstage = nstage;
+                make_layout(p);
+                if (p.L.total <= limit) best_stage = nstage;
+            }
         }
     }
     if (!best_stage && tensor) {
@@ -1177,7 +1245,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     cudaError_t ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
                             : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
     if (ce != cudaSuccess) return ce;
-    int ctas_per_sm = p.L.total <= 110 * 1024 ? 2 : 1;
+    int ctas_per_sm = p.L.total <= two_ctas ? 2 : 1;
     long long blocks = (n_total + TU - 1) / TU;
     const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
     if (blocks > max_blocks) blocks = max_blocks;
