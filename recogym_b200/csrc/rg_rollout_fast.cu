@@ -22,6 +22,8 @@
 //           user id from a global queue.
 //
 // All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
+#include <cstdlib>
+
 #include "rg_device.cuh"
 #include "rg_host.h"
 #include "rg_tensor.cuh"
@@ -1219,7 +1221,10 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     int best_stage = 0;
     for (int pass = 0; pass < 2 && !best_stage; ++pass) {
         const int limit = pass == 0 ? two_ctas : 227 * 1024;
-        for (int a2 = tensor ? 1 : 0; a2 >= 0 && !best_stage; --a2) {
+        // asynchronous re-sampling (warps 5-7 underneath pass 1) is correct but measured SLOWER at C3 (3.2e8 vs
+        // 4.1e8 steps/s: three warps take longer over the sweep than pass 1 lasts); opt-in via RG_ASYNC_RESAMPLE=1
+        static const bool want_async = [] { const char *v = getenv("RG_ASYNC_RESAMPLE"); return v && v[0] == '1'; }();
+        for (int a2 = (tensor && want_async) ? 1 : 0; a2 >= 0 && !best_stage; --a2) {
             p.async2 = a2;
             for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
                 p.nstage = nstage;
