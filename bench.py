@@ -49,6 +49,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def measured_traffic(user_steps_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the committed ncu --set full
+    capture (profiles/r01_roofline_traffic.json), scaled from the captured launch to this launch's size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
+        per_step = (t["dram_bytes_read"] + t["dram_bytes_write"]) / float(t["user_steps_in_captured_launch"])
+        return per_step * user_steps_per_launch
+    except Exception:
+        return None
+
+
 def static_params(P, K):
     import recogym_b200 as rg
     from recogym_b200.envs.static_params import draw_static_params
@@ -323,7 +334,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_gbs / hbm_peak, "traffic": measured_traffic(launch_events), "peak_source": peak_src,
                      "algorithmic_bytes_per_user_step": alg_bytes,
                      "note": "fused rollout keeps user state on chip: HBM is not the physical bound (SURVEY.md 8d); "
                              "see roofline_fp32 / roofline_mufu"},
