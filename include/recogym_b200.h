@@ -98,6 +98,14 @@ typedef struct rg_rollout_out {
     int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
                             [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] binary64-ambiguous
                             samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, rest reserved */
+    /* Event log == the rows of the generate_logs DataFrame (abstract.py:256-327), unordered: one int32x4
+     * record {u = user_id - user_begin, t, x = product viewed | action, flags} per row, flags bit 0: z
+     * (0 organic, 1 bandit), bit 1: click, bit 2: phantom row after done (abstract.py:311-316).  Rows of one
+     * user have distinct t, so sorting by (u, t) restores the reference order.  *log_count accumulates the
+     * rows produced; rows beyond log_capacity are dropped (call again with a larger buffer). */
+    int32_t *log;        /* [log_capacity][4] or NULL */
+    int64_t log_capacity;
+    int64_t *log_count;  /* [1] */
 } rg_rollout_out;
 
 /* AbstractEnv.generate_logs(num_offline_users=n_users, agent, num_organic_offline_users=

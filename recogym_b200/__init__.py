@@ -5,7 +5,8 @@ value types, env args, enums, `test_agent`, `verify_agents`, `evaluate_agent`, `
 and `make('reco-gym-v1')` in place of gym's registry (gym is not a dependency).
 """
 from .envs import (Configuration, Context, DefaultContext, Observation, Session, OrganicSessions, RecoEnv1,
-                   env_args, env_1_args, DeviceEnv, BatchState, DefaultTimeGenerator, NormalTimeGenerator)
+                   env_args, env_1_args, DeviceEnv, BatchState, rollout_log, DefaultTimeGenerator,
+                   NormalTimeGenerator)
 from .constants import AgentStats, AgentInit, EvolutionCase, TrainingApproach, RoiMetrics
 from .bench_agents import test_agent
 from .evaluate_agent import evaluate_agent, build_agent_init, verify_agents

@@ -40,7 +40,8 @@ class Policy(C.Structure):
 class RolloutOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "n_events", "n_organic", "n_bandit", "n_clicks", "last_view", "hash", "omega",
-        "view_hist", "action_hist", "click_hist", "totals")]
+        "view_hist", "action_hist", "click_hist", "totals")] + [
+        ("log", C.c_void_p), ("log_capacity", C.c_int64), ("log_count", C.c_void_p)]
 
 
 _lib = None

@@ -58,4 +58,5 @@ class BanditCount(Agent):
         pass
 
     def device_policy(self):
-        return {"policy": "table", "table": self.ctr.argmax(axis=1).astype(np.int32)}
+        table = self.ctr.argmax(axis=1).astype(np.int32)
+        return {"policy": "table", "table": table, "ps_table": self.ctr[np.arange(len(table)), table]}

@@ -51,6 +51,9 @@ rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
     d.action_hist = (unsigned long long *)o.action_hist;
     d.click_hist = (unsigned long long *)o.click_hist;
     d.totals = (unsigned long long *)o.totals;
+    d.log = (o.log && o.log_count && o.log_capacity > 0) ? (int4 *)o.log : nullptr;
+    d.log_capacity = d.log ? o.log_capacity : 0;
+    d.log_count = (unsigned long long *)o.log_count;
     return d;
 }
 
@@ -271,6 +274,9 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     const size_t o_om = add(out->omega, 8 * (size_t)n * K, false);
     const size_t o_vh = add(out->view_hist, 8 * (size_t)P, true), o_ah = add(out->action_hist, 8 * (size_t)P, true);
     const size_t o_ch = add(out->click_hist, 8 * (size_t)P, true), o_t = add(out->totals, 8 * 16, true);
+    const size_t o_log = add(out->log && out->log_count && out->log_capacity > 0 ? out->log : nullptr,
+                             16 * (size_t)(out->log_capacity > 0 ? out->log_capacity : 0), false);
+    const size_t o_lc = add(out->log && out->log_count ? out->log_count : nullptr, 8, true);
     const size_t o_tab = total;
     if (policy->kind == RG_POLICY_TABLE) total += ((size_t)4 * P + 255) & ~(size_t)255;
     char *arena = nullptr;
@@ -295,6 +301,11 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     if (out->action_hist) dv.action_hist = (int64_t *)(arena + o_ah);
     if (out->click_hist) dv.click_hist = (int64_t *)(arena + o_ch);
     if (out->totals) dv.totals = (int64_t *)(arena + o_t);
+    if (out->log && out->log_count && out->log_capacity > 0) {
+        dv.log = (int32_t *)(arena + o_log);
+        dv.log_capacity = out->log_capacity;
+        dv.log_count = (int64_t *)(arena + o_lc);
+    }
     if (ce == cudaSuccess) {
         rc = rg_rollout_device(env, &pd, user_begin, n_organic_users, n_users, &dv, math_mode, nullptr);
         if (rc != RG_OK) { cudaFree(arena); return rc; }

@@ -40,7 +40,19 @@ struct RolloutOutDev {
     uint64_t *hash;
     double *omega;
     unsigned long long *view_hist, *action_hist, *click_hist, *totals;
+    int4 *log;                     // event log records {u, t, x, flags}
+    long long log_capacity;
+    unsigned long long *log_count;
 };
+
+// append n consecutive log rows: returns the first row index (rows >= capacity must not be written)
+__device__ __forceinline__ unsigned long long log_reserve(const RolloutOutDev &out, int n) {
+    return atomicAdd(out.log_count, (unsigned long long)n);
+}
+__device__ __forceinline__ void log_write(const RolloutOutDev &out, unsigned long long row, long long u, uint32_t t,
+                                          int x, int flags) {
+    if (row < (unsigned long long)out.log_capacity) out.log[row] = make_int4((int)u, (int)t, x, flags);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -91,9 +91,11 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
                 n_org += 1;
                 h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
                 if (out.view_hist && lane == 0) atomicAdd(out.view_hist + v, 1ull);
+                if (out.log && lane == 0) log_write(out, log_reserve(out, 1), i, t - 1u, v, 0);
             } else if (state == RG_BANDIT && !organic_only) {
                 const int a = policy_action(env, pol, user, t, last_view);
                 const int c = bandit_event(env, wc, user, a, state, t, lane);
+                if (out.log && lane == 0) log_write(out, log_reserve(out, 1), i, t - 1u, a, 1 | (c << 1));
                 n_ban += 1;
                 n_clk += c;
                 h = hash_fold(h, ((uint64_t)(uint32_t)a << 2) | ((uint64_t)c << 1) | 1u);
@@ -106,6 +108,8 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
             }
         }
         h = hash_fold(h, ((uint64_t)t << 2) | 3u);
+        if (out.log && lane == 0 && !organic_only)  // phantom action after done (abstract.py:311-316), reward 0
+            log_write(out, log_reserve(out, 1), i, t, policy_action(env, pol, user, t, last_view), 1 | 4);
         if (lane == 0) {
             if (out.n_events) out.n_events[i] = (int32_t)t;
             if (out.n_organic) out.n_organic[i] = n_org;

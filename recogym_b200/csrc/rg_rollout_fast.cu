@@ -1028,6 +1028,12 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 for (int k = 0; k < K; ++k) p.out.omega[(size_t)idx * K + k] = om[k];
             tot_users += 1; tot_events += t; tot_org += n_org; tot_ban += n_ban; tot_clk += n_clk;
             tot_ph += idx < p.n_organic_users ? 0 : 1;
+            if (p.out.log && idx >= p.n_organic_users) {  // phantom action after done (abstract.py:311-316)
+                int a;
+                if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
+                else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
+                log_write(p.out, log_reserve(p.out, 1), idx, t, a, 1 | 4);
+            }
             claim(slot);
         };
         const bool serial_bandit = env.change_omega_for_bandits != 0;
@@ -1045,6 +1051,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 n_org += 1;
                 h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
                 if (p.out.view_hist) atomicAdd(p.out.view_hist + v, 1ull);
+                if (p.out.log) log_write(p.out, log_reserve(p.out, 1), (long long)user - p.user_begin, t, v, 0);
             }
             const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
             int st = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
@@ -1061,6 +1068,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 int c = 0;
                 if (uc >= 0.9706) c = click_from_uniform(ctr_of_action(env, om, a), uc);
                 st = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
+                if (p.out.log) log_write(p.out, log_reserve(p.out, 1), (long long)user - p.user_begin, t, a, 1 | (c << 1));
                 t += 1;
                 if (st == RG_ORGANIC) pend = 1;  // the loop ends here: deferred
                 else thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
@@ -1120,6 +1128,13 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     const int nev = m ? __ffs(m) : 32;  // events of this turn that really happen
                     const uint64_t rec = ((uint64_t)(uint32_t)a << 2) | ((uint64_t)c << 1) | 1u;
                     for (int j = 0; j < nev; ++j) h = hash_fold(h, __shfl_sync(0xffffffffu, rec, j));
+                    if (p.out.log) {  // one reservation per turn, lane j writes the row of its event
+                        unsigned long long row0 = 0;
+                        if (lane == 0) row0 = log_reserve(p.out, nev);
+                        row0 = __shfl_sync(0xffffffffu, row0, 0);
+                        if (lane < nev)
+                            log_write(p.out, row0 + (unsigned long long)lane, (long long)user - p.user_begin, tt, a, 1 | (c << 1));
+                    }
                     if (lane < nev) {
                         if (p.out.action_hist) atomicAdd(p.out.action_hist + a, 1ull);
                         if (c && p.out.click_hist) atomicAdd(p.out.click_hist + a, 1ull);

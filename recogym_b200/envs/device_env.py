@@ -161,6 +161,59 @@ class DeviceEnv:
         return res
 
 
+def _policy_struct(keep, policy, table, P, host):
+    pol = L.Policy()
+    if policy == "uniform":
+        pol.kind = L.POLICY_UNIFORM
+    elif policy == "table":
+        pol.kind = L.POLICY_TABLE
+        if host:
+            t = np.ascontiguousarray(table, np.int32)
+            assert t.shape == (P,)
+            pol.table = t.ctypes.data
+        else:
+            torch = _torch()
+            t = table if (hasattr(table, "is_cuda") and table.is_cuda) else None
+            assert t is not None and t.dtype == torch.int32 and t.numel() == P
+            pol.table = t.data_ptr()
+        keep.append(t)
+    else:
+        raise ValueError("unknown policy %r" % (policy,))
+    return pol
+
+
+def rollout_log(env, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
+                math_mode=L.MATH_TENSOR, rows_per_user=110.0):
+    """The rows of AbstractEnv.generate_logs (abstract.py:241-327) for users user_begin.., produced by ONE fused
+    rollout (event-log output of the kernels) and sorted into the reference order on the host.
+    Returns a dict of numpy arrays: u, t, z (0 organic / 1 bandit), v, a, c (-1 where the reference has NaN)."""
+    n = int(n_users) + int(n_organic_users)
+    cap = int(n * rows_per_user) + 4096
+    keep = []
+    while True:
+        log = np.empty((cap, 4), np.int32)
+        count = np.zeros(1, np.int64)
+        totals = np.zeros(16, np.int64)
+        out = L.RolloutOut()
+        out.totals = totals.ctypes.data
+        out.log, out.log_capacity, out.log_count = log.ctypes.data, cap, count.ctypes.data
+        pol = _policy_struct(keep, policy, table, env.P, host=True)
+        L.check(L.lib().rg_rollout_host(env._h, C.byref(pol), int(user_begin), int(n_organic_users), int(n_users),
+                                        C.byref(out), int(math_mode)))
+        rows = int(count[0])
+        if rows <= cap:
+            break
+        cap = rows + 1024  # the buffer was too small: the rows are a pure function of the inputs, run again
+    log = log[:rows]
+    order = np.lexsort((log[:, 1], log[:, 0]))
+    log = log[order]
+    z = (log[:, 3] & 1).astype(np.int8)
+    click = ((log[:, 3] >> 1) & 1).astype(np.int8)
+    return {"u": log[:, 0] + int(user_begin), "t": log[:, 1], "z": z,
+            "v": np.where(z == 0, log[:, 2], -1).astype(np.int32), "a": np.where(z == 1, log[:, 2], -1).astype(np.int32),
+            "c": np.where(z == 1, click, -1).astype(np.int8), "totals": totals}
+
+
 class BatchState:
     """Device SoA of N concurrent users for the batched gym protocol."""
 

@@ -354,3 +354,49 @@ def test_tensor_core_logits_match_binary64():
         assert err.max() < 2e-4, (P, K, err.max())
         assert (got[:, P:] < -1e29).all()          # padded products carry no mass
         de.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
+def test_event_log_equals_oracle_and_reference_rows(oracle, mode):
+    """The event-log output of the fused rollout == the rows of generate_logs: against the T2 reference logs
+    (golden) and against the oracle's log at a larger size, every column, in the reference's row order."""
+    from recogym_b200 import rollout_log
+    for case in ("t2_seed7_P100_K5_u60_o5", "t2_seed5_P60_K8_u40_bandit_count_flips"):
+        g = load_golden(case)
+        de = device_env_from_golden(g)
+        table = g["table"] if "table" in g.files else None
+        r = rollout_log(de, int(g["n_users"]), str(g["policy"]), table, 0, int(g["n_organic_users"]), MODES[mode])
+        for k in "utzvac":
+            assert np.array_equal(r[k].astype(np.int64), g["log_" + k].astype(np.int64)), (case, k)
+        de.close()
+    oe, de = both_envs(300, 8, 5)
+    table = np.random.RandomState(3).randint(0, 300, 300).astype(np.int32)
+    ro = oracle.rollout(oe, 10, 400, policy="table", table=table, n_organic_users=7, log=True)
+    r = rollout_log(de, 400, "table", table, 10, 7, MODES[mode], rows_per_user=20.0)   # forces the capacity retry
+    for k in "utzvac":
+        assert np.array_equal(r[k].astype(np.int64), ro["log"][k].astype(np.int64)), k
+    de.close()
+
+
+def test_fused_generate_logs_equals_stepwise_facade():
+    """generate_logs(fused) and the per-step gym loop produce the same DataFrame (uniform logging policy and a
+    BanditCount table agent, whose 'ps' column is its click-rate estimate)."""
+    import recogym_b200 as rg
+    env = rg.make("reco-gym-v1")
+    env.init_gym({**rg.env_1_args, "random_seed": 11, "num_products": 30, "K": 4})
+    a = env.generate_logs(40, num_organic_offline_users=3)
+    b = env.generate_logs(40, num_organic_offline_users=3, fused=False)
+    agent = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": 30}))
+    rs = np.random.RandomState(0)
+    agent.pulls_a += rs.randint(0, 5, (30, 30)); agent.clicks_a += rs.randint(0, 2, (30, 30)) * (agent.pulls_a > 0)
+    agent.ctr = (agent.clicks_a + 1) / (agent.pulls_a + 2)
+    c = env.generate_logs(40, agent=agent)
+    d = env.generate_logs(40, agent=agent, fused=False)
+    for x, y in ((a, b), (c, d)):
+        assert list(x.columns) == list(y.columns) and len(x) == len(y)
+        for col in ("t", "u", "v", "a", "c", "ps"):
+            xv = x[col].to_numpy(dtype="float64", na_value=np.nan)
+            yv = y[col].to_numpy(dtype="float64", na_value=np.nan)
+            assert np.array_equal(np.isnan(xv), np.isnan(yv)), col
+            assert np.array_equal(np.nan_to_num(xv, nan=-1), np.nan_to_num(yv, nan=-1)), col
+        assert (x["z"] == y["z"]).all()
