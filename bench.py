@@ -33,6 +33,11 @@ WORKLOADS = {
                label="reco-env-v1 P=10000 K=20 1M users/GPU/step, organic_count agent (configs[2])"),
     "c4": dict(P=100000, K=64, policy="bandit_count", users=1_250_000,
                label="reco-env-v1 P=100000 K=64 1.25M users/GPU/step (10M over 8 GPUs), bandit_count agent (configs[3])"),
+    # verify_agents-style A/B sweep (evaluate_agent.py:732-750): every agent is rolled out over the SAME users
+    "c5": dict(P=10000, K=20, policy=["random", "organic_count", "bandit_count", "organic_user_count", "bandit_mf"],
+               users=200_000,
+               label="A/B sweep: 5 leaderboard agents x 200k users/GPU/step, P=10000 K=20 (configs[4]: 1M users per "
+                     "agent = 5 steps at 1 GPU, 1 step at 5+ GPUs)"),
 }
 SEED = 42
 # algorithmic HBM bytes per user-step of the step-synchronous protocol
@@ -67,29 +72,50 @@ def static_params(P, K):
     return cfg, draw_static_params(cfg)
 
 
-def train_policy_table(kind, P, K, n_train):
-    """Trains the count agent exactly as test_agent does (bench_agents.py:176-190) on n_train logged
-    users through the RecoEnv1 facade (GPU), then compiles it to a last-view -> action table."""
+def build_policies(kinds, P, K, n_train):
+    """-> [(kind, device policy name, table or None)].  Trainable agents are trained exactly as test_agent does
+    (bench_agents.py:176-190) on the SAME n_train logged users through the RecoEnv1 facade (GPU, default uniform
+    logging policy), then compiled to device policies (recogym_b200/policy.py)."""
     import recogym_b200 as rg
-    if kind == "uniform":
-        return "uniform", None
-    env = rg.make("reco-gym-v1")
-    env.init_gym({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED})
-    if kind == "organic_count":
-        agent = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
-    else:
-        agent = _SparseBanditCount(P)
-    for uid in range(n_train):
-        env.reset(uid)
-        new_obs, _, done, reward = env.step(None)
-        while not done:
+    A = rg.agents
+    agents = {}
+    for kind in kinds:
+        if kind == "organic_count":
+            agents[kind] = A.OrganicCount(rg.Configuration({**A.organic_count_args, "num_products": P}))
+        elif kind == "bandit_count":
+            agents[kind] = _SparseBanditCount(P)
+        elif kind == "bandit_mf":
+            import torch
+            torch.manual_seed(SEED)
+            agents[kind] = A.BanditMFSquare(rg.Configuration({**A.bandit_mf_square_args, "num_products": P}))
+        elif kind == "organic_user_count":
+            agents[kind] = A.OrganicUserEventCounterAgent(rg.Configuration(
+                {**A.organic_user_count_args, "num_products": P, "random_seed": SEED}))
+        elif kind in ("uniform", "random"):
+            agents[kind] = A.RandomAgent(rg.Configuration({**A.random_args, "num_products": P, "random_seed": SEED}))
+        else:
+            raise ValueError(kind)
+    trainable = [a for k, a in agents.items() if k in ("organic_count", "bandit_count", "bandit_mf")]
+    if trainable:
+        env = rg.make("reco-gym-v1")
+        env.init_gym({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED})
+        for uid in range(n_train):
+            env.reset(uid)
+            new_obs, _, done, reward = env.step(None)
+            while not done:
+                old_obs = new_obs
+                action, new_obs, reward, done, _ = env.step_offline(old_obs, reward, done)
+                for a in trainable:
+                    a.train(old_obs, action, reward, False)
             old_obs = new_obs
-            action, new_obs, reward, done, _ = env.step_offline(old_obs, reward, done)
-            agent.train(old_obs, action, reward, False)
-        old_obs = new_obs
-        action, _, reward, done, _ = env.step_offline(old_obs, reward, done)
-        agent.train(old_obs, action, reward, True)
-    return "table", agent.device_policy()["table"]
+            action, _, reward, done, _ = env.step_offline(old_obs, reward, done)
+            for a in trainable:
+                a.train(old_obs, action, reward, True)
+    out = []
+    for kind in kinds:
+        pol = agents[kind].device_policy()
+        out.append((kind, pol["policy"], pol.get("table")))
+    return out
 
 
 class _SparseBanditCount:
@@ -173,7 +199,9 @@ def run_reference(args, wl):
                      cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
     cores = os.cpu_count() or 1
     policy, table = ("uniform", None)
-    if wl["policy"] != "uniform":
+    if isinstance(wl["policy"], list):
+        policy = "user_views"      # the most expensive acting policy of the sweep on the CPU (dense P-vector per act)
+    elif wl["policy"] != "uniform":
         policy, table = "table", np.random.RandomState(SEED).randint(0, wl["P"], wl["P"]).astype(np.int32)
     users = {100: 8192, 10000: 96, 100000: 12}.get(wl["P"], 96) * cores   # a few seconds per step on all cores
     base = 10_000_000
@@ -240,9 +268,11 @@ def main():
     P, K, U = wl["P"], wl["K"], wl["users"]
 
     cfg, sp = static_params(P, K)
-    policy, table = train_policy_table(wl["policy"], P, K, args.train_users)
+    kinds = wl["policy"] if isinstance(wl["policy"], list) else [wl["policy"]]
+    policies = build_policies(kinds, P, K, args.train_users)
     de = rg.DeviceEnv(sp, cfg.sigma_omega_initial, cfg.sigma_omega, SEED, device=local_rank)
-    table_dev = torch.as_tensor(table, device=dev) if table is not None else None
+    tables_dev = [torch.as_tensor(t, device=dev) if t is not None else None for _, _, t in policies]
+    policy, table = policies[0][1], policies[0][2]          # cpu_baseline leg: the first policy of the workload
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     step_tots = torch.zeros((args.steps, 16), dtype=torch.int64, device=dev)
@@ -250,7 +280,8 @@ def main():
     def step(s, tot):
         """one fused rollout of U fresh users on this rank + the all-reduce of the CTR counters"""
         first = (s * world + rank) * U
-        de.rollout_device(U, policy, table_dev, first, 0, math_mode, per_user=False, totals=tot)
+        for (_, pol, _), tdev in zip(policies, tables_dev):   # every agent of an A/B sweep sees the same users
+            de.rollout_device(U, pol, tdev, first, 0, math_mode, per_user=False, totals=tot)
         allreduce_counters(tot)
 
     def barrier():
@@ -284,16 +315,16 @@ def main():
     value = events / (total_ms * 1e-3)
 
     # ---- e2e: the reference-facing host API (C ABI with HOST buffers), copies inside the timed region
-    host_table = table
     barrier()
     t0 = time.perf_counter()
     e2e_events = 0
     d2h = 0
     for s in range(args.steps):
         first = ((s + 5000) * world + rank) * U
-        r = de.rollout_host(U, policy, host_table, first, 0, math_mode, per_user=False)
-        e2e_events += int(r["totals"][1])
-        d2h = 64
+        for _, pol, tab in policies:
+            r = de.rollout_host(U, pol, tab, first, 0, math_mode, per_user=False)
+            e2e_events += int(r["totals"][1])
+        d2h = 128 * len(policies)
     if world > 1:
         # counters of the host path are reduced with the same collective, on device
         tt = torch.tensor([e2e_events], dtype=torch.int64, device=dev)
@@ -304,7 +335,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_val = e2e_events / float(e2e_dt.item())
-    h2d = 4 * P if table is not None else 0
+    h2d = sum(4 * P for _, _, t in policies if t is not None)
 
     if rank != 0:
         if world > 1:
@@ -314,8 +345,8 @@ def main():
     hbm_peak, peak_src, sm_max = peaks()
     per_gpu_steps_s = value / world
     alg_bytes = ALG_BYTES_PER_STEP.get(K, 4.0 * K * 2.2 + 16)
-    avg_launch_s = (total_ms * 1e-3) / args.steps
-    launch_events = events / world / args.steps
+    avg_launch_s = (total_ms * 1e-3) / args.steps / len(policies)
+    launch_events = events / world / args.steps / len(policies)
     achieved_gbs = alg_bytes * launch_events / avg_launch_s / 1e9
     # compute roofline (the physically binding one): fp32 FMA pipe of the organic contraction
     flops_per_step = F_ORG * (2.0 * P * K)
@@ -326,13 +357,13 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tensor": "f64+tf32x2", "fast": "f64+f32", "exact": "f64"}[args.math],
         "data": "synthetic",
         "config": {"workload": wl["label"], "num_products": P, "K": K, "users_per_gpu_per_step": U,
-                   "policy": wl["policy"], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
+                   "policy": wl["policy"], "device_policies": [p for _, p, _ in policies], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
                    "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
                    "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
                    "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7])},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps * len(policies),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": measured_traffic(launch_events), "peak_source": peak_src,
                      "algorithmic_bytes_per_user_step": alg_bytes,

@@ -41,6 +41,12 @@ extern "C" {
 #define RG_POLICY_UNIFORM 0 /* default logging policy, abstract.py:211-221 (uniform over products) */
 #define RG_POLICY_TABLE 1   /* action = table[last viewed product]: OrganicCount.act (agents/organic_count.py:54-72),
                                BanditCount.act (agents/bandit_count.py:28-47), BanditMFSquare.act (agents/bandit_mf.py:44-87) */
+#define RG_POLICY_USER_VIEWS 2 /* OrganicUserEventCounterAgent.act with its default configuration
+                               (agents/organic_user_count.py:29-116: exploit_explore, epsilon = 0, select_randomly):
+                               action ~ Categorical(views_of_this_user / their sum) by numpy's inverse CDF
+                               (cumsum, /= cdf[-1], searchsorted right) on the policy stream's second uniform.
+                               The per-user view counts (ViewsFeaturesProvider, agents/abstract.py:318-409) live in
+                               a device scratch owned by rg_env. */
 
 /* math modes of the organic-view sampler */
 #define RG_MATH_EXACT 0 /* every view sampled in binary64 (reference arithmetic) */
@@ -97,7 +103,8 @@ typedef struct rg_rollout_out {
     int64_t *click_hist; /* [P] accumulated (clicked actions; evaluate_agent.py:121-124) */
     int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
                             [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] binary64-ambiguous
-                            samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, rest reserved */
+                            samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, [9] RG_POLICY_USER_VIEWS:
+                            users whose distinct views overflowed the device list (must be 0), rest reserved */
     /* Event log == the rows of the generate_logs DataFrame (abstract.py:256-327), unordered: one int32x4
      * record {u = user_id - user_begin, t, x = product viewed | action, flags} per row, flags bit 0: z
      * (0 organic, 1 bandit), bit 1: click, bit 2: phantom row after done (abstract.py:311-316).  Rows of one

@@ -67,6 +67,8 @@ def lib():
         L.rgo_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.rgo_policy_uniform_action.restype = C.c_int32
         L.rgo_policy_uniform_action.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32]
+        L.rgo_policy_uniform53.restype = C.c_double
+        L.rgo_policy_uniform53.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]
         L.rgo_rollout.restype = None
         L.rgo_rollout.argtypes = [C.POINTER(_Env), C.POINTER(_Policy), C.c_int64, C.c_int64, C.c_int64,
                                   C.POINTER(_Outputs), C.c_int]
@@ -97,6 +99,9 @@ def norm_ppf(p): return lib().rgo_norm_ppf(float(p))
 def ff(x): return lib().rgo_ff(float(x))
 def event_uniform(seed, user, t, which): return lib().rgo_event_uniform(int(seed), int(user), int(t), int(which))
 def policy_uniform_action(seed, user, t, P): return lib().rgo_policy_uniform_action(int(seed), int(user), int(t), int(P))
+
+
+def policy_uniform53(seed, user, t, which): return lib().rgo_policy_uniform53(int(seed), int(user), int(t), int(which))
 
 
 def normals(seed, user, t, K):
@@ -145,6 +150,9 @@ def make_policy(kind="uniform", table=None):
         pol.kind = 1
         keep = np.ascontiguousarray(table, np.int32)
         pol.table = _p(keep)
+    elif kind == "user_views":
+        pol.kind = 2
+        keep = None
     else:
         raise ValueError(kind)
     return pol, keep

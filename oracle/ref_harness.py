@@ -145,6 +145,27 @@ class PhiloxUserRNG:
         return idx if np.isscalar(a) or isinstance(a, (int, np.integer)) else a[idx]
 
 
+class PhiloxAgentRNG:
+    """Drop-in for the `rng` of an agent's model (e.g. OrganicUserEventCounterModel.rng,
+    agents/organic_user_count.py:43): draws come from the POLICY stream of the RNG spec at the env's
+    current (user, time) -- first uniform for the explore coin `choice([True, False], p)`
+    (organic_user_count.py:49-52), second uniform for the action `choice(P, p)` (:65)."""
+
+    def __init__(self, env, seed):
+        self.env = env
+        self.seed = int(seed)
+
+    def choice(self, a, p=None):
+        from oracle import oracle as O
+        u, t = int(self.env.current_user_id), int(self.env.current_time)
+        is_coin = not (np.isscalar(a) or isinstance(a, (int, np.integer)))
+        x = O.policy_uniform53(self.seed, u, t, 0 if is_coin else 1)
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
+        idx = int(cdf.searchsorted(x, side="right"))
+        return a[idx] if is_coin else idx
+
+
 def make_env(args, tier):
     """Build the reference RecoEnv1 with `args` merged over env_1_args. tier: 'T1' | 'T2'."""
     ref = load_reference()

@@ -9,7 +9,9 @@ from .envs import (Configuration, Context, DefaultContext, Observation, Session,
                    NormalTimeGenerator)
 from .constants import AgentStats, AgentInit, EvolutionCase, TrainingApproach, RoiMetrics
 from .bench_agents import test_agent
-from .evaluate_agent import evaluate_agent, build_agent_init, verify_agents
+from .evaluate_agent import (evaluate_agent, build_agent_init, build_agents, verify_agents, gather_agent_stats,
+                             gather_exploration_stats)
+from .competition import competition_score
 from . import agents
 from ._lib import MATH_EXACT, MATH_FAST, MATH_TENSOR, RecoGymB200Error
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librecogym_b200.so")
 
 RG_OK, RG_EINVAL, RG_ECUDA, RG_ENOMEM, RG_ENODEVICE = 0, -1, -2, -3, -4
 ORGANIC, BANDIT, STOP = 0, 1, 2
-POLICY_UNIFORM, POLICY_TABLE = 0, 1
+POLICY_UNIFORM, POLICY_TABLE, POLICY_USER_VIEWS = 0, 1, 2
 MATH_EXACT, MATH_FAST, MATH_TENSOR = 0, 1, 2
 
 

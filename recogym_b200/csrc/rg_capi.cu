@@ -40,7 +40,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_env(rg_env_impl &e) {
     cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
-    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.diag);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_views); cudaFree(e.diag);
 }
 
 rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
@@ -61,7 +61,7 @@ int check_rollout_args(const rg_env *env, const rg_policy *policy, int64_t n_org
                        const rg_rollout_out *out, int math_mode) {
     if (!env || !policy || !out) return fail(RG_EINVAL, "null argument");
     if (n_organic_users < 0 || n_users < 0) return fail(RG_EINVAL, "negative user count");
-    if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE)
+    if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE && policy->kind != RG_POLICY_USER_VIEWS)
         return fail(RG_EINVAL, "unknown policy kind %d", policy->kind);
     if (policy->kind == RG_POLICY_TABLE && !policy->table) return fail(RG_EINVAL, "table policy without table");
     if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST && math_mode != RG_MATH_TENSOR)
@@ -241,8 +241,25 @@ int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, 
     int rc = check_rollout_args(env, policy, n_organic_users, n_users, out, math_mode);
     if (rc != RG_OK) return rc;
     RG_CUDA(cudaSetDevice(env->impl.device));
-    rg::PolicyDev pol{policy->kind, policy->table};
+    rg::PolicyDev pol{policy->kind, policy->table, nullptr, 0, nullptr};
     const rg::RolloutOutDev od = to_dev(*out);
+    if (policy->kind == RG_POLICY_USER_VIEWS) {
+        // one sorted (product, views) list per resident user: 2 CTAs x 128 slots per SM in the CTA-batched kernel,
+        // 64 warps per SM in the warp-per-user kernel.  A user with more than 1024 distinct views would need an
+        // episode of > ~4000 events (probability 0.99^4000 per user); it is counted in totals[9] if it ever happens.
+        rg_env_impl &e = env->impl;
+        const int cap = e.dev.P < 1024 ? e.dev.P : 1024;
+        const size_t lists = (size_t)e.num_sms * 2 * 128;
+        if (e.views_lists < lists || e.view_cap != cap) {
+            if (e.d_views) cudaFree(e.d_views);
+            e.d_views = nullptr; e.views_lists = 0;
+            RG_CUDA(cudaMalloc((void **)&e.d_views, sizeof(int2) * lists * (size_t)cap));
+            e.views_lists = lists; e.view_cap = cap;
+        }
+        pol.views = e.d_views;
+        pol.view_cap = cap;
+        pol.view_overflow = od.totals ? od.totals + 9 : e.diag + 1;
+    }
     if (math_mode == RG_MATH_FAST || math_mode == RG_MATH_TENSOR)
         RG_CUDA(rg::launch_rollout_fast(env->impl, pol, user_begin, n_organic_users, n_organic_users + n_users, od,
                                         (cudaStream_t)stream, math_mode == RG_MATH_TENSOR));

@@ -33,7 +33,42 @@ struct EnvDev {
 struct PolicyDev {
     int kind;
     const int32_t *table;  // device [P]
+    // RG_POLICY_USER_VIEWS: one list of (product, views) pairs, sorted by product, per resident user
+    // (ViewsFeaturesProvider of the reference, agents/abstract.py:318-409, kept sparse)
+    int2 *views;           // [lists][view_cap]
+    int view_cap;
+    unsigned long long *view_overflow;  // counts users whose distinct views exceeded view_cap (results invalid)
 };
+
+// ViewsFeaturesProvider.observe (agents/abstract.py:340-351): views[0, v] += 1 on the sparse sorted list.
+__device__ __forceinline__ void views_insert(int2 *list, int &d, int cap, int v, unsigned long long *overflow) {
+    int lo = 0, hi = d;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid].x < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo < d && list[lo].x == v) { list[lo].y += 1; return; }
+    if (d >= cap) { atomicAdd(overflow, 1ull); return; }
+    for (int k = d; k > lo; --k) list[k] = list[k - 1];
+    list[lo] = make_int2(v, 1);
+    d += 1;
+}
+
+// OrganicUserEventCounterModel.act with exploit_explore, epsilon = 0, select_randomly
+// (agents/organic_user_count.py:49-75): action_proba = features / sum(features); numpy choice(P, p) on ONE
+// uniform = cumsum(p) (sequential; products never viewed add an exact 0), /= cdf[-1], searchsorted right.
+// n = total views of the user so far, d = distinct products.
+__device__ __forceinline__ int views_action(const int2 *list, int d, int n, double u) {
+    const double dn = (double)n;
+    double T = 0.0;
+    for (int k = 0; k < d; ++k) T += (double)list[k].y / dn;
+    double S = 0.0;
+    for (int k = 0; k < d; ++k) {
+        S += (double)list[k].y / dn;
+        if (S / T > u) return list[k].x;
+    }
+    return list[d - 1].x;  // not reached: cdf[-1] / cdf[-1] == 1 > u
+}
 
 struct RolloutOutDev {
     int32_t *n_events, *n_organic, *n_bandit, *n_clicks, *last_view;

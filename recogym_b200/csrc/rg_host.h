@@ -15,6 +15,9 @@ struct rg_env_impl {
     float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
     double *d_om_scratch = nullptr;      // RG_MATH_TENSOR: omega rows of the resident slots
     size_t om_scratch_bytes = 0;
+    int2 *d_views = nullptr;             // RG_POLICY_USER_VIEWS: sorted (product, views) lists of the resident users
+    size_t views_lists = 0;              // lists allocated (each view_cap entries)
+    int view_cap = 0;
     unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
 };
 

@@ -57,9 +57,11 @@ __device__ __forceinline__ int bandit_event(const EnvDev &env, const WarpCtx &wc
 }
 
 __device__ __forceinline__ int policy_action(const EnvDev &env, const PolicyDev &pol, uint64_t user, uint32_t t,
-                                             int last_view) {
+                                             int last_view, const int2 *vlist, int nd, int nviews) {
     if (pol.kind == RG_POLICY_TABLE) return __ldg(pol.table + last_view);
-    return uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, env.P);
+    const u32x4 w = draw(env.seed, user, t, SLOT_POLICY);
+    if (pol.kind == RG_POLICY_USER_VIEWS) return views_action(vlist, nd, nviews, uniform53(w.z, w.w));
+    return uniform_action(w.x, env.P);
 }
 
 // generate_logs (abstract.py:241-327) reduced to counters, RG_MATH_EXACT.
@@ -84,6 +86,9 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
         uint64_t h = kHashInit;
         warp_omega_update(wc.omega, env.K, env.sigma0, true, env.seed, user, 0u, lane);
         const bool organic_only = i < n_organic_users;
+        const bool track_views = pol.kind == RG_POLICY_USER_VIEWS;
+        int2 *vlist = track_views ? pol.views + (size_t)warp0 * pol.view_cap : nullptr;
+        int nd = 0;  // distinct products viewed by this user (per-user features reset, organic_user_count.py:111-116)
         for (;;) {
             if (state == RG_ORGANIC) {
                 const int v = organic_event(env, wc, user, state, t, lane, ambig);
@@ -92,8 +97,13 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
                 h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
                 if (out.view_hist && lane == 0) atomicAdd(out.view_hist + v, 1ull);
                 if (out.log && lane == 0) log_write(out, log_reserve(out, 1), i, t - 1u, v, 0);
+                if (track_views) {
+                    if (lane == 0) views_insert(vlist, nd, pol.view_cap, v, pol.view_overflow);
+                    nd = __shfl_sync(0xffffffffu, nd, 0);
+                    __syncwarp();
+                }
             } else if (state == RG_BANDIT && !organic_only) {
-                const int a = policy_action(env, pol, user, t, last_view);
+                const int a = policy_action(env, pol, user, t, last_view, vlist, nd, n_org);
                 const int c = bandit_event(env, wc, user, a, state, t, lane);
                 if (out.log && lane == 0) log_write(out, log_reserve(out, 1), i, t - 1u, a, 1 | (c << 1));
                 n_ban += 1;
@@ -109,7 +119,7 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
         }
         h = hash_fold(h, ((uint64_t)t << 2) | 3u);
         if (out.log && lane == 0 && !organic_only)  // phantom action after done (abstract.py:311-316), reward 0
-            log_write(out, log_reserve(out, 1), i, t, policy_action(env, pol, user, t, last_view), 1 | 4);
+            log_write(out, log_reserve(out, 1), i, t, policy_action(env, pol, user, t, last_view, vlist, nd, n_org), 1 | 4);
         if (lane == 0) {
             if (out.n_events) out.n_events[i] = (int32_t)t;
             if (out.n_organic) out.n_organic[i] = n_org;

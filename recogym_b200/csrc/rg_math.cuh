@@ -17,7 +17,8 @@
 namespace rg {
 
 constexpr uint32_t SLOT_EVENT = 0u;     // words 0,1: view/click uniform; words 2,3: transition uniform
-constexpr uint32_t SLOT_POLICY = 1u;    // word 0: uniform logging-policy action
+constexpr uint32_t SLOT_POLICY = 1u;    // word 0: uniform logging-policy action; RG_POLICY_USER_VIEWS: words 0,1 =
+                                        // the explore coin's uniform, words 2,3 = the action's uniform
 constexpr uint32_t SLOT_NORMAL = 0x100u; // + j : normals 2j, 2j+1 of omega init (t=0) / drift into t
 
 struct u32x4 { uint32_t x, y, z, w; };

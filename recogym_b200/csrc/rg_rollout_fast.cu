@@ -41,7 +41,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        nview, amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
 
@@ -93,6 +93,7 @@ __host__ inline void make_layout(Params &p) {
     L.pos2slot = o; o += 4 * TU;
     L.shift = o; o += 4 * TU;
     L.eps = o; o += 4 * TU;
+    L.nview = o; o += 4 * TU;
     L.amb_list = o; o += 4 * TU;
     L.fb_slot = o; o += 4 * FB;
     L.fb_pos = o; o += 4 * FB;
@@ -462,6 +463,17 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *s_shift = (float *)(smem + L.shift);
     float *s_eps = (float *)(smem + L.eps);
     int *amb_list = (int *)(smem + L.amb_list);
+    int *s_nview = (int *)(smem + L.nview);   // RG_POLICY_USER_VIEWS: distinct products viewed by the slot's user
+    const bool track_views = p.pol.kind == RG_POLICY_USER_VIEWS;
+    int2 *const vlists = track_views ? p.pol.views + (size_t)blockIdx.x * TU * p.pol.view_cap : nullptr;
+    // acting policy at (user, t): Agent.act of the compiled agent (include/recogym_b200.h RG_POLICY_*)
+    auto policy_act = [&](int slot, uint64_t user, uint32_t t, int last_view, int n_org) -> int {
+        if (p.pol.kind == RG_POLICY_TABLE) return __ldg(p.pol.table + last_view);
+        const u32x4 w = draw(p.env.seed, user, t, SLOT_POLICY);
+        if (p.pol.kind == RG_POLICY_USER_VIEWS)
+            return views_action(vlists + (size_t)slot * p.pol.view_cap, s_nview[slot], n_org, uniform53(w.z, w.w));
+        return uniform_action(w.x, p.env.P);
+    };
     int *fb_slot = (int *)(smem + L.fb_slot);
     double *fb_u = (double *)(smem + L.fb_u);
     double *fb_lse = (double *)(smem + L.fb_lse);
@@ -520,6 +532,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         s_state[slot] = RG_ORGANIC;
         s_last_view[slot] = -1;
         s_n_org[slot] = 0; s_n_ban[slot] = 0; s_n_clk[slot] = 0;
+        s_nview[slot] = 0;
         s_live[slot] = 1;
         s_wait[slot] = 0;
         s_pend[slot] = 2;  // omega = sigma0 * z(user, 0) (reco_env_v1.py:80-82), done by omega_phase()
@@ -1029,9 +1042,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             tot_users += 1; tot_events += t; tot_org += n_org; tot_ban += n_ban; tot_clk += n_clk;
             tot_ph += idx < p.n_organic_users ? 0 : 1;
             if (p.out.log && idx >= p.n_organic_users) {  // phantom action after done (abstract.py:311-316)
-                int a;
-                if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
-                else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
+                const int a = policy_act(slot, user, t, last_view, n_org);
                 log_write(p.out, log_reserve(p.out, 1), idx, t, a, 1 | 4);
             }
             claim(slot);
@@ -1052,6 +1063,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
                 if (p.out.view_hist) atomicAdd(p.out.view_hist + v, 1ull);
                 if (p.out.log) log_write(p.out, log_reserve(p.out, 1), (long long)user - p.user_begin, t, v, 0);
+                if (track_views && !organic_only) {
+                    int nd = s_nview[slot];
+                    views_insert(vlists + (size_t)slot * p.pol.view_cap, nd, p.pol.view_cap, v, p.pol.view_overflow);
+                    s_nview[slot] = nd;
+                }
             }
             const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
             int st = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
@@ -1060,9 +1076,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             if (st == RG_ORGANIC) pend = 1;
             else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
             while (serial_bandit && st == RG_BANDIT && !organic_only) {  // abstract.py:174-181, one event per turn
-                int a;
-                if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
-                else a = uniform_action(draw(env.seed, user, t, SLOT_POLICY).x, P);
+                const int a = policy_act(slot, user, t, last_view, n_org);
                 const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
                 const double uc = uniform53(wb.x, wb.y);
                 int c = 0;
@@ -1114,9 +1128,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 int st = RG_BANDIT, pend = 0;
                 while (st == RG_BANDIT) {  // 32 candidate events per turn (a run is ~14 events on average)
                     const uint32_t tt = t + (uint32_t)lane;
-                    int a;
-                    if (p.pol.kind == RG_POLICY_TABLE) a = __ldg(p.pol.table + last_view);
-                    else a = uniform_action(draw(env.seed, user, tt, SLOT_POLICY).x, P);
+                    const int a = policy_act(slot, user, tt, last_view, s_n_org[slot]);
                     const u32x4 wb = draw(env.seed, user, tt, SLOT_EVENT);
                     const double uc = uniform53(wb.x, wb.y);
                     // ff() never exceeds sig(5*0.5-6) = 0.02931, so the click threshold (1-ctr)/((1-ctr)+ctr) is

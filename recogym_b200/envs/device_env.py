@@ -107,18 +107,10 @@ class DeviceEnv:
                 setattr(out, name, res[name].data_ptr())
         res["totals"] = totals if totals is not None else torch.zeros(16, dtype=torch.int64, device=dev)
         out.totals = res["totals"].data_ptr()
-        pol = L.Policy()
-        if policy == "uniform":
-            pol.kind = L.POLICY_UNIFORM
-        elif policy == "table":
-            pol.kind = L.POLICY_TABLE
-            if not (hasattr(table, "is_cuda") and table.is_cuda):
-                table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
-            assert table.dtype == torch.int32 and table.numel() == self.P
-            res["_table"] = table  # keep alive until the launch has been enqueued
-            pol.table = table.data_ptr()
-        else:
-            raise ValueError("unknown policy %r" % (policy,))
+        if policy == "table" and not (hasattr(table, "is_cuda") and table.is_cuda):
+            table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
+        keep = res["_keep"] = []  # keeps the table alive until the launch has been enqueued
+        pol = _policy_struct(keep, policy, table, self.P, host=False)
         L.check(L.lib().rg_rollout_device(self._h, C.byref(pol), int(user_begin), int(n_organic_users),
                                           int(n_users), C.byref(out), int(math_mode), self._stream()))
         return res
@@ -144,17 +136,8 @@ class DeviceEnv:
                 setattr(out, name, res[name].ctypes.data)
         res["totals"] = np.zeros(16, np.int64)
         out.totals = res["totals"].ctypes.data
-        pol = L.Policy()
-        keep = None
-        if policy == "uniform":
-            pol.kind = L.POLICY_UNIFORM
-        elif policy == "table":
-            pol.kind = L.POLICY_TABLE
-            keep = np.ascontiguousarray(table, np.int32)
-            assert keep.shape == (self.P,)
-            pol.table = keep.ctypes.data
-        else:
-            raise ValueError("unknown policy %r" % (policy,))
+        keep = []
+        pol = _policy_struct(keep, policy, table, self.P, host=True)
         L.check(L.lib().rg_rollout_host(self._h, C.byref(pol), int(user_begin), int(n_organic_users), int(n_users),
                                         C.byref(out), int(math_mode)))
         del keep
@@ -165,6 +148,8 @@ def _policy_struct(keep, policy, table, P, host):
     pol = L.Policy()
     if policy == "uniform":
         pol.kind = L.POLICY_UNIFORM
+    elif policy == "user_views":   # OrganicUserEventCounterAgent, default configuration (RG_POLICY_USER_VIEWS)
+        pol.kind = L.POLICY_USER_VIEWS
     elif policy == "table":
         pol.kind = L.POLICY_TABLE
         if host:

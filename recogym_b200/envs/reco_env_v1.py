@@ -341,6 +341,14 @@ class RecoEnv1:
         P = self.config.num_products
         if pol["policy"] == "uniform":
             ps = np.where(organic, np.nan, 1.0 / P)
+        elif pol["policy"] == "user_views":
+            # ps = (1 - epsilon) * action_proba[a] = views of product a by this user so far / all its views so far
+            # (agents/organic_user_count.py:66-72 with epsilon = 0)
+            org = organic.astype(np.int64)
+            x = np.where(organic, r["v"], r["a"]).astype(np.int64)
+            seen = pd.Series(org).groupby(r["u"].astype(np.int64) * P + x).cumsum().to_numpy()
+            total = pd.Series(org).groupby(r["u"]).cumsum().to_numpy()
+            ps = np.where(organic, np.nan, seen / np.maximum(total, 1))
         else:
             ps_table = pol.get("ps_table")
             ps = np.where(organic, np.nan, 1.0)
@@ -363,7 +371,9 @@ class RecoEnv1:
         df.loc[organic, "a"] = pd.NA
         psa = np.empty(len(df), dtype=object)
         psa[:] = None
-        psa[~organic] = [()] * int((~organic).sum())
+        empty = np.empty(1, dtype=object)
+        empty[0] = ()          # the reference logs `()` for bandit rows without with_ps_all (abstract.py:290)
+        psa[~organic] = empty
         df["ps-a"] = psa
         return df
 

@@ -1,10 +1,19 @@
-"""A/B and evolution drivers (reference: recogym/evaluate_agent.py:51-146,158-182,732-750)."""
+"""A/B, sweep and evolution drivers (reference: recogym/evaluate_agent.py:51-447,732-750).
+
+The reference spreads sweep points over a `multiprocessing.Pool` (evaluate_agent.py:255-277,416-445) because
+one rollout occupies one core; here one rollout is one fused CUDA launch over all users, so the sweeps run
+in-process, point after point (a forked child could not use the CUDA context anyway)."""
+import time
 from copy import deepcopy
 
 from scipy.stats import beta
 
-from .constants import AgentInit, EvolutionCase, TrainingApproach
+from .constants import AgentInit, AgentStats, EvolutionCase, TrainingApproach
+from .envs.configuration import Configuration
 from .policy import device_policy
+
+EpsilonPrecision = 2
+EvolutionEpsilons = (0.00, 0.01, 0.02, 0.03, 0.05, 0.08)
 
 
 def build_agent_init(agent_key, ctor, def_args):
@@ -109,3 +118,73 @@ def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000,
         rewards[EvolutionCase.FAILURE].append(failures)
         rewards[EvolutionCase.FAILURE_GREEDY].append(failures_greedy)
     return rewards
+
+
+def build_agents(agents_init_data, new_env_args):
+    """evaluate_agent.py:284-296: agent = ctor(Configuration({**def_args, **env_args}))."""
+    agents = dict()
+    for agent_key, init in agents_init_data.items():
+        agents[agent_key] = init[AgentInit.CTOR](Configuration({**init[AgentInit.DEF_ARGS], **new_env_args}))
+    return agents
+
+
+def gather_agent_stats(env, env_args, extra_env_args, agents_init_data,
+                       user_samples=(100, 1000, 2000, 3000, 5000, 8000, 10000, 13000, 14000, 15000),
+                       num_online_users=15000, num_epochs=1, epoch_with_random_reset=False,
+                       num_organic_offline_users=100, with_cache=False, verbose=False, allow_probe=False):
+    """CTR quantiles of every agent as a function of the number of training users
+    (evaluate_agent.py:185-281).  Returns {SAMPLES: user_samples, AGENTS: {name: {Q0_025, Q0_500, Q0_975}}}."""
+    from .bench_agents import test_agent
+    new_env_args = {**env_args, **extra_env_args}
+    new_env = deepcopy(env)
+    new_env.init_gym(new_env_args)
+    agents = build_agents(agents_init_data, new_env_args)
+    agent_stats = {AgentStats.SAMPLES: user_samples, AgentStats.AGENTS: dict()}
+    for agent_key, agent in agents.items():
+        stats = {AgentStats.Q0_025: [], AgentStats.Q0_500: [], AgentStats.Q0_975: []}
+        for num_offline_users in user_samples:
+            start = time.time()
+            q500, q025, q975 = test_agent(deepcopy(new_env), deepcopy(agent), num_offline_users, num_online_users,
+                                          num_organic_offline_users, num_epochs, epoch_with_random_reset, with_cache,
+                                          allow_probe=allow_probe)
+            if verbose:
+                print(f"Agent {agent_key}: {num_offline_users} offline users ({time.time() - start:.2f}s)")
+            stats[AgentStats.Q0_025].append(q025)
+            stats[AgentStats.Q0_500].append(q500)
+            stats[AgentStats.Q0_975].append(q975)
+        agent_stats[AgentStats.AGENTS][agent_key] = stats
+    return agent_stats
+
+
+def generate_epsilons(epsilon_step=0.02, iterations=6):
+    return [0.00, 0.01, 0.02, 0.03, 0.05, 0.08]      # evaluate_agent.py:299-300 (the arguments are unused there too)
+
+
+def format_epsilon(epsilon):
+    return ("{0:." + f"{EpsilonPrecision}" + "f}").format(round(epsilon, EpsilonPrecision))
+
+
+def gather_exploration_stats(env, env_args, extra_env_args, agents_init_data, training_approach,
+                             num_initial_train_users=1000, num_step_users=1000, epsilons=EvolutionEpsilons,
+                             num_evolution_steps=6):
+    """Evolution of every agent under EpsilonGreedy(epsilon) for each epsilon (evaluate_agent.py:344-447).
+    Returns {agent: {format_epsilon(eps): {SUCCESS, SUCCESS_GREEDY, FAILURE, FAILURE_GREEDY, ACTIONS}}}."""
+    from .agents import EpsilonGreedy, epsilon_greedy_args
+    new_env_args = {**env_args, **extra_env_args}
+    new_env = deepcopy(env)
+    new_env.init_gym(new_env_args)
+    agents = build_agents(agents_init_data, new_env_args)
+    out = dict()
+    for agent_key, agent in agents.items():
+        agent_stats = dict()
+        for epsilon in epsilons:
+            eg = EpsilonGreedy(Configuration({**epsilon_greedy_args, **new_env_args, "epsilon": epsilon}),
+                               deepcopy(agent))
+            rewards = evaluate_agent(deepcopy(new_env), eg, num_initial_train_users, num_step_users,
+                                     num_evolution_steps, training_approach)
+            assert len(rewards[EvolutionCase.SUCCESS]) == len(rewards[EvolutionCase.FAILURE]) == num_evolution_steps
+            agent_stats[format_epsilon(epsilon)] = {k: rewards[k] for k in (
+                EvolutionCase.SUCCESS, EvolutionCase.SUCCESS_GREEDY, EvolutionCase.FAILURE,
+                EvolutionCase.FAILURE_GREEDY, EvolutionCase.ACTIONS)}
+        out[agent_key] = agent_stats
+    return out

@@ -25,6 +25,8 @@ T2_CASES = [
     "t2_seed3_P1000_K20_u24_organic_count",
     "t2_seed5_P60_K8_u40_bandit_count_flips",
     "t2_seed9_P33_K3_u40_omega_bandits",
+    "t2_seed13_P40_K6_u60_o3_organic_user_count",
+    "t2_seed21_P500_K10_u30_organic_user_count",
 ]
 
 

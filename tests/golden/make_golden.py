@@ -69,7 +69,14 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
     if agent_kind is not None:
         ref = H.load_reference()
         from recogym.agents import OrganicCount, organic_count_args, BanditCount, bandit_count_args
-        if agent_kind == "organic_count":
+        if agent_kind == "organic_user_count":
+            from recogym.agents import OrganicUserEventCounterAgent, organic_user_count_args
+            agent = OrganicUserEventCounterAgent(ref.Configuration(
+                {**organic_user_count_args, "num_products": cfg.num_products, "random_seed": cfg.random_seed}))
+            # build the lazily-built model now and key its RNG by the env's (user, time): policy stream
+            agent.feature_provider, agent.model = agent.model_builder.build()
+            agent.model.rng = H.PhiloxAgentRNG(env, cfg.random_seed)
+        elif agent_kind == "organic_count":
             agent = OrganicCount(ref.Configuration({**organic_count_args, "num_products": cfg.num_products}))
         else:
             agent = BanditCount(ref.Configuration({**bandit_count_args, "num_products": cfg.num_products}))
@@ -86,16 +93,15 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
             action, _, reward, done, _ = train_env.step_offline(old_obs, reward, done)
             agent.train(old_obs, action, reward, True)
         if agent_kind == "organic_count":
-            table = agent.co_counts.argmax(axis=1).astype(np.int32)
-        else:
-            table = agent.ctr.argmax(axis=1).astype(np.int32)
-        extra["table"] = table
+            extra["table"] = agent.co_counts.argmax(axis=1).astype(np.int32)
+        elif agent_kind == "bandit_count":
+            extra["table"] = agent.ctr.argmax(axis=1).astype(np.int32)
     df = env.generate_logs(n_users, agent=agent, num_organic_offline_users=n_organic)
     A = H.logs_to_arrays(df)
     save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_organic,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=int(bool(cfg.change_omega_for_bandits)),
-         policy=("table" if agent is not None else "uniform"),
+         policy=("user_views" if agent_kind == "organic_user_count" else "table" if agent is not None else "uniform"),
          **sp, **{"log_" + k: v for k, v in A.items()}, **extra)
     print(name, "rows", len(df), "clicks", int((A["c"] == 1).sum()))
 
@@ -103,6 +109,9 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
 def main():
     if not H.reference_available():
         raise SystemExit("reference not available at " + H.REFERENCE_ROOT)
+    if "--user-views-only" in sys.argv:
+        user_views_cases()
+        return
     t1_static_and_stats()
     t2_case("t2_seed42_P10_K5_u100", {"random_seed": 42}, 100)
     t2_case("t2_seed7_P100_K5_u60_o5", {"random_seed": 7, "num_products": 100, "K": 5}, 60, n_organic=5)
@@ -115,6 +124,15 @@ def main():
             {"random_seed": 9, "num_products": 33, "K": 3, "change_omega_for_bandits": True,
              "prob_organic_to_bandit": 0.4, "prob_bandit_to_organic": 0.2, "prob_leave_organic": 0.03},
             40)
+    user_views_cases()
+
+
+def user_views_cases():
+    t2_case("t2_seed13_P40_K6_u60_o3_organic_user_count",
+            {"random_seed": 13, "num_products": 40, "K": 6, "sigma_mu_organic": 1.0}, 60, n_organic=3,
+            agent_kind="organic_user_count")
+    t2_case("t2_seed21_P500_K10_u30_organic_user_count",
+            {"random_seed": 21, "num_products": 500, "K": 10}, 30, agent_kind="organic_user_count")
 
 
 if __name__ == "__main__":

@@ -149,6 +149,24 @@ def test_rollout_model_variants(oracle, mode):
         de.close()
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
+def test_user_views_policy_equals_oracle(oracle, mode):
+    """RG_POLICY_USER_VIEWS (OrganicUserEventCounterAgent: action ~ the user's own view counts) against the
+    oracle's dense restatement: small P (every product viewed, many repeats), P past a chunk boundary, the C3
+    shape, and change_omega_for_bandits (the serial bandit loop of the CTA kernel)."""
+    for P, K, n, over in ((7, 3, 400, {}), (1025, 20, 150, {}), (10000, 20, 40, {}),
+                          (64, 6, 300, {"change_omega_for_bandits": True, "sigma_omega": 0.4}),
+                          (50, 4, 300, {"prob_organic_to_bandit": 0.1, "prob_leave_organic": 0.002,
+                                        "prob_leave_bandit": 0.002})):   # long organic sessions: long lists
+        oe, de = both_envs(P, K, 300 + P, **over)
+        rc = oracle.rollout(oe, 2, n, policy="user_views", n_organic_users=2, hist=True, omega=True, threads=8)
+        rg = de.rollout_host(n, "user_views", None, 2, 2, MODES[mode], per_user=True, omega=True, hist=True)
+        assert_rollout_equal(rg, rc)
+        assert rg["totals"][9] == 0          # no view-list overflow
+        assert (rg["action_hist"] > 0).sum() <= (rg["view_hist"] > 0).sum()   # only viewed products are recommended
+        de.close()
+
+
 def test_empty_and_device_entry_points(oracle):
     import torch
     oe, de = both_envs(50, 5, 9)
@@ -361,7 +379,8 @@ def test_event_log_equals_oracle_and_reference_rows(oracle, mode):
     """The event-log output of the fused rollout == the rows of generate_logs: against the T2 reference logs
     (golden) and against the oracle's log at a larger size, every column, in the reference's row order."""
     from recogym_b200 import rollout_log
-    for case in ("t2_seed7_P100_K5_u60_o5", "t2_seed5_P60_K8_u40_bandit_count_flips"):
+    for case in ("t2_seed7_P100_K5_u60_o5", "t2_seed5_P60_K8_u40_bandit_count_flips",
+                 "t2_seed13_P40_K6_u60_o3_organic_user_count"):
         g = load_golden(case)
         de = device_env_from_golden(g)
         table = g["table"] if "table" in g.files else None
@@ -392,6 +411,18 @@ def test_fused_generate_logs_equals_stepwise_facade():
     agent.ctr = (agent.clicks_a + 1) / (agent.pulls_a + 2)
     c = env.generate_logs(40, agent=agent)
     d = env.generate_logs(40, agent=agent, fused=False)
+    # OrganicUserEventCounterAgent: device policy RG_POLICY_USER_VIEWS; 'ps' = views of a / all views so far
+    uc = rg.agents.OrganicUserEventCounterAgent(rg.Configuration(
+        {**rg.agents.organic_user_count_args, "num_products": 30, "random_seed": 11}))
+    e = env.generate_logs(30, agent=uc)
+    for u in (0, 7, 29):
+        rows = e[e["u"] == u]
+        seen = {}
+        for _, r in rows.iterrows():
+            if r["z"] == "organic":
+                seen[int(r["v"])] = seen.get(int(r["v"]), 0) + 1
+            else:
+                assert int(r["a"]) in seen and r["ps"] == seen[int(r["a"])] / sum(seen.values())
     for x, y in ((a, b), (c, d)):
         assert list(x.columns) == list(y.columns) and len(x) == len(y)
         for col in ("t", "u", "v", "a", "c", "ps"):
