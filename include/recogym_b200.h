@@ -126,6 +126,64 @@ int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, 
 int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, int64_t n_organic_users,
                     int64_t n_users, const rg_rollout_out *out_host, int math_mode);
 
+/* ---- Ordered, columnar logs and the reductions over them -------------------------
+ * All pointers are DEVICE memory.  A column that is NULL is skipped. */
+typedef struct rg_log_columns {
+    int64_t capacity;  /* rows each column can hold */
+    float *t;          /* 't'  float32 (abstract.py:318) */
+    int32_t *u;        /* 'u'  user id (int32; the reference's UInt16 overflows at 65 535 users, abstract.py:319) */
+    int8_t *z;         /* 'z'  0 = 'organic', 1 = 'bandit' */
+    int32_t *v;        /* 'v'  viewed product, -1 where the reference has NaN */
+    int32_t *a;        /* 'a'  action, -1 where the reference has NaN */
+    float *c;          /* 'c'  reward (0/1; the phantom row after done carries 0), NaN for organic rows */
+    double *ps;        /* 'ps' propensity of the logged action (NaN for organic rows and for RG_POLICY_USER_VIEWS) */
+    int32_t *lv;       /* derived: the acting last view, i.e. Agent.update_lpv's value when the row's action was chosen */
+    int32_t *lvp;      /* derived: lv of the PREVIOUS train call == BanditCount.train's row index
+                          (agents/bandit_count.py:54-57); -1 = None (numpy then updates the whole row `a`); organic rows -1 */
+    int32_t *sess;     /* derived: rows since the first view of the organic session this view belongs to */
+    int8_t *flags;     /* derived: 1 = phantom row after done (abstract.py:311-316), 2 = view of the user's final
+                          session (after its last real bandit row), 4 = the user has no real bandit row */
+} rg_log_columns;
+
+/* Which observations a training loop of the reference hands to Agent.train: */
+#define RG_TRAIN_TEST_AGENT 0   /* test_agent (bench_agents.py:169-190): every session, every bandit row incl. phantom */
+#define RG_TRAIN_EVOLUTION_STEP 1 /* evaluate_agent's step loop (evaluate_agent.py:100-139): stops at done -- no phantom
+                                     call, the final session is never trained on */
+#define RG_TRAIN_EVOLUTION_INIT 2 /* evaluate_agent's warm-up (evaluate_agent.py:56-78): as STEP, but a user whose first
+                                     observation is already done gets the phantom call */
+
+/* AbstractEnv.generate_logs (abstract.py:241-327), complete and in the reference's row order, on the device:
+ * fused rollout -> exclusive scan of the per-user row counts -> one scatter (position = row_offset[u] + t, no sort) ->
+ * column writer.  row_offset_device [n_organic_users + n_users + 1] and last_view_device [n_organic_users + n_users]
+ * are optional outputs; rows_device[0] receives the number of rows of the log -- if it exceeds cols->capacity the tail
+ * was dropped: call again with larger columns (the rows are a pure function of the arguments).
+ * ps_table_device (nullable, [P]): 'ps' reported by a table agent for each last view (BanditCount, BanditMFSquare).
+ * prev_last_view: BanditCount.last_product_viewed before the first user of this call (-1 = None); train_mode
+ * (RG_TRAIN_*) decides which train calls move it, i.e. what the `lvp` column holds; carry_device (nullable, int32[1])
+ * receives its value after the last user of this call.
+ * totals_device as rg_rollout_out.totals.  Temporary buffers come from the stream-ordered allocator. */
+int rg_generate_logs_device(rg_env *env, const rg_policy *policy, const double *ps_table_device, int64_t user_begin,
+                            int64_t n_organic_users, int64_t n_users, int32_t prev_last_view, int train_mode,
+                            int32_t *carry_device, const rg_log_columns *cols_device, int64_t *row_offset_device, int32_t *last_view_device,
+                            int64_t *rows_device, int64_t *totals_device, int math_mode, void *stream);
+
+/* Agent.train over a whole log, as scatter-adds of the count agents' sufficient statistics (all int32 [P][P], nullable,
+ * accumulated): co_counts += b b^T per organic session (OrganicCount.train, agents/organic_count.py:74-82);
+ * pulls[lvp][a] += 1, clicks[lvp][a] += c per bandit row (BanditCount.train, agents/bandit_count.py:49-62).
+ * train_mode must be the one the columns were generated with.  Needs the columns z, v, a, c, lvp, sess, flags. */
+int rg_count_stats_device(const rg_log_columns *cols_device, int64_t rows, int32_t P, int train_mode,
+                          int32_t *co_counts, int32_t *pulls, int32_t *clicks, void *stream);
+/* The acting table of a count agent: kind 0 = OrganicCount.act, table[v] = argmax_j A[v][j] (A = co_counts, B unused);
+ * kind 1 = BanditCount.act, table[v] = argmax_j (B[v][j] + 1) / (A[v][j] + 2) (A = pulls, B = clicks), ps[v] = that
+ * ratio.  First maximum wins (numpy.argmax). */
+int rg_count_policy_device(int kind, int32_t P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+                           void *stream);
+/* evaluate_IPS / evaluate_SNIPS (evaluate_agent.py:753-835) of a deterministic table policy over the bandit rows of the
+ * users < u_end: out4_device = {sum ee, sum ee^2, sum pi/ps, rows} with ee = c * [a == target[lv]] / ps.
+ * Needs the columns z, u, a, c, ps, lv. */
+int rg_ips_device(const rg_log_columns *cols_device, int64_t rows, int64_t u_end, const int32_t *target_table,
+                  double *out4_device, void *stream);
+
 /* Batched gym protocol.  State of N concurrent users is a caller-owned SoA on the device:
  *   user_id[N] int64, state[N] int32 (RG_*), t[N] int32 (current_time), last_view[N] int32,
  *   omega[N][K] double.

@@ -14,6 +14,7 @@ RG_OK, RG_EINVAL, RG_ECUDA, RG_ENOMEM, RG_ENODEVICE = 0, -1, -2, -3, -4
 ORGANIC, BANDIT, STOP = 0, 1, 2
 POLICY_UNIFORM, POLICY_TABLE, POLICY_USER_VIEWS = 0, 1, 2
 MATH_EXACT, MATH_FAST, MATH_TENSOR = 0, 1, 2
+TRAIN_TEST_AGENT, TRAIN_EVOLUTION_STEP, TRAIN_EVOLUTION_INIT = 0, 1, 2
 
 
 class RecoGymB200Error(RuntimeError):
@@ -44,10 +45,16 @@ class RolloutOut(C.Structure):
         ("log", C.c_void_p), ("log_capacity", C.c_int64), ("log_count", C.c_void_p)]
 
 
+class LogColumns(C.Structure):
+    _fields_ = [("capacity", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "t", "u", "z", "v", "a", "c", "ps", "lv", "lvp", "sess", "flags")]
+
+
 _lib = None
 
 EXPORTS = (
     "rg_env_create", "rg_env_set_seed", "rg_env_destroy", "rg_rollout_device", "rg_rollout_host",
+    "rg_generate_logs_device", "rg_count_stats_device", "rg_count_policy_device", "rg_ips_device",
     "rg_batch_reset_device", "rg_batch_step_device", "rg_batch_continue_device",
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
     "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
@@ -79,6 +86,15 @@ def lib():
     L.rg_rollout_device.argtypes = [vp, C.POINTER(Policy), i64, i64, i64, C.POINTER(RolloutOut), C.c_int, vp]
     L.rg_rollout_host.restype = C.c_int
     L.rg_rollout_host.argtypes = [vp, C.POINTER(Policy), i64, i64, i64, C.POINTER(RolloutOut), C.c_int]
+    L.rg_generate_logs_device.restype = C.c_int
+    L.rg_generate_logs_device.argtypes = [vp, C.POINTER(Policy), vp, i64, i64, i64, i32, C.c_int, vp,
+                                          C.POINTER(LogColumns), vp, vp, vp, vp, C.c_int, vp]
+    L.rg_count_stats_device.restype = C.c_int
+    L.rg_count_stats_device.argtypes = [C.POINTER(LogColumns), i64, i32, C.c_int, vp, vp, vp, vp]
+    L.rg_count_policy_device.restype = C.c_int
+    L.rg_count_policy_device.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
+    L.rg_ips_device.restype = C.c_int
+    L.rg_ips_device.argtypes = [C.POINTER(LogColumns), i64, i64, vp, vp, vp]
     L.rg_batch_reset_device.restype = C.c_int
     L.rg_batch_reset_device.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_int, vp]
     L.rg_batch_step_device.restype = C.c_int

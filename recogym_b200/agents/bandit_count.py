@@ -22,6 +22,7 @@ class BanditCount(Agent):
         self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
 
     def act(self, observation, reward, done):
+        self.sync_host()
         self.update_lpv(observation)
         row = self.ctr[self.last_product_viewed, :]
         action = row.argmax()
@@ -35,6 +36,7 @@ class BanditCount(Agent):
     def train(self, observation, action, reward, done=False):
         # NB the reference credits the pull to last_product_viewed BEFORE updating it from the
         # observation (bandit_count.py:54-57); kept.
+        self.sync_host()
         if action is not None and reward is not None:
             ix, jx = self.last_product_viewed, action["a"]
             self.update_lpv(observation)
@@ -57,6 +59,33 @@ class BanditCount(Agent):
     def reset(self):
         pass
 
+    # ---- device residency (recogym_b200/logs.py) --------------------------------------------------------------
+    _stats = None
+
+    def device_train(self, log):
+        """`train` for every bandit row of a DeviceLog (scatter-add kernel).  The log must have been generated with
+        prev_last_view = self.device_last_view()."""
+        from ..logs import CountStats
+        import torch
+        if self._stats is None:
+            self._stats = CountStats(self.config.num_products, log.env.device, organic=False, bandit=True)
+            self._stats.pulls.copy_(torch.as_tensor(self.pulls_a.astype(np.int32)))
+            self._stats.clicks.copy_(torch.as_tensor(self.clicks_a.astype(np.int32)))
+        self._stats.train(log)
+        self.last_product_viewed = None if self._stats.last_view < 0 else int(self._stats.last_view)
+
+    def device_last_view(self):
+        return -1 if self.last_product_viewed is None else int(self.last_product_viewed)
+
+    def sync_host(self):
+        if self._stats is not None:
+            self.pulls_a = self._stats.pulls.cpu().numpy().astype(np.float64)
+            self.clicks_a = self._stats.clicks.cpu().numpy().astype(np.float64)
+            self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
+            self._stats = None
+
     def device_policy(self):
+        if self._stats is not None:
+            return self._stats.bandit_count_policy()
         table = self.ctr.argmax(axis=1).astype(np.int32)
         return {"policy": "table", "table": table, "ps_table": self.ctr[np.arange(len(table)), table]}

@@ -21,6 +21,7 @@ class OrganicCount(Agent):
         self.corr = None
 
     def act(self, observation, reward, done):
+        self.sync_host()
         self.update_lpv(observation)
         action = self.co_counts[self.last_product_viewed, :].argmax()
         if self.config.with_ps_all:
@@ -33,6 +34,7 @@ class OrganicCount(Agent):
     def train(self, observation, action, reward, done=False):
         """co_counts += b b^T with b the view-count vector of the observation's sessions
         (organic_count.py:74-82); done as a sparse outer product over the distinct views."""
+        self.sync_host()
         sessions = observation.sessions()
         if sessions:
             views, cnt = np.unique(np.array([s["v"] for s in sessions], dtype=np.int64), return_counts=True)
@@ -42,5 +44,26 @@ class OrganicCount(Agent):
         if observation.sessions():
             self.last_product_viewed = observation.sessions()[-1]["v"]
 
+    # ---- device residency (recogym_b200/logs.py): train() over a whole fused log, act() as a table ----------
+    _stats = None
+
+    def device_train(self, log):
+        """`train` for every observation of a DeviceLog (scatter-add kernel); the statistics then live on the GPU
+        until `sync_host()`."""
+        from ..logs import CountStats
+        import torch
+        if self._stats is None:
+            self._stats = CountStats(self.config.num_products, log.env.device, organic=True, bandit=False)
+            self._stats.co_counts.copy_(torch.as_tensor(self.co_counts.astype(np.int32)))
+        self._stats.train(log)
+
+    def sync_host(self):
+        if self._stats is not None:
+            self.co_counts = self._stats.co_counts.cpu().numpy().astype(np.float64)
+            self._stats = None
+
     def device_policy(self):
+        if self._stats is not None:
+            pol = self._stats.organic_count_policy()
+            return {"policy": "table", "table": pol["table"]}
         return {"policy": "table", "table": self.co_counts.argmax(axis=1).astype(np.int32)}

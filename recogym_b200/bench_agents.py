@@ -24,6 +24,20 @@ def _collect_stats(args):
     else:
         train_env = env
     uid = 0
+    log_pol = device_policy(train_env.agent, train_env.config.num_products) if train_env.agent else {"policy": "uniform"}
+    if args.get("device_training", True) and hasattr(new_agent, "device_train") and log_pol is not None \
+            and not getattr(new_agent.config, "with_ps_all", False):
+        # count agents: the whole training phase is ONE fused rollout of the logging policy + scatter-add kernels over
+        # its ordered device log (recogym_b200/logs.py) -- the same train calls as the loops below
+        from . import _lib as L
+        from .logs import generate_logs_device
+        prev = new_agent.device_last_view() if hasattr(new_agent, "device_last_view") else -1
+        log = generate_logs_device(train_env.device_env, args["num_offline_users"], log_pol["policy"],
+                                   log_pol.get("table"), log_pol.get("ps_table"), 0,
+                                   args["num_organic_offline_users"], L.MATH_TENSOR, prev_last_view=prev,
+                                   train_mode=L.TRAIN_TEST_AGENT)
+        new_agent.device_train(log)
+        args = {**args, "num_organic_offline_users": 0, "num_offline_users": 0}
     # offline organic training (bench_agents.py:169-173)
     for _ in range(args["num_organic_offline_users"]):
         train_env.reset(uid)
@@ -61,7 +75,7 @@ def _collect_stats(args):
 
 
 def test_agent(env, agent, num_offline_users=1000, num_online_users=100, num_organic_offline_users=0,
-               num_epochs=1, epoch_with_random_reset=False, with_cache=False, allow_probe=False):
+               num_epochs=1, epoch_with_random_reset=False, with_cache=False, allow_probe=False, device_training=True):
     """-> (median, q0.025, q0.975) of Beta(successes+1, failures+1) (bench_agents.py:215-251)."""
     if with_cache:
         raise NotImplementedError("the on-disk training-log cache of the reference is out of scope")
@@ -71,6 +85,7 @@ def test_agent(env, agent, num_offline_users=1000, num_online_users=100, num_org
             "env": env, "agent": agent, "num_offline_users": num_offline_users,
             "num_online_users": num_online_users, "num_organic_offline_users": num_organic_offline_users,
             "epoch_with_random_reset": epoch_with_random_reset, "epoch": epoch, "allow_probe": allow_probe,
+            "device_training": device_training,
         })
         successes += res[AgentStats.SUCCESSES]
         failures += res[AgentStats.FAILURES]

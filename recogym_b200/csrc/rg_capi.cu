@@ -114,6 +114,15 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
         return fail(RG_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
                     prop.minor);
 
+    {   // temporaries of the log pipeline come from the stream-ordered allocator: keep freed blocks in the pool
+        // instead of returning them to the driver at every synchronisation (a 3 GB arena costs ~100 ms to re-map)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     rg_env *env = new (std::nothrow) rg_env();
     if (!env) return fail(RG_ENOMEM, "out of host memory");
     rg_env_impl &e = env->impl;
@@ -342,6 +351,101 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     cudaFree(arena);
     if (ce != cudaSuccess) return fail(RG_ECUDA, "rollout failed: %s", cudaGetErrorString(ce));
+    return RG_OK;
+}
+
+static int current_num_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+int rg_generate_logs_device(rg_env *env, const rg_policy *policy, const double *ps_table_device, int64_t user_begin,
+                            int64_t n_organic_users, int64_t n_users, int32_t prev_last_view, int train_mode,
+                            int32_t *carry_device, const rg_log_columns *cols, int64_t *row_offset_device, int32_t *last_view_device,
+                            int64_t *rows_device, int64_t *totals_device, int math_mode, void *stream_) {
+    if (!cols || !rows_device) return fail(RG_EINVAL, "null argument");
+    if (cols->capacity < 0) return fail(RG_EINVAL, "negative capacity");
+    if (train_mode < 0 || train_mode > 2) return fail(RG_EINVAL, "unknown train mode %d", train_mode);
+    rg_rollout_out probe;
+    std::memset(&probe, 0, sizeof(probe));
+    int rc = check_rollout_args(env, policy, n_organic_users, n_users, &probe, math_mode);
+    if (rc != RG_OK) return rc;
+    RG_CUDA(cudaSetDevice(env->impl.device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t n = n_organic_users + n_users, cap = cols->capacity;
+    const int64_t ntiles = (n + 4095) / 4096;
+    // one stream-ordered arena: unordered records | ordered records | n_events | last_view | row_offset | scan tiles | count
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_log = take(16 * (size_t)(cap > 0 ? cap : 1)), o_ord = take(16 * (size_t)(cap > 0 ? cap : 1));
+    const size_t o_ne = take(4 * (size_t)(n + 1)), o_lv = take(4 * (size_t)(n + 1));
+    const size_t o_ro = take(8 * (size_t)(n + 1)), o_ts = take(8 * (size_t)(ntiles + 2)), o_cnt = take(16);
+    char *arena = nullptr;
+    RG_CUDA(cudaMallocAsync((void **)&arena, off, stream));
+    cudaError_t ce = cudaMemsetAsync(arena + o_cnt, 0, 16, stream);
+    int32_t *lv = last_view_device ? last_view_device : (int32_t *)(arena + o_lv);
+    long long *ro = row_offset_device ? (long long *)row_offset_device : (long long *)(arena + o_ro);
+    if (ce == cudaSuccess) {
+        rg_rollout_out o;
+        std::memset(&o, 0, sizeof(o));
+        o.n_events = (int32_t *)(arena + o_ne);
+        o.last_view = lv;
+        o.totals = totals_device;
+        o.log = (int32_t *)(arena + o_log);
+        o.log_capacity = cap;
+        o.log_count = (int64_t *)(arena + o_cnt);
+        rc = cap > 0 || n == 0 ? rg_rollout_device(env, policy, user_begin, n_organic_users, n_users, &o, math_mode, stream_)
+                               : fail(RG_EINVAL, "columns without capacity");
+        if (rc != RG_OK) { cudaFreeAsync(arena, stream); return rc; }
+        ce = rg::launch_row_offsets((const int32_t *)(arena + o_ne), n, n_organic_users, ro, (long long *)(arena + o_ts), stream);
+    }
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(rows_device, ro + n, 8, cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess && n > 0)
+        ce = rg::launch_order((const int4 *)(arena + o_log), (const unsigned long long *)(arena + o_cnt), cap, ro,
+                              (int4 *)(arena + o_ord), cap, env->impl.num_sms, stream);
+    if (ce == cudaSuccess)
+        ce = rg::launch_columns((const int4 *)(arena + o_ord), ro, n, n_organic_users, user_begin, lv, prev_last_view,
+                                policy->kind, env->impl.dev.P, ps_table_device, *cols, train_mode, carry_device,
+                                env->impl.num_sms, stream);
+    cudaFreeAsync(arena, stream);
+    if (ce != cudaSuccess) return fail(RG_ECUDA, "generate_logs failed: %s", cudaGetErrorString(ce));
+    return RG_OK;
+}
+
+int rg_count_stats_device(const rg_log_columns *cols, int64_t rows, int32_t P, int train_mode, int32_t *co_counts,
+                          int32_t *pulls, int32_t *clicks, void *stream) {
+    if (!cols || rows < 0 || P < 1 || train_mode < 0 || train_mode > 2) return fail(RG_EINVAL, "bad argument");
+    if (rows > cols->capacity) return fail(RG_EINVAL, "rows exceed the column capacity");
+    if (!cols->z || !cols->v || !cols->a || !cols->c || !cols->lvp || !cols->sess || !cols->flags)
+        return fail(RG_EINVAL, "count statistics need the columns z, v, a, c, lvp, sess, flags");
+    if ((pulls == nullptr) != (clicks == nullptr)) return fail(RG_EINVAL, "pulls and clicks come together");
+    RG_CUDA(rg::launch_count_stats(*cols, rows, P, train_mode, co_counts, pulls, clicks, current_num_sms(),
+                                   (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_count_policy_device(int kind, int32_t P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+                           void *stream) {
+    if ((kind != 0 && kind != 1) || P < 1 || !A || !table || (kind == 1 && !B)) return fail(RG_EINVAL, "bad argument");
+    RG_CUDA(rg::launch_row_argmax(kind, P, A, B, table, ps, (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_ips_device(const rg_log_columns *cols, int64_t rows, int64_t u_end, const int32_t *target_table,
+                  double *out4_device, void *stream_) {
+    if (!cols || rows < 0 || !target_table || !out4_device) return fail(RG_EINVAL, "bad argument");
+    if (rows > cols->capacity) return fail(RG_EINVAL, "rows exceed the column capacity");
+    if (!cols->z || !cols->u || !cols->a || !cols->c || !cols->ps || !cols->lv)
+        return fail(RG_EINVAL, "IPS needs the columns z, u, a, c, ps, lv");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nblocks = current_num_sms() * 4;
+    double *part = nullptr;
+    RG_CUDA(cudaMallocAsync((void **)&part, sizeof(double) * 4 * (size_t)nblocks, stream));
+    cudaError_t ce = rg::launch_ips(*cols, rows, u_end, target_table, part, nblocks, out4_device, stream);
+    cudaFreeAsync(part, stream);
+    if (ce != cudaSuccess) return fail(RG_ECUDA, "ips failed: %s", cudaGetErrorString(ce));
     return RG_OK;
 }
 

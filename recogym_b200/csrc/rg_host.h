@@ -38,5 +38,20 @@ cudaError_t launch_batch(const rg_env_impl &e, int mode, long long N, const long
                          cudaStream_t stream);
 cudaError_t launch_tc_logits(const rg_env_impl &e, const double *omega, const float *shift, float *out,
                              cudaStream_t stream);
+cudaError_t launch_row_offsets(const int32_t *n_events, long long n, long long n_organic_users, long long *row_offset,
+                               long long *tile_scratch, cudaStream_t stream);
+cudaError_t launch_order(const int4 *log, const unsigned long long *log_count, long long log_capacity,
+                         const long long *row_offset, int4 *ordered, long long ordered_capacity, int num_sms,
+                         cudaStream_t stream);
+cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, long long n_total,
+                           long long n_organic_users, long long user_begin, const int32_t *last_view, int prev_last_view,
+                           int policy_kind, int P, const double *ps_table, const rg_log_columns &c, int train_mode,
+                           int32_t *carry_out, int num_sms, cudaStream_t stream);
+cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int32_t *co,
+                               int32_t *pulls, int32_t *clicks, int num_sms, cudaStream_t stream);
+cudaError_t launch_row_argmax(int kind, int P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+                              cudaStream_t stream);
+cudaError_t launch_ips(const rg_log_columns &c, long long rows, long long u_end, const int32_t *target, double *part,
+                       int nblocks, double *out, cudaStream_t stream);
 cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);
 }  // namespace rg

@@ -41,7 +41,7 @@ constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampl
 
 struct Layout {  // byte offsets into dynamic shared memory
     int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
-        nview, amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, pend, pend_list, misc, om32, tilesum, gtile, atile,
+        nview, amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, q3_slot, q3_u, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
 
@@ -78,6 +78,7 @@ __host__ inline void make_layout(Params &p) {
     L.pu = o; if (!p.tc) o += 8 * TU;
     L.rq_u = o; o += 8 * TU;
     L.rq_lse = o; o += 8 * TU;
+    L.q3_u = o; o += 8 * TU;
     L.ptau = o; if (!p.tc) o += 8 * TU;
     L.pcum = o; if (!p.tc) o += 8 * TU;
     L.user = o; o += 8 * TU;
@@ -101,6 +102,7 @@ __host__ inline void make_layout(Params &p) {
     L.prsel = o; o += 4 * TU;
     L.wait = o; o += 4 * TU;
     L.rq_slot = o; o += 4 * TU;
+    L.q3_slot = o; o += 4 * TU;
     L.pend = o; o += 4 * TU;
     L.pend_list = o; o += 4 * TU;
     L.misc = o; o += 64;
@@ -262,6 +264,82 @@ __device__ __forceinline__ void batch_partial_sums(const EnvDev &env, const doub
     }
 }
 
+// TIER 2 sweep on the FP64 tensor path: one DMMA (mma.sync m8n8k4, f64) is the [8 users] x [8 products] x [4 k]
+// block of the logit contraction -- 256 fma per warp instruction with ONE Gamma element per lane as operand, instead
+// of 8 DFMA instructions and PP loads per k.  A = omega (row = user, lane>>2; col = k, lane&3) stays in registers for
+// the whole sweep; B = Gamma^T (row = k, lane&3; col = product, lane>>2) straight from L2, K-major; D (row = user;
+// cols 2*(lane&3), +1).  The accumulation order inside the DMMA is the hardware's; tier 2 does not need the oracle's
+// fma chain, only a bounded error: 2^-40 relative to the logit bound is added to the a-posteriori bound (a binary64
+// dot product of K+1 terms is within (K+1) 2^-53 of it).  Tier 3 keeps the oracle's chains.
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int KS>
+__device__ __forceinline__ void batch_partial_sums_mma(const EnvDev &env, const double *om_s, int KP, double *csum,
+                                                       double *esum, int ncs, int nb, const double *shiftv, int lane,
+                                                       int warp, int nwarps) {
+    constexpr int G = 4;                         // 8-product groups in flight (independent accumulators)
+    const int K = env.K, P = env.P, Ppad = env.Ppad;
+    const int g = lane >> 2, q = lane & 3;
+    const int gu = g < nb ? g : nb - 1;          // rows beyond the batch repeat the last user (results discarded)
+    double a[KS];
+    const double *grow[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int k = 4 * ks + q;
+        a[ks] = k < K ? om_s[gu * KP + k] : 0.0;                       // zero omega: the clamped Gamma row adds 0
+        grow[ks] = env.GammaT + (size_t)(k < K ? k : K - 1) * Ppad;
+    }
+    const double sv = shiftv[gu];
+    const int nch = (Ppad + CHUNK - 1) / CHUNK;
+    for (int c = warp; c < nch; c += nwarps) {
+        double part = 0.0, perr = 0.0;
+        for (int g0 = 0; g0 < CHUNK / 8; g0 += G) {
+            double acc[G][2];
+            int pb[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                acc[i][0] = 0.0; acc[i][1] = 0.0;
+                const int p = c * CHUNK + (g0 + i) * 8 + g;
+                pb[i] = p < Ppad ? p : Ppad - 1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double b[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) b[i] = __ldg(grow[ks] + pb[i]);
+#pragma unroll
+                for (int i = 0; i < G; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a[ks], b[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int p0 = c * CHUNK + (g0 + i) * 8 + 2 * q;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = p0 + h;
+                    if (j < P) {
+                        const double x = (acc[i][h] + __ldg(env.mu_o + j)) * 1.4426950408889634074 - sv;
+                        const double m = (double)ex2_approx((float)x);
+                        part += m;
+                        perr = fma(m, fma(fabs(x), 4.14e-8, 4.8e-7), perr);
+                    }
+                }
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        perr += __shfl_xor_sync(0xffffffffu, perr, 1);
+        perr += __shfl_xor_sync(0xffffffffu, perr, 2);
+        if (q == 0 && g < nb) {
+            csum[(size_t)g * ncs + c] = part;
+            esum[(size_t)g * ncs + c] = perr;
+        }
+    }
+}
+
 // slots/us/shiftv: shared arrays [FB] (slot index, view uniform, tier-2 log-sum-exp or unused);
 // unresolved[f] (shared) is set to 1 when tier 2 cannot certify the draw of user f.
 template <bool T2>
@@ -298,6 +376,12 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         om_s[idx] = k < K ? om64[(size_t)slots[f < nb ? f : nb - 1] * KP + k] : 0.0;
     }
     gsync();
+    if (T2) {   // FP64 tensor path (any nb <= 8 in one pass)
+        if (K <= 20) batch_partial_sums_mma<5>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else if (K <= 32) batch_partial_sums_mma<8>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else if (K <= 64) batch_partial_sums_mma<16>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else batch_partial_sums_mma<32>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+    } else
     switch (nb) {
         case 1: batch_partial_sums<1, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
         case 2: batch_partial_sums<2, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
@@ -418,8 +502,14 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
             found = min(end, P) - 1;
             amb = true;
         } else {
-            // tier 2: twice the a-posteriori error bound of a prefix sum; tier 3: binary64 summation-order level
-            const double tol = T2 ? (2.02 * E + 1e-12 * Z) : 1e-11 * Z;
+            // tier 2: the a-posteriori bound E of sum_p |e_p| enters S^ - u Z^ as (1-u) e(<=j) - u e(>j), i.e. at most
+            // max(u, 1-u) E, plus twice the crossing chunk's share (its masses are recomputed here, the sweep's
+            // values sit in Z^); tier 3: binary64 summation-order level
+            double tol = 1e-11 * Z;
+            if (T2) {
+                const double uu = us[f];
+                tol = 1.01 * (fmax(uu, 1.0 - uu) * E + 2.0 * uu * esum[(size_t)f * ncs + csel]) + 1e-12 * Z;
+            }
             amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
         }
         if (lane == 0) {
@@ -478,17 +568,17 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     double *fb_u = (double *)(smem + L.fb_u);
     double *fb_lse = (double *)(smem + L.fb_lse);
     double *fb_om = (double *)(smem + L.fb_om);
-    double *s_lse = (double *)(smem + L.lse);  // log2-sum-exp of the fp32 pass, per position (ambiguous draws)
     double *s_Z = (double *)(smem + L.pz);
     double *s_u = (double *)(smem + L.pu);
     double *rq_u = (double *)(smem + L.rq_u);       // re-sampling queues [2][TU] (double-buffered by round parity)
     double *rq_lse = (double *)(smem + L.rq_lse);
     int *rq_slot = (int *)(smem + L.rq_slot);
+    int *q3_slot = (int *)(smem + L.q3_slot);      // draws tier 2 could not certify, waiting for a tier-3 sweep
+    double *q3_u = (double *)(smem + L.q3_u);
     int *s_wait = (int *)(smem + L.wait);           // 0 none, 2 queued this round, 1 being re-sampled this round
     double *s_tau = (double *)(smem + L.ptau);
     double *s_cum = (double *)(smem + L.pcum);
     int *s_rsel = (int *)(smem + L.prsel);
-    int *fb_pos = (int *)(smem + L.fb_pos);
     int *fb_unres = (int *)(smem + L.fb_unres);
     int *s_pend = (int *)(smem + L.pend);      // 0 none, 1 drift into s_t, 2 init of a fresh user
     int *pend_list = (int *)(smem + L.pend_list);
@@ -570,7 +660,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         if (tid < TU) s_pend[tid] = 0;
     };
     if (tid < TU) { s_pend[tid] = 0; s_wait[tid] = 0; claim(tid); }
-    if (tid == 0) misc[6] = 0;
+    if (tid == 0) { misc[6] = 0; misc[4] = 0; }
     const bool ASYNC = TC && p.async2 != 0;
     __syncthreads();
     omega_phase();
@@ -620,8 +710,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
         const int nlive = misc[0];
-        const int nq = misc[6];  // draws queued in the previous round
-        if (nlive == 0 && nq == 0) break;
+        const int nq = misc[6];  // draws waiting for a re-sampling sweep (tier 2) ...
+        const int nq3 = misc[4]; // ... and for a tier-3 sweep
+        if (nlive == 0 && nq == 0 && nq3 == 0) break;
 
         // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
         // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
@@ -661,7 +752,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const double nadd = TC ? (double)(tc::TILE_N / 4 + 4 + p.rec_sub * (128 / tc::TILE_N)) : 8.0 * p.rec_sub + 6.0;
                 const double delta = 0.6931471805599453 * dl2 * 1.01 + 4.76837158203125e-07 + nadd * u24;
                 sh = (float)shift;
-                ep = (float)(2.0 * delta * 1.05 + 1e-7);
+                ep = (float)(delta * 1.05 + 5e-8);   // bound of the relative error of every computed mass
             }
             s_shift[tid] = sh;
             s_eps[tid] = ep;
@@ -795,7 +886,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             tc::tc_fence_before();
             __syncthreads();
             tc::tc_fence_after();
-            if (tid == 0) misc[6] = 0;  // the queue has been consumed; pass 2b refills it (after the next barrier)
+            if (ASYNC && tid == 0) misc[6] = 0;  // the queue has been consumed; pass 2b refills it (after the next barrier)
             seq_use += (unsigned)ntile;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
@@ -952,64 +1043,77 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 if (found < 0) {
                     amb = true;
                 } else {
-                    const double tol = (double)s_eps[i] * Z;
-                    amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
+                    // Filter.  Every computed mass is within d (relative) of the exact one; the SAME pass-1 masses
+                    // enter both the prefix sum S^ and the total Z^, so their errors largely cancel in S^ - u Z^:
+                    //   |(S^ - u Z^) - (S - u Z)| <= d [ (1-u) S + u (Z - S) + 2u m(T) ]
+                    // where the last term covers the products of the crossing record tile that are counted once
+                    // with their pass-1 value (in Z^) and once with their recomputed value (in S^).  At the
+                    // crossing S ~ u Z, i.e. the bound is ~ 2u(1-u) d Z instead of the uncorrelated 2 d Z.
+                    const double dlt = (double)s_eps[i], u = s_u[i];
+                    const double tmass = (double)tilesum[(size_t)i * p.nrec_pad + rsel];
+                    const double tl = dlt * ((1.0 - u) * lower + u * fmax(Z - lower, 0.0) + 2.0 * u * tmass) + 1e-10 * Z;
+                    const double tu = dlt * ((1.0 - u) * upper + u * fmax(Z - upper, 0.0) + 2.0 * u * tmass) + 1e-10 * Z;
+                    amb = (tau - lower < tl && found > 0) || (upper - tau < tu && found < P - 1);
                 }
             }
             if (lane == 0) {
                 s_view[slot] = found;
                 if (amb) {
                     const double lse = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
-                    if (ASYNC) {  // re-sampled underneath the next round's pass 1; the slot sits that round out
-                        const int e = atomicAdd(&misc[6], 1);
-                        rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
-                        s_wait[slot] = 2;
-                    } else {
-                        amb_list[atomicAdd(&misc[1], 1)] = i;
-                        s_lse[i] = lse;
-                    }
+                    // queued for a re-sampling sweep; the slot sits out until its draw has been resolved
+                    const int e = atomicAdd(&misc[6], 1);
+                    rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
+                    s_wait[slot] = ASYNC ? 2 : 1;
                 }
             }
         }
         __syncthreads();
 
         // ---- C2: re-sampling of the draws the fp32 filter could not certify: tier 2 (binary64 logits, fp32 ex2,
-        // a-posteriori bound) for all of them, tier 3 (all binary64) for what tier 2 leaves open
-        {
-            const int namb = misc[1];
-            if (tid == 0) misc[4] = 0;
+        // a-posteriori bound), tier 3 (all binary64) for what tier 2 leaves open.  One sweep streams the whole binary64
+        // Gamma (L2 -> SM) whatever the number of users in it, so uncertified draws WAIT in a queue (their slots sit the
+        // rounds out) until FB of them share a sweep; in the tail of the launch (few live slots) they are resolved at once.
+        if (!ASYNC) {
+            const bool tail = nlive < 16;
             for (int tier = 2; tier <= 3; ++tier) {
-                __syncthreads();
-                const int n = tier == 2 ? namb : misc[4];
-                const int *list = tier == 2 ? amb_list : pend_list;  // pend_list doubles as the tier-3 list here
-                for (int b0 = 0; b0 < n; b0 += FB) {
-                    const int nb = min(FB, n - b0);
+                int *qs = tier == 2 ? rq_slot : q3_slot;
+                double *qu = tier == 2 ? rq_u : q3_u;
+                for (;;) {
+                    __syncthreads();
+                    const int n = tier == 2 ? misc[6] : misc[4];
+                    if (n == 0 || (n < FB && !tail)) break;
+                    const int nb = min(FB, n);
                     if (tid < nb) {
-                        const int pos = list[b0 + tid];
-                        const int slot = pos2slot[pos];
-                        const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
-                        fb_slot[tid] = slot;
-                        fb_pos[tid] = pos;
-                        fb_u[tid] = uniform53(w.x, w.y);
-                        fb_lse[tid] = s_lse[pos];
+                        fb_slot[tid] = qs[tid];
+                        fb_u[tid] = qu[tid];
+                        fb_lse[tid] = tier == 2 ? rq_lse[tid] : 0.0;
                         fb_unres[tid] = 0;
                     }
                     __syncthreads();
-                    if (tier == 2) {
+                    if (tier == 2)
                         block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
                                                  fb_om, tid, NTH, 0, ambig64);
-                        if (tid < nb && fb_unres[tid]) pend_list[atomicAdd(&misc[4], 1)] = fb_pos[tid];
-                    } else {
+                    else
                         block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view,
                                                   fb_unres, fb_om, tid, NTH, 0, ambig64);
+                    if (tid == 0) {   // bookkeeping of <= FB results, then pop the front of the queue
+                        for (int f = 0; f < nb; ++f) {
+                            if (tier == 2 && fb_unres[f]) {
+                                const int e3 = misc[4]++;
+                                q3_slot[e3] = fb_slot[f]; q3_u[e3] = fb_u[f];
+                                n_tier3 += 1;
+                            } else {
+                                s_wait[fb_slot[f]] = 0;   // its view is in s_view: advanced by D below
+                            }
+                        }
+                        if (tier == 2) n_fallback += (unsigned long long)nb;
+                        for (int e = nb; e < n; ++e) {
+                            qs[e - nb] = qs[e]; qu[e - nb] = qu[e];
+                            if (tier == 2) rq_lse[e - nb] = rq_lse[e];
+                        }
+                        if (tier == 2) misc[6] = n - nb; else misc[4] = n - nb;
                     }
-                    __syncthreads();
                 }
-            }
-            if (tid == 0) {
-                n_fallback += (unsigned long long)namb;
-                n_tier3 += (unsigned long long)misc[4];
-                misc[1] = 0;
             }
             __syncthreads();
         }

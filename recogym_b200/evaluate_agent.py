@@ -45,11 +45,86 @@ def verify_agents(env, number_of_users, agents, allow_probe=False):
     return pd.DataFrame().from_dict(stat)
 
 
+def _device_evolution_agent(agent):
+    """The count agent behind `agent` when the whole evolution loop can stay on the GPU: OrganicCount / BanditCount,
+    bare or wrapped in an EpsilonGreedy that never explores (epsilon == 0: every action is 'greedy')."""
+    from .agents import BanditCount, EpsilonGreedy, OrganicCount
+    inner = agent
+    if isinstance(agent, EpsilonGreedy):
+        if float(agent.config.epsilon) != 0.0 or agent.config.with_ps_all:
+            return None
+        inner = agent.agent
+    if type(inner) in (OrganicCount, BanditCount) and not inner.config.with_ps_all:
+        return inner
+    return None
+
+
+def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps, training_approach,
+                           math_mode=None):
+    """evaluate_agent (evaluate_agent.py:51-146) with every phase on the GPU: the warm-up users are rolled out under
+    the env's logging policy and the agent trains on their log (RG_TRAIN_EVOLUTION_INIT); each evolution step is ONE
+    fused rollout of the frozen acting table, whose ordered log feeds the training copy (RG_TRAIN_EVOLUTION_STEP) --
+    scatter-add kernels -- and the next acting table is a row arg-max kernel."""
+    import torch
+    from . import _lib as L
+    from .logs import generate_logs_device
+    mm = L.MATH_TENSOR if math_mode is None else math_mode
+    de = env.device_env
+    P = env.config.num_products
+    greedy = inner is not agent          # EpsilonGreedy(epsilon=0) marks every action greedy (epsilon_greedy.py:59-62)
+    lpv = lambda a: a.device_last_view() if hasattr(a, "device_last_view") else -1
+    initial_agent = deepcopy(inner)
+    log_pol = device_policy(env.agent, P) if env.agent else {"policy": "uniform"}
+    if num_initial_train_users > 0:
+        log = generate_logs_device(de, num_initial_train_users, log_pol["policy"], log_pol.get("table"), None, 0, 0, mm,
+                                   prev_last_view=lpv(inner), train_mode=L.TRAIN_EVOLUTION_INIT)
+        inner.device_train(log)
+    unique_user_id = num_initial_train_users
+    rewards = {EvolutionCase.SUCCESS: [], EvolutionCase.SUCCESS_GREEDY: [], EvolutionCase.FAILURE: [],
+               EvolutionCase.FAILURE_GREEDY: [], EvolutionCase.ACTIONS: dict()}
+    acting = inner
+    training = deepcopy(inner)
+    per_action = [[0] for _ in range(P)]
+    for step in range(num_steps):
+        pol = acting.device_policy()
+        log = generate_logs_device(de, num_step_users, pol["policy"], pol.get("table"), pol.get("ps_table"),
+                                   unique_user_id, 0, mm, prev_last_view=lpv(training),
+                                   train_mode=L.TRAIN_EVOLUTION_STEP)
+        tot = log.totals.cpu().numpy()
+        successes, failures = int(tot[4]), int(tot[3] - tot[4])        # real bandit events only: the loop stops at done
+        n = log.rows
+        clicked = log.a[:n][log.c[:n] == 1].long()
+        hist = torch.bincount(clicked, minlength=P).cpu().numpy()
+        training.device_train(log)
+        unique_user_id += num_step_users
+        acting = training
+        for a in range(P):
+            per_action[a][-1] += int(hist[a])
+            per_action[a].append(0)
+        training = deepcopy(initial_agent if training_approach == TrainingApproach.LAST_STEP else acting)
+        rewards[EvolutionCase.SUCCESS].append(successes)
+        rewards[EvolutionCase.SUCCESS_GREEDY].append(successes if greedy else 0)
+        rewards[EvolutionCase.FAILURE].append(failures)
+        rewards[EvolutionCase.FAILURE_GREEDY].append(failures if greedy else 0)
+    rewards[EvolutionCase.ACTIONS] = {a: per_action[a] for a in range(P)}
+    return rewards
+
+
 def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000, num_steps=10,
-                   training_approach=TrainingApproach.ALL_DATA, sliding_window_samples=10000):
-    """Explore/exploit evolution (evaluate_agent.py:51-146) through the facade: the acting policy is
-    frozen inside a step and swapped at the step boundary.  Host-serial (Python agents train per
-    sample); the on-device variant is SURVEY.md 8f rank 1."""
+                   training_approach=TrainingApproach.ALL_DATA, sliding_window_samples=10000, device=None):
+    """Explore/exploit evolution (evaluate_agent.py:51-146): the acting policy is frozen inside a step and swapped at
+    the step boundary.  device=None: count agents (bare or under a never-exploring EpsilonGreedy) with the ALL_DATA /
+    LAST_STEP approaches run entirely on the GPU (`_evaluate_agent_device`); anything else goes user by user through
+    the gym facade with the Python agents, exactly as the reference does."""
+    inner = _device_evolution_agent(agent)
+    if device is None:
+        device = (inner is not None and training_approach in (TrainingApproach.ALL_DATA, TrainingApproach.LAST_STEP)
+                  and (not env.agent or device_policy(env.agent, env.config.num_products) is not None))
+    if device:
+        if inner is None:
+            raise ValueError("the device evolution loop needs a count agent (OrganicCount / BanditCount)")
+        return _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps,
+                                      training_approach)
     initial_agent = deepcopy(agent)
     unique_user_id = 0
     for u in range(num_initial_train_users):

@@ -1,0 +1,197 @@
+"""Device-resident logs and what consumes them.
+
+`generate_logs_device` is AbstractEnv.generate_logs (reference: recogym/envs/abstract.py:241-327) kept on the GPU: the
+fused rollout, then an exclusive scan + one scatter put the rows into the reference's row order and a column writer
+produces the DataFrame columns plus the per-row context (acting last view, session position) the consumers need:
+
+  * `CountStats`  -- OrganicCount.train / BanditCount.train over a whole log as scatter-adds, and the agents' acting
+    tables by a row arg-max (reference: agents/organic_count.py:54-87, agents/bandit_count.py:28-62);
+  * `ips_table_policy` -- evaluate_IPS / evaluate_SNIPS of a table policy (reference: evaluate_agent.py:753-835).
+
+torch supplies the device buffers; every computation is a kernel of librecogym_b200.so behind the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .envs.device_env import _policy_struct
+
+_COLS = (("t", "float32"), ("u", "int32"), ("z", "int8"), ("v", "int32"), ("a", "int32"), ("c", "float32"),
+         ("ps", "float64"), ("lv", "int32"), ("lvp", "int32"), ("sess", "int32"), ("flags", "int8"))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceLog:
+    """Columns of one generate_logs() call on the device (torch tensors, first `rows` entries valid)."""
+
+    def __init__(self, env, capacity):
+        torch = _torch()
+        self.env = env
+        self.capacity = int(capacity)
+        self.rows = 0
+        for name, dt in _COLS:
+            setattr(self, name, torch.empty(self.capacity, dtype=getattr(torch, dt), device=env.torch_device))
+        self.row_offset = None
+        self.last_view = None
+        self.totals = None
+
+    def struct(self):
+        s = L.LogColumns()
+        s.capacity = self.capacity
+        for name, _ in _COLS:
+            setattr(s, name, getattr(self, name).data_ptr())
+        return s
+
+    def to_host(self):
+        """dict of numpy columns (u, t, z, v, a, c as rollout_log returns them, plus ps / lv / lvp / sess)."""
+        n = self.rows
+        out = {name: getattr(self, name)[:n].cpu().numpy() for name, _ in _COLS}
+        out["t"] = out["t"].astype(np.int32)
+        c = out["c"]
+        out["c"] = np.where(np.isnan(c), -1, c).astype(np.int8)
+        return out
+
+    def to_dataframe(self):
+        """The generate_logs DataFrame: t f32, u/v/a Int32 (nullable), z str, c f32, ps, ps-a."""
+        import pandas as pd
+        n = self.rows
+        z = self.z[:n].cpu().numpy()
+        organic = z == 0
+        v = self.v[:n].cpu().numpy()
+        a = self.a[:n].cpu().numpy()
+        df = pd.DataFrame({
+            "t": self.t[:n].cpu().numpy(),
+            "u": pd.array(self.u[:n].cpu().numpy(), dtype=pd.Int32Dtype()),
+            "z": np.where(organic, "organic", "bandit"),
+            "v": pd.array(v, dtype=pd.Int32Dtype()),
+            "a": pd.array(a, dtype=pd.Int32Dtype()),
+            "c": self.c[:n].cpu().numpy(),
+            "ps": self.ps[:n].cpu().numpy(),
+        })
+        df.loc[~organic, "v"] = pd.NA
+        df.loc[organic, "a"] = pd.NA
+        psa = np.empty(n, dtype=object)
+        psa[:] = None
+        empty = np.empty(1, dtype=object)
+        empty[0] = ()
+        psa[~organic] = empty
+        df["ps-a"] = psa
+        return df
+
+
+def generate_logs_device(env, n_users, policy="uniform", table=None, ps_table=None, user_begin=0, n_organic_users=0,
+                         math_mode=L.MATH_TENSOR, prev_last_view=-1, rows_per_user=108.0, log=None,
+                         train_mode=L.TRAIN_TEST_AGENT):
+    """generate_logs(n_users, agent, n_organic_users) -> DeviceLog, everything on the GPU.  `env` is a DeviceEnv.
+    One synchronisation (the row count) per call; a log that does not fit is regenerated into larger columns.
+    train_mode (L.TRAIN_*) names the reference training loop whose train calls the derived columns describe."""
+    torch = _torch()
+    dev = env.torch_device
+    n = int(n_users) + int(n_organic_users)
+    if policy == "table" and not (hasattr(table, "is_cuda") and table.is_cuda):
+        table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
+    if ps_table is not None and not (hasattr(ps_table, "is_cuda") and ps_table.is_cuda):
+        ps_table = torch.as_tensor(np.ascontiguousarray(ps_table, np.float64), device=dev)
+    cap = int(n * rows_per_user) + 4096
+    keep = []
+    pol = _policy_struct(keep, policy, table, env.P, host=False)
+    while True:
+        if log is None or log.capacity < cap:
+            log = DeviceLog(env, cap)
+        log.row_offset = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        log.last_view = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        log.totals = torch.zeros(16, dtype=torch.int64, device=dev)
+        rows = torch.zeros(1, dtype=torch.int64, device=dev)
+        log.carry = torch.zeros(1, dtype=torch.int32, device=dev)
+        log.train_mode = int(train_mode)
+        cols = log.struct()
+        L.check(L.lib().rg_generate_logs_device(
+            env._h, C.byref(pol), C.c_void_p(ps_table.data_ptr()) if ps_table is not None else None, int(user_begin),
+            int(n_organic_users), int(n_users), int(prev_last_view), int(train_mode), C.c_void_p(log.carry.data_ptr()),
+            C.byref(cols),
+            C.c_void_p(log.row_offset.data_ptr()), C.c_void_p(log.last_view.data_ptr()), C.c_void_p(rows.data_ptr()),
+            C.c_void_p(log.totals.data_ptr()), int(math_mode), env._stream()))
+        need = int(rows.item())
+        if need <= log.capacity:
+            log.rows = need
+            log.n_users_total = n
+            log.n_organic_users = int(n_organic_users)
+            log.user_begin = int(user_begin)
+            return log
+        cap = need + 1024
+        log = None
+
+
+class CountStats:
+    """Sufficient statistics of OrganicCount (co_counts) and BanditCount (pulls, clicks) on the GPU, int32 [P][P].
+    Holds no environment handle, so agents that own one stay deep-copyable / picklable."""
+
+    def __init__(self, P, device=0, organic=True, bandit=True):
+        torch = _torch()
+        self.P = int(P)
+        self.device = int(device)
+        dev = torch.device("cuda", self.device)
+        self.co_counts = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if organic else None
+        self.pulls = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if bandit else None
+        self.clicks = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if bandit else None
+        self.last_view = -1     # BanditCount.last_product_viewed carried from one log to the next (-1 = None)
+
+    def _stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream)
+
+    def train(self, log):
+        """agent.train(...) for every train call the loop named by log.train_mode makes on `log`'s users, in the
+        reference's order (bench_agents.py:169-190 / evaluate_agent.py:56-78,100-139).  The log must have been
+        generated with prev_last_view = self.last_view."""
+        cols = log.struct()
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        L.check(L.lib().rg_count_stats_device(C.byref(cols), int(log.rows), self.P, int(log.train_mode),
+                                              p(self.co_counts), p(self.pulls), p(self.clicks), self._stream()))
+        self.last_view = int(log.carry.item())
+
+    def _policy(self, kind, A, B):
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        table = torch.empty(self.P, dtype=torch.int32, device=dev)
+        ps = torch.empty(self.P, dtype=torch.float64, device=dev)
+        L.check(L.lib().rg_count_policy_device(kind, self.P, C.c_void_p(A.data_ptr()),
+                                               C.c_void_p(B.data_ptr()) if B is not None else None,
+                                               C.c_void_p(table.data_ptr()), C.c_void_p(ps.data_ptr()), self._stream()))
+        return {"policy": "table", "table": table, "ps_table": ps}
+
+    def organic_count_policy(self):
+        """OrganicCount.act as a device table (agents/organic_count.py:54-72)."""
+        return self._policy(0, self.co_counts, None)
+
+    def bandit_count_policy(self):
+        """BanditCount.act as a device table, 'ps' = the smoothed click rate (agents/bandit_count.py:28-47)."""
+        return self._policy(1, self.pulls, self.clicks)
+
+
+def ips_table_policy(log, target_table, u_end=None):
+    """evaluate_IPS / evaluate_SNIPS of the deterministic policy a = target_table[last view] on a DeviceLog
+    (evaluate_agent.py:753-835).  Returns dict(ips_mean, ips_se, snips_mean, snips_se, n) with the reference's
+    definitions: se = std(ee) / sqrt(n), SNIPS mean = sum(ee) / sum(ratio).  As in the reference the last user of the
+    log is left out (`for u in range(max(reco_log.u))`)."""
+    torch = _torch()
+    dev = log.env.torch_device
+    if not (hasattr(target_table, "is_cuda") and target_table.is_cuda):
+        target_table = torch.as_tensor(np.ascontiguousarray(target_table, np.int32), device=dev)
+    if u_end is None:
+        u_end = log.user_begin + log.n_users_total - 1
+    out = torch.zeros(4, dtype=torch.float64, device=dev)
+    cols = log.struct()
+    L.check(L.lib().rg_ips_device(C.byref(cols), int(log.rows), int(u_end), C.c_void_p(target_table.data_ptr()),
+                                  C.c_void_p(out.data_ptr()), log.env._stream()))
+    s_ee, s_ee2, s_ratio, n = (float(x) for x in out.cpu().numpy())
+    mean = s_ee / n
+    var = max(s_ee2 / n - mean * mean, 0.0)
+    se = var ** 0.5 / n ** 0.5
+    return {"ips_mean": mean, "ips_se": se, "snips_mean": s_ee / s_ratio if s_ratio else float("nan"), "snips_se": se,
+            "n": int(n), "sum_ee": s_ee, "sum_ratio": s_ratio}

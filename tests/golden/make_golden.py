@@ -112,6 +112,12 @@ def main():
     if "--user-views-only" in sys.argv:
         user_views_cases()
         return
+    if "--train-only" in sys.argv:
+        train_case()
+        return
+    if "--evolution-only" in sys.argv:
+        evolution_case()
+        return
     t1_static_and_stats()
     t2_case("t2_seed42_P10_K5_u100", {"random_seed": 42}, 100)
     t2_case("t2_seed7_P100_K5_u60_o5", {"random_seed": 7, "num_products": 100, "K": 5}, 60, n_organic=5)
@@ -125,6 +131,92 @@ def main():
              "prob_organic_to_bandit": 0.4, "prob_bandit_to_organic": 0.2, "prob_leave_organic": 0.03},
             40)
     user_views_cases()
+    train_case()
+    evolution_case()
+
+
+def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
+    """The reference's count agents trained by test_agent's own loop (bench_agents.py:169-190) on T2 streams, the log
+    the same users produce through generate_logs, and the reference's IPS / SNIPS estimates of the trained
+    OrganicCount on that log (evaluate_agent.py:753-835)."""
+    ref = H.load_reference()
+    from recogym.agents import OrganicCount, organic_count_args, BanditCount, bandit_count_args
+    from recogym.evaluate_agent import evaluate_SNIPS, verify_agents_SNIPS
+    args = {"random_seed": 5, "num_products": 60, "K": 8, "sigma_omega": 0.3}
+    env = H.make_env(args, "T2")
+    sp = H.static_params(env)
+    cfg = env.config
+    P = cfg.num_products
+    oc = OrganicCount(ref.Configuration({**organic_count_args, "num_products": P, "with_ps_all": True}))
+    bc = BanditCount(ref.Configuration({**bandit_count_args, "num_products": P}))
+    uid = 0
+    for _ in range(n_organic):
+        env.reset(uid); uid += 1
+        obs, _, _, _ = env.step(None)
+        for ag in (oc, bc):
+            ag.train(obs, None, None, True)
+    for _ in range(n_users):
+        env.reset(uid); uid += 1
+        new_obs, _, done, reward = env.step(None)
+        while not done:
+            old_obs = new_obs
+            action, new_obs, reward, done, _ = env.step_offline(old_obs, reward, done)
+            for ag in (oc, bc):
+                ag.train(old_obs, action, reward, False)
+        old_obs = new_obs
+        action, _, reward, done, _ = env.step_offline(old_obs, reward, done)
+        for ag in (oc, bc):
+            ag.train(old_obs, action, reward, True)
+    env2 = H.make_env(args, "T2")
+    df = env2.generate_logs(n_users, num_organic_offline_users=n_organic)
+    A = H.logs_to_arrays(df)
+    # off-policy estimates of the trained OrganicCount on a fresh uniform-policy log of the same env
+    env3 = H.make_env(args, "T2")
+    df3 = env3.generate_logs(n_users)
+    # (evaluate_IPS itself no longer runs under numpy 2: `prob_policy != ()` at evaluate_agent.py:776 raises; its
+    # per-row terms c * pi(a) / ps are exactly evaluate_SNIPS's rewards * p_ratio, evaluate_agent.py:777,808-809)
+    rewards, p_ratio = evaluate_SNIPS(oc, df3)
+    snips = verify_agents_SNIPS(df3, {"oc": oc})
+    B = H.logs_to_arrays(df3)
+    save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_organic,
+         sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
+         change_omega_for_bandits=0, policy="uniform", **sp, **{"log_" + k: v for k, v in A.items()},
+         **{"ipslog_" + k: v for k, v in B.items()},
+         co_counts=oc.co_counts, pulls_a=bc.pulls_a, clicks_a=bc.clicks_a, ctr=bc.ctr,
+         bandit_lpv=int(bc.last_product_viewed),
+         ips_rewards=np.asarray(rewards, np.float64), ips_p_ratio=np.asarray(p_ratio, np.float64),
+         snips=np.array([snips["0.025"][0], snips["0.500"][0], snips["0.975"][0]], np.float64))
+    print(name, "rows", len(df), "co sum", oc.co_counts.sum(), "pulls", bc.pulls_a.sum(), "snips", snips.values.tolist())
+
+
+def evolution_case(name="t2_evolution_seed8_P30_K5"):
+    """The reference's evaluate_agent (evaluate_agent.py:51-146) on T2 streams for its two count agents: per-step
+    successes / failures / per-action clicks, and the warm-up statistics left in the agent that was passed in."""
+    ref = H.load_reference()
+    from recogym.agents import OrganicCount, organic_count_args, BanditCount, bandit_count_args
+    from recogym import evaluate_agent, TrainingApproach, EvolutionCase
+    args = {"random_seed": 8, "num_products": 30, "K": 5}
+    n_init, n_step, n_steps = 25, 40, 3
+    out = {}
+    sp = cfg = None
+    for tag, ctor, cargs, approach in (("bc_all", BanditCount, bandit_count_args, TrainingApproach.ALL_DATA),
+                                       ("oc_all", OrganicCount, organic_count_args, TrainingApproach.ALL_DATA),
+                                       ("bc_last", BanditCount, bandit_count_args, TrainingApproach.LAST_STEP)):
+        env = H.make_env(args, "T2")
+        sp, cfg = H.static_params(env), env.config
+        agent = ctor(ref.Configuration({**cargs, "num_products": 30}))
+        rw = evaluate_agent(env, agent, n_init, n_step, n_steps, approach)
+        out[tag + "_success"] = np.array(rw[EvolutionCase.SUCCESS], np.int64)
+        out[tag + "_failure"] = np.array(rw[EvolutionCase.FAILURE], np.int64)
+        out[tag + "_actions"] = np.array([rw[EvolutionCase.ACTIONS][a] for a in range(30)], np.int64)
+        if ctor is BanditCount:
+            out[tag + "_warm_pulls"], out[tag + "_warm_clicks"] = agent.pulls_a, agent.clicks_a
+        else:
+            out[tag + "_warm_co"] = agent.co_counts
+        print(name, tag, "success", rw[EvolutionCase.SUCCESS], "failure", rw[EvolutionCase.FAILURE])
+    save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps,
+         sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
+         change_omega_for_bandits=0, **sp, **out)
 
 
 def user_views_cases():
