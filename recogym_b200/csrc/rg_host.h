@@ -15,6 +15,8 @@ struct rg_env_impl {
     float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
     double *d_om_scratch = nullptr;      // RG_MATH_TENSOR: omega rows of the resident slots
     size_t om_scratch_bytes = 0;
+    float *d_gsum = nullptr;             // RG_MATH_TENSOR: pass-1 mass sums per 32-product group of the resident slots
+    size_t gsum_bytes = 0;
     int2 *d_views = nullptr;             // RG_POLICY_USER_VIEWS: sorted (product, views) lists of the resident users
     size_t views_lists = 0;              // lists allocated (each view_cap entries)
     int view_cap = 0;

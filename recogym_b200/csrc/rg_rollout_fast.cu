@@ -55,6 +55,7 @@ struct Params {
     int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
     int async2;             // tc: tier 2/3 re-sampling runs on warps 5-7 underneath the next round's pass 1
     double *om_scratch;     // tc: the binary64 omega rows live in global memory, [grid][TU][kp]
+    float *gsum;            // tc: pass-1 mass sums per 32-product group, [grid][nsub * 4][TU] (L2-resident scratch)
     Layout L;
 };
 
@@ -167,6 +168,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// (Measured and dropped: sending 3 of every 8 exponentials of the tensor-core epilogue through a degree-5 polynomial
+// on the FMA pipe -- max relative error 2.2e-7, inside the filter's allowance -- takes MUFU time off pass 1 but costs 10
+// issue slots per exponential; with two co-resident CTAs sharing the schedulers the kernel got 10 % slower, 4.6e8 vs
+// 5.1e8 user-steps/s at C3.)
 
 // ---- scalar (one thread per user) pieces --------------------------------------------------------
 // omega init / drift by ONE thread: same operation sequence as warp_omega_update.
@@ -539,6 +545,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     uint64_t *mbar = (uint64_t *)(smem + L.mbar);
     double *om64 = TC ? p.om_scratch + (size_t)blockIdx.x * TU * p.kp : (double *)(smem + L.om64);
     double *csum = (double *)(smem + L.csum);
+    float *const gsum_cta = TC ? p.gsum + (size_t)blockIdx.x * (size_t)p.env.nsub * 4 * TU : nullptr;
     uint64_t *s_user = (uint64_t *)(smem + L.user);
     uint64_t *s_hash = (uint64_t *)(smem + L.hash);
     uint32_t *s_t = (uint32_t *)(smem + L.t);
@@ -856,9 +863,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
                     tc::tc_fence_after();
                     constexpr int HALF = tc::TILE_N;  // columns of this thread (the whole tile row)
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    float *gs_out = gsum_cta + (size_t)tt * (tc::TILE_N / 32) * TU + pos;
 #pragma unroll
                     for (int c = 0; c < HALF; c += 32) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                         float v[32];
                         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)tc::TILE_N +
                                           (uint32_t)c, v);
@@ -874,8 +882,12 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                                 s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
                             }
                         }
+                        // the masses of this 32-product group: kept (coalesced over the 32 users of the warp) so that
+                        // pass 2b only has to recompute ONE group of 32 products instead of the whole record tile
+                        const float cs = (s0 + s1) + (s2 + s3);
+                        gs_out[(size_t)(c / 32) * TU] = cs;
+                        part += cs;
                     }
-                    part += (s0 + s1) + (s2 + s3);
                     if ((tt + 1) % (p.rec_sub * (128 / tc::TILE_N)) == 0 || tt == ntile - 1) {
                         if (act) tilesum[(size_t)pos * p.nrec_pad + rec] = part;
                         part = 0.f;
@@ -983,6 +995,55 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const float shf = s_shift[i];
                 const int p0 = rsel * p.rec_sub * SUB;
                 const int p1 = min(p0 + p.rec_sub * SUB, nsub * SUB);
+              if constexpr (TC) {
+                // the 32-product groups of the record tile: their pass-1 masses were kept by the epilogue; locate the
+                // crossing group with them, then recompute only that group (one product per lane) for the index and
+                // its margins.  (These group sums are the very terms the record-tile sum was built from, up to the
+                // fp32 rounding of that chain, which the mass-error bound accounts for; the filter below charges the
+                // whole record tile as "counted with two different values".)
+                const int ngr = (p1 - p0) / 32;
+                int gsel = -1;
+                for (int g0 = 0; g0 < ngr && gsel < 0; g0 += 32) {
+                    const int gi = g0 + lane;
+                    double x = gi < ngr ? (double)__ldcg(gsum_cta + (size_t)(p0 / 32 + gi) * TU + i) : 0.0;
+                    const double own = x;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= d) x += y;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, (cum + x > tau) && gi < ngr);
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        gsel = g0 + fl;
+                        cum += __shfl_sync(0xffffffffu, x - own, fl);   // mass of the groups before the crossing one
+                    } else {
+                        cum += __shfl_sync(0xffffffffu, x, 31);
+                    }
+                }
+                if (gsel >= 0) {
+                    const int pj = p0 + gsel * 32 + lane;
+                    const float *gp = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & (SUB - 1));
+                    float a0 = 0.f;
+#pragma unroll 7
+                    for (int k = 0; k < K1; ++k) a0 = fmaf(om32[k * TU + i], __ldg(gp + k * SUB), a0);
+                    double x = (double)ex2_approx(a0 - shf);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= d) x += y;
+                    }
+                    const double pre = cum + x;
+                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        found = p0 + gsel * 32 + fl;
+                        upper = __shfl_sync(0xffffffffu, pre, fl);
+                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                        lower = fl > 0 ? below : cum;
+                    }   // else: the recomputed group is lighter than its pass-1 sum by a rounding: ambiguous
+                }
+              } else {
                 // two 128-product tiles per step: 8 masses per lane (8 independent FFMA chains keep 8 x K1 L2 loads
                 // in flight), the 8 group totals by butterfly sums, a scan only in the crossing group
                 bool done = false;
@@ -1040,6 +1101,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         }
                     }
                 }
+              }
                 if (found < 0) {
                     amb = true;
                 } else {
@@ -1335,6 +1397,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.tc = tensor ? 1 : 0;
     p.async2 = tensor ? 1 : 0;
     p.om_scratch = nullptr;
+    p.gsum = nullptr;
     const int K1 = e.dev.K + 1;
     p.kp = e.dev.K | 1;  // odd row stride of the binary64 omega rows: conflict-free per-slot access
     p.ncs = (e.dev.Ppad + CHUNK - 1) / CHUNK + 1;
@@ -1396,6 +1459,16 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.om_scratch_bytes = need;
         }
         p.om_scratch = e.d_om_scratch;
+        const size_t need_g = sizeof(float) * (size_t)max_blocks * (size_t)e.dev.nsub * 4 * TU;
+        if (e.gsum_bytes < need_g) {       // pass-1 group sums of every resident slot (48 MB at C3: L2-resident)
+            if (e.d_gsum) cudaFree(e.d_gsum);
+            e.d_gsum = nullptr;
+            e.gsum_bytes = 0;
+            ce = cudaMalloc((void **)&e.d_gsum, need_g);
+            if (ce != cudaSuccess) return ce;
+            e.gsum_bytes = need_g;
+        }
+        p.gsum = e.d_gsum;
         rollout_cta_kernel<true><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     } else {
         rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
