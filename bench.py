@@ -360,7 +360,9 @@ def main():
                    "policy": wl["policy"], "device_policies": [p for _, p, _ in policies], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
                    "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
                    "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
-                   "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7])},
+                   "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7]),
+                   "phase_cycle_share": dict(zip(("compact", "pass1", "pass2", "resample", "advance", "omega"),
+                                                 [round(float(x) / max(1.0, float(ev[10:16].sum())), 4) for x in ev[10:16]]))},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": args.steps * len(policies),

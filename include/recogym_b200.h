@@ -104,7 +104,8 @@ typedef struct rg_rollout_out {
     int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
                             [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] binary64-ambiguous
                             samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, [9] RG_POLICY_USER_VIEWS:
-                            users whose distinct views overflowed the device list (must be 0), rest reserved */
+                            users whose distinct views overflowed the device list (must be 0); [10..15] diagnostic, CTA-batched
+                            kernels: SM cycles per phase (compact, pass 1, pass 2, re-sampling, advance, omega) */
     /* Event log == the rows of the generate_logs DataFrame (abstract.py:256-327), unordered: one int32x4
      * record {u = user_id - user_begin, t, x = product viewed | action, flags} per row, flags bit 0: z
      * (0 organic, 1 bandit), bit 1: click, bit 2: phantom row after done (abstract.py:311-316).  Rows of one

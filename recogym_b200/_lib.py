@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librecogym_b200.so")
+LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(_HERE, "librecogym_b200.so")   # override: kernel experiments
 
 RG_OK, RG_EINVAL, RG_ECUDA, RG_ENOMEM, RG_ENODEVICE = 0, -1, -2, -3, -4
 ORGANIC, BANDIT, STOP = 0, 1, 2

@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // NBUF accumulator tiles of TILE_N columns
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
     unsigned long long n_fallback = 0, n_tier3 = 0;
+    unsigned long long ph_a = 0, ph_b = 0, ph_c = 0, ph_c2 = 0, ph_d = 0, ph_o = 0;
     unsigned ambig64 = 0;
 
     auto claim = [&](int slot) -> bool {  // next user id from the global queue -> reset()
@@ -702,6 +703,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     const int tx = tid & 15, ty = tid >> 4;
 
     for (;;) {
+        long long tk0 = clock64();   // diagnostic: cycles per phase as seen by thread 0 (totals[10..15])
         // ---- A: compact the live slots into positions 0..nlive-1 (no data moves: pos2slot indirection)
         if (warp == 0) {
             int base = 0;
@@ -766,6 +768,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
 
+        { const long long tk1 = clock64(); ph_a += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- B: pass 1, dense contraction + exponentials + per-record-tile partial sums
         if constexpr (TC) {
             // Tensor-core form.  A = omega tile (tf32 hi/lo, UMMA K-major layout) written by the CTA, B = Gamma
@@ -959,6 +962,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             seq_use += (unsigned)nsub;
         }
 
+        { const long long tk1 = clock64(); ph_b += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- C: pass 2a, one thread per live user: view uniform, total mass, tau = u*Z, the record tile that
         // contains tau and the mass before it (sequential binary64 sums of the fp32 tile sums)
         if (tid < nlive) {
@@ -1131,6 +1135,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
 
+        { const long long tk1 = clock64(); ph_c += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- C2: re-sampling of the draws the fp32 filter could not certify: tier 2 (binary64 logits, fp32 ex2,
         // a-posteriori bound), tier 3 (all binary64) for what tier 2 leaves open.  One sweep streams the whole binary64
         // Gamma (L2 -> SM) whatever the number of users in it, so uncertified draws WAIT in a queue (their slots sit the
@@ -1186,6 +1191,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             for (int s2 = 0; s2 < tc_prologue; ++s2) issue_load(seq_use + (unsigned)s2);
         }
 
+        { const long long tk1 = clock64(); ph_c2 += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- D: advance the users.  D1 (one thread per slot) finishes the organic event: bookkeeping of the
         // view, transition.  D2 (one warp per user) runs the bandit events: the draws of an event depend only
         // on (user, t), so lane j evaluates the event at time t+j assuming the run is still alive; the run ends
@@ -1340,8 +1346,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
         }
         __syncthreads();
+        { const long long tk1 = clock64(); ph_d += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         omega_phase();
         __syncthreads();
+        { const long long tk1 = clock64(); ph_o += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
     }
 
     // ---- drain the prefetched tiles (a CTA must not exit with bulk copies in flight)
@@ -1368,6 +1376,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
     // ---- totals: warp reduction, one atomic per counter per warp
     if (p.out.totals) {
+        if (tid == 0) {   // SM cycles thread 0 of this CTA spent in each phase (diagnostic, summed over the CTAs)
+            atomicAdd(p.out.totals + 10, ph_a); atomicAdd(p.out.totals + 11, ph_b); atomicAdd(p.out.totals + 12, ph_c);
+            atomicAdd(p.out.totals + 13, ph_c2); atomicAdd(p.out.totals + 14, ph_d); atomicAdd(p.out.totals + 15, ph_o);
+        }
         unsigned long long v[9] = {tot_users, tot_events, tot_org, tot_ban, tot_clk, tot_ph, n_fallback,
                                    (unsigned long long)ambig64, n_tier3};
 #pragma unroll
@@ -1404,7 +1416,8 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     const int nsub = e.dev.nsub;
     // record tiles: at most 64 partial sums per user, at least 2 sub-tiles each
     int rec_sub = 2;
-    while ((nsub + rec_sub - 1) / rec_sub > 64) ++rec_sub;
+    static const int rec_max = [] { const char *v = getenv("RG_REC_MAX"); const int x = v ? atoi(v) : 0; return x > 0 ? x : 64; }();
+    while ((nsub + rec_sub - 1) / rec_sub > rec_max) ++rec_sub;
     if (rec_sub > nsub) rec_sub = nsub;
     p.rec_sub = rec_sub;
     p.nrec = (nsub + rec_sub - 1) / rec_sub;
