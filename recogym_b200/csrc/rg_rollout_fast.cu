@@ -169,6 +169,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// (Measured and dropped, all on 1xB200 at C3 with 5.9e8 user-steps/s as the baseline: software-pipelining the tcgen05.ld
+// of the next 32 columns under the exponentials of the current ones (5.86e8); issuing the 32 exponentials of a chunk
+// before any addition (5.90e8); 64-product UMMA tiles with 4-6 ring stages (4.4e8); one pass-1 token per SM so that the
+// two co-resident CTAs alternate on the MUFU pipe (5.56e8 vs 5.82e8 in the same run).  The epilogue warp issues one
+// MUFU.EX2 per ~14 cycles whether or not the other CTA is in pass 1.)
 // (Measured and dropped: sending 3 of every 8 exponentials of the tensor-core epilogue through a degree-5 polynomial
 // on the FMA pipe -- max relative error 2.2e-7, inside the filter's allowance -- takes MUFU time off pass 1 but costs 10
 // issue slots per exponential; with two co-resident CTAs sharing the schedulers the kernel got 10 % slower, 4.6e8 vs
