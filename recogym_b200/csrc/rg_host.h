@@ -15,6 +15,8 @@ struct rg_env_impl {
     float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
     double *d_om_scratch = nullptr;      // RG_MATH_TENSOR: omega rows of the resident slots
     size_t om_scratch_bytes = 0;
+    double *d_csum_scratch = nullptr;    // CUDA-core form with large P x K: re-sampling partial sums spilled to global memory
+    size_t csum_scratch_bytes = 0;
     float *d_gsum = nullptr;             // RG_MATH_TENSOR: pass-1 mass sums per 32-product group of the resident slots
     size_t gsum_bytes = 0;
     int2 *d_views = nullptr;             // RG_POLICY_USER_VIEWS: sorted (product, views) lists of the resident users

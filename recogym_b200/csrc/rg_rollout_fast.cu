@@ -54,7 +54,9 @@ struct Params {
     int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
     int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
     int async2;             // tc: tier 2/3 re-sampling runs on warps 5-7 underneath the next round's pass 1
-    double *om_scratch;     // tc: the binary64 omega rows live in global memory, [grid][TU][kp]
+    double *om_scratch;     // tc (or spill >= 2): the binary64 omega rows live in global memory, [grid][TU][kp]
+    double *csum_scratch;   // spill >= 1: partial sums of the re-sampling sweeps in global memory, [grid][ncs * FB * 2]
+    int spill;              // CUDA-core form, large P x K: 0 all in shared memory, 1 csum global, 2 csum + omega global
     float *gsum;            // tc: pass-1 mass sums per 32-product group, [grid][nsub * 4][TU] (L2-resident scratch)
     Layout L;
 };
@@ -69,8 +71,8 @@ __host__ inline void make_layout(Params &p) {
     const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES_B;  // one 64-product B tile (hi + lo)
     const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
     L.mbar = o; o += 8 * (kMaxStages + 2 * NBUF + 1);  // ring, NBUF TMEM-full, NBUF TMEM-empty barriers, TMEM address
-    L.om64 = o; if (!p.tc) o += 8 * TU * p.kp;
-    L.csum = o; if (!p.tc || p.async2) o += 8 * p.ncs * FB * 2;
+    L.om64 = o; if (!p.tc && p.spill < 2) o += 8 * TU * p.kp;
+    L.csum = o; if ((!p.tc || p.async2) && p.spill < 1) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
     L.fb_om = o; o += 8 * FB * p.kp;
@@ -548,8 +550,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     uint64_t *mbar = (uint64_t *)(smem + L.mbar);
-    double *om64 = TC ? p.om_scratch + (size_t)blockIdx.x * TU * p.kp : (double *)(smem + L.om64);
-    double *csum = (double *)(smem + L.csum);
+    double *om64 = (TC || p.spill >= 2) ? p.om_scratch + (size_t)blockIdx.x * TU * p.kp : (double *)(smem + L.om64);
+    double *csum = p.spill >= 1 ? p.csum_scratch + (size_t)blockIdx.x * (size_t)p.ncs * FB * 2 : (double *)(smem + L.csum);
     float *const gsum_cta = TC ? p.gsum + (size_t)blockIdx.x * (size_t)p.env.nsub * 4 * TU : nullptr;
     uint64_t *s_user = (uint64_t *)(smem + L.user);
     uint64_t *s_hash = (uint64_t *)(smem + L.hash);
@@ -1414,6 +1416,8 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.tc = tensor ? 1 : 0;
     p.async2 = tensor ? 1 : 0;
     p.om_scratch = nullptr;
+    p.csum_scratch = nullptr;
+    p.spill = 0;
     p.gsum = nullptr;
     const int K1 = e.dev.K + 1;
     p.kp = e.dev.K | 1;  // odd row stride of the binary64 omega rows: conflict-free per-slot access
@@ -1431,7 +1435,11 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     const int hi_stage = tensor ? kMaxStages : 3, lo_stage = tensor ? NBUF : 2;
     const int two_ctas = 113 * 1024;  // (228 KB - 1 KB reserved per CTA) / 2
     int best_stage = 0;
+    // (CUDA-core form) when P x K is too large for one CTA's shared memory, the partial sums of the re-sampling sweeps,
+    // then also the binary64 omega rows, move to an L2-resident global scratch (C4: P = 100 000, K = 64)
+    for (int spill = 0; spill <= (tensor ? 0 : 2) && !best_stage; ++spill)
     for (int pass = 0; pass < 2 && !best_stage; ++pass) {
+        p.spill = spill;
         const int limit = pass == 0 ? two_ctas : 227 * 1024;
         // asynchronous re-sampling (warps 5-7 underneath pass 1) is correct but measured SLOWER at C3 (3.2e8 vs
         // 4.1e8 steps/s: three warps take longer over the sweep than pass 1 lasts); opt-in via RG_ASYNC_RESAMPLE=1
@@ -1466,7 +1474,19 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     long long blocks = (n_total + TU - 1) / TU;
     const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
     if (blocks > max_blocks) blocks = max_blocks;
-    if (tensor) {
+    if (p.spill >= 1) {
+        const size_t need_c = sizeof(double) * (size_t)max_blocks * (size_t)p.ncs * FB * 2;
+        if (e.csum_scratch_bytes < need_c) {
+            if (e.d_csum_scratch) cudaFree(e.d_csum_scratch);
+            e.d_csum_scratch = nullptr;
+            e.csum_scratch_bytes = 0;
+            ce = cudaMalloc((void **)&e.d_csum_scratch, need_c);
+            if (ce != cudaSuccess) return ce;
+            e.csum_scratch_bytes = need_c;
+        }
+        p.csum_scratch = e.d_csum_scratch;
+    }
+    if (tensor || p.spill >= 2) {
         const size_t need = sizeof(double) * (size_t)max_blocks * TU * p.kp;
         if (e.om_scratch_bytes < need) {   // binary64 omega rows of every resident slot (grown once per env)
             if (e.d_om_scratch) cudaFree(e.d_om_scratch);
@@ -1477,6 +1497,8 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.om_scratch_bytes = need;
         }
         p.om_scratch = e.d_om_scratch;
+    }
+    if (tensor) {
         const size_t need_g = sizeof(float) * (size_t)max_blocks * (size_t)e.dev.nsub * 4 * TU;
         if (e.gsum_bytes < need_g) {       // pass-1 group sums of every resident slot (48 MB at C3: L2-resident)
             if (e.d_gsum) cudaFree(e.d_gsum);

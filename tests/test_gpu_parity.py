@@ -236,6 +236,24 @@ def test_c3_shape_fast_equals_exact_on_device():
     de.close()
 
 
+def test_c4_shape_fast_equals_exact_on_device():
+    """P=100000, K=64 (BASELINE C4): the CTA-batched kernel needs its global-memory spill of the re-sampling sums and of
+    the omega rows (one CTA per SM); RG_MATH_TENSOR falls back to the CUDA-core contraction for this K.  Discrete
+    results must equal the all-binary64 sampler."""
+    from recogym_b200 import DeviceEnv
+    cfg, sp = synthetic_env(100000, 64, 42)
+    de = DeviceEnv(sp, 1, 0.1, 42)
+    table = np.random.RandomState(1).randint(0, 100000, 100000).astype(np.int32)
+    a = de.rollout_host(400, "table", table, 0, 0, 0, per_user=True, hist=True, omega=True)
+    for mode in (1, 2):
+        b = de.rollout_host(400, "table", table, 0, 0, mode, per_user=True, hist=True, omega=True)
+        for k in PER_USER + ("hash", "view_hist", "action_hist", "click_hist", "omega"):
+            assert np.array_equal(a[k], b[k]), (mode, k)
+        assert np.array_equal(a["totals"][:6], b["totals"][:6])
+        assert a["totals"][7] == 0 and b["totals"][7] == 0
+    de.close()
+
+
 def test_batch_protocol_equals_oracle(oracle):
     """rg_batch_reset/step/continue == the oracle's reset/step, sessions included (tiny sess_cap
     forces the continuation path)."""
