@@ -165,13 +165,17 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     }
 
     // tf32 hi/lo UMMA tiles of the tensor-core sampler (layout: rg_tensor.cuh)
-    const int KC = rg::tc::kt_chunks(K);
-    const size_t tile_floats = (size_t)2 * KC * (rg::tc::CHUNK_BYTES_B / 4);   // one 64-product tile, hi + lo
+    int KC = 0, KCs = 0, nslab = 0;
+    rg::tc::kt_slabs(K, &KC, &KCs, &nslab);
+    const size_t slab_floats = (size_t)2 * KCs * (rg::tc::CHUNK_BYTES_B / 4);   // one K slab of one B tile, hi + lo
+    const size_t tile_floats = slab_floats * nslab;
     std::vector<float> GTC((size_t)nsub * (128 / rg::tc::TILE_N) * tile_floats, 0.f);
     for (int p = 0; p < nsub * 128; ++p) {
-        float *tile = GTC.data() + (size_t)(p / rg::tc::TILE_N) * tile_floats;
+        float *tile0 = GTC.data() + (size_t)(p / rg::tc::TILE_N) * tile_floats;
         const int row = p % rg::tc::TILE_N;
         for (int k = 0; k < KC * 4; ++k) {
+            float *tile = tile0 + (size_t)(k / (4 * KCs)) * slab_floats;
+            const int kk = k % (4 * KCs);
             float x = 0.f;
             if (p < P) {
                 if (k < K) x = (float)(d->Gamma[(size_t)p * K + k] * kLog2e);
@@ -181,8 +185,8 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
                 x = -1e30f;
             }
             const float hi = rg::tc::tf32_hi(x);
-            tile[rg::tc::tile_index_b(0, KC, row, k)] = hi;
-            tile[rg::tc::tile_index_b(1, KC, row, k)] = rg::tc::tf32_hi(x - hi);
+            tile[rg::tc::tile_index_b(0, KCs, row, kk)] = hi;
+            tile[rg::tc::tile_index_b(1, KCs, row, kk)] = rg::tc::tf32_hi(x - hi);
         }
     }
 
@@ -225,6 +229,8 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     v.nsub = nsub;
     v.GTC = e.d_GTC;
     v.KC = KC;
+    v.KCs = KCs;
+    v.nslab = nslab;
     v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
     v.seed = d->seed;
     *out = env;

@@ -24,8 +24,8 @@ struct EnvDev {
     double muabsmax;           // max_p |mu_organic[p]|
     const float *G32;          // [nsub][K+1][128] fp32 tiles of log2(e)*Gamma (row K = log2(e)*mu_organic)
     int nsub;                  // number of 128-product tiles
-    const float *GTC;          // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
-    int KC;                    // 16-byte K chunks per UMMA operand row
+    const float *GTC;          // [tiles][nslab][2][KCs][TILE_N/8][8][4] tf32 hi/lo UMMA tiles in K slabs (rg_tensor.cuh)
+    int KC, KCs, nslab;        // 16-byte K chunks per operand row: padded total, per slab, slabs (KC = KCs * nslab)
     int change_omega_for_bandits;
     uint64_t seed;
 };

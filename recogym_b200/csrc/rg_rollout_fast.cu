@@ -67,10 +67,11 @@ __host__ inline void make_layout(Params &p) {
     const int K = p.env.K, K1 = K + 1;
     Layout &L = p.L;
     int o = 0;
-    const int KC = tc::kt_chunks(K);
-    const int tc_tile_bytes = 2 * KC * tc::CHUNK_BYTES_B;  // one 64-product B tile (hi + lo)
+    int KC = 0, KCs = 0, nslab = 0;
+    tc::kt_slabs(K, &KC, &KCs, &nslab);
+    const int tc_tile_bytes = 2 * KCs * tc::CHUNK_BYTES_B;  // one K slab of a B tile (hi + lo): the ring unit
     const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
-    L.mbar = o; o += 8 * (kMaxStages + 2 * NBUF + 1);  // ring, NBUF TMEM-full, NBUF TMEM-empty barriers, TMEM address
+    L.mbar = o; o += 8 * (2 * kMaxStages + 2 * NBUF + 1);  // ring full / ring free, NBUF TMEM-full, NBUF TMEM-empty, TMEM address
     L.om64 = o; if (!p.tc && p.spill < 2) o += 8 * TU * p.kp;
     L.csum = o; if ((!p.tc || p.async2) && p.spill < 1) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
@@ -550,8 +551,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     uint64_t *mbar = (uint64_t *)(smem + L.mbar);
+    // (the spill levels only exist in the CUDA-core form: for TC both selections are compile-time)
     double *om64 = (TC || p.spill >= 2) ? p.om_scratch + (size_t)blockIdx.x * TU * p.kp : (double *)(smem + L.om64);
-    double *csum = p.spill >= 1 ? p.csum_scratch + (size_t)blockIdx.x * (size_t)p.ncs * FB * 2 : (double *)(smem + L.csum);
+    double *csum = (!TC && p.spill >= 1) ? p.csum_scratch + (size_t)blockIdx.x * (size_t)p.ncs * FB * 2
+                                         : (double *)(smem + L.csum);
     float *const gsum_cta = TC ? p.gsum + (size_t)blockIdx.x * (size_t)p.env.nsub * 4 * TU : nullptr;
     uint64_t *s_user = (uint64_t *)(smem + L.user);
     uint64_t *s_hash = (uint64_t *)(smem + L.hash);
@@ -601,19 +604,21 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *tilesum = (float *)(smem + L.tilesum);
     float *gtile = (float *)(smem + L.gtile);
     float *a_tile = (float *)(smem + L.atile);
-    uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
-    uint64_t *dempty = mbar + kMaxStages + NBUF;           // TC: accumulator tile drained by the 4 epilogue warps
-    uint32_t *tmem_slot = (uint32_t *)(mbar + kMaxStages + 2 * NBUF);
-    const int KC = env.KC;
-    const unsigned tc_tile_bytes = 2u * (unsigned)KC * tc::CHUNK_BYTES_B;
+    uint64_t *sfree = mbar + kMaxStages;                   // TC: the UMMAs that read this ring stage have completed
+    uint64_t *dfull = mbar + 2 * kMaxStages;               // TC: accumulator tile ready, one per TMEM buffer
+    uint64_t *dempty = dfull + NBUF;                       // TC: accumulator tile drained by the 4 epilogue warps
+    uint32_t *tmem_slot = (uint32_t *)(dempty + NBUF);
+    const int KC = env.KC, KCs = env.KCs, nslab = env.nslab;
+    const unsigned tc_tile_bytes = 2u * (unsigned)KCs * tc::CHUNK_BYTES_B;   // one K slab of a B tile
 
     const unsigned tile_bytes = TC ? tc_tile_bytes : (unsigned)(4 * K1 * SUB);
     const int nsub = env.nsub, nstage = p.nstage;
-    const int ntile = TC ? nsub * (128 / tc::TILE_N) : nsub;  // tiles streamed per round
+    const int ntile = TC ? nsub * (128 / tc::TILE_N) : nsub;  // product tiles per round
+    const int nunit = TC ? ntile * nslab : nsub;               // ring units streamed per round (TC: K slabs of tiles)
 
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < nstage; ++s) { mbar_init(&mbar[s], 1); if (TC) mbar_init(&sfree[s], 1); }
         if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], 4); }
         fence_barrier_init();
         misc[1] = 0;
@@ -681,10 +686,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     omega_phase();
     __syncthreads();
 
-    unsigned seq_use = 0;  // sequence number of the next tile to consume (same in every thread)
-    auto issue_load = [&](unsigned seq) {  // thread 0 only: tile (seq % nsub) -> ring stage (seq % nstage)
+    unsigned seq_use = 0;   // sequence number of the next ring unit to consume (same in every thread)
+    auto issue_load = [&](unsigned seq) {  // thread 0 only: unit (seq % nunit) -> ring stage (seq % nstage)
         const int stage = (int)(seq % (unsigned)nstage);
-        const int sub = (int)(seq % (unsigned)ntile);
+        const int sub = (int)(seq % (unsigned)nunit);
         mbar_expect_tx(&mbar[stage], tile_bytes);
         if (TC)
             tma_bulk_g2s((unsigned char *)gtile + (size_t)stage * tile_bytes, env.GTC + (size_t)sub * (tile_bytes / 4),
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     };
     // non-TC: the ring is always nstage-1 tiles ahead, across rounds.  TC: the ring bytes are reused between
     // pass 1 and the next round, so each round starts with its own prologue of min(nstage, nsub) loads.
-    const int tc_prologue = nstage < ntile ? nstage : ntile;
+    const int tc_prologue = nstage < nunit ? nstage : nunit;
     if (tid == 0) {
         if (TC) for (int s = 0; s < tc_prologue; ++s) issue_load((unsigned)s);
         else for (int s = 0; s < nstage - 1; ++s) issue_load((unsigned)s);
@@ -808,20 +813,37 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
                 // has completed, i.e. independently of the epilogue.
                 if (lane == 0) {
-                    for (int tt = 0; tt < ntile; ++tt) {
-                        const unsigned gs = seq_use + (unsigned)tt;
-                        const unsigned st = gs % (unsigned)nstage, buf = gs % NBUF, use = gs / NBUF;
+                    const unsigned tile_use = seq_use / (unsigned)nslab;   // accumulator tiles consumed so far
+                    for (int uu = 0; uu < nunit; ++uu) {   // ring units: K slab sl of product tile tt
+                        const unsigned gs = seq_use + (unsigned)uu;
+                        const unsigned st = gs % (unsigned)nstage;
+                        const int tt = uu / nslab, sl = uu - tt * nslab;
+                        const unsigned gt = tile_use + (unsigned)tt, buf = gt % NBUF, use = gt / NBUF;
                         mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
-                        if (use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
+                        if (sl == 0 && use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
                         tc::tc_fence_after();
-                        tc::issue_tile_mmas(tmem_base + buf * (uint32_t)tc::TILE_N, a_saddr, ring_saddr + st * tile_bytes, KC);
-                        tc::umma_commit(&dfull[buf]);
-                        if (tt > 0 && tt - 1 + nstage < ntile) {
-                            // MMA(gs-1) complete <=> dfull of its buffer completed its phase
+                        tc::issue_slab_mmas(tmem_base + buf * (uint32_t)tc::TILE_N, a_saddr, KC, sl,
+                                            ring_saddr + st * tile_bytes, KCs);
+                        tc::umma_commit(&sfree[st]);                       // this ring stage may be refilled ...
+                        if (sl == nslab - 1) tc::umma_commit(&dfull[buf]);  // ... and the accumulator tile is complete
+                        if (ASYNC && uu > 0 && uu - 1 + nstage < nunit) {   // (ASYNC: no free warp for the loader)
                             const unsigned gp = gs - 1u;
-                            mbar_wait(&dfull[gp % NBUF], (gp / NBUF) & 1u);
+                            mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
                             issue_load(gp + (unsigned)nstage);
                         }
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 5 && !ASYNC) {
+                // ---- loader (one thread): refills a ring stage the moment the UMMAs that read it have completed.
+                // Decoupled from the MMA issuer: that thread is blocked on "B tile landed" most of the time, and a
+                // refill issued from there would start a full TMA latency late.  sfree[stage] flips once per use of
+                // the stage and the next use needs this thread's load, so a phase can never be missed.
+                if (lane == 0) {
+                    for (int uu = 0; uu + nstage < nunit; ++uu) {
+                        const unsigned gp = seq_use + (unsigned)uu;
+                        mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
+                        issue_load(gp + (unsigned)nstage);
                     }
                 }
                 __syncwarp();
@@ -867,8 +889,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const bool act = pos < nlive;
                 float part = 0.f;
                 int rec = 0;
+                const unsigned tile_use = seq_use / (unsigned)nslab;
                 for (int tt = 0; tt < ntile; ++tt) {
-                    const unsigned gs = seq_use + (unsigned)tt;
+                    const unsigned gs = tile_use + (unsigned)tt;
                     const unsigned buf = gs % NBUF;
                     mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
                     tc::tc_fence_after();
@@ -909,7 +932,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             __syncthreads();
             tc::tc_fence_after();
             if (ASYNC && tid == 0) misc[6] = 0;  // the queue has been consumed; pass 2b refills it (after the next barrier)
-            seq_use += (unsigned)ntile;
+            seq_use += (unsigned)nunit;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
         } else {

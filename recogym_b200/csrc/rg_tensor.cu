@@ -54,12 +54,13 @@ __device__ void build_a_tile(float *a_tile, int KC, int K, const double *omega, 
     }
 }
 
-__global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict__ GTC, int nsub, int KC, int K,
+__global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict__ GTC, int nsub, int KC, int KCs,
+                                                        int nslab, int K,
                                                         const double *__restrict__ omega,
                                                         const float *__restrict__ shift, float *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned a_bytes = 2u * (unsigned)KC * CHUNK_BYTES, tile_bytes = 2u * (unsigned)KC * CHUNK_BYTES_B;
+    const unsigned a_bytes = 2u * (unsigned)KC * CHUNK_BYTES, tile_bytes = 2u * (unsigned)KCs * CHUNK_BYTES_B;  // one slab
     float *a_tile = (float *)smem;
     float *b_tile = (float *)(smem + a_bytes);
     uint64_t *bars = (uint64_t *)(smem + a_bytes + tile_bytes);  // [0] TMA, [1] MMA
@@ -78,19 +79,22 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    for (int sub = 0; sub < nsub * (128 / TILE_N); ++sub) {  // TILE_N-product tiles
-        const unsigned parity = (unsigned)sub & 1u;
-        if (tid == 0) {
-            mbar_expect_tx(&bars[0], tile_bytes);
-            bulk_g2s(b_tile, GTC + (size_t)sub * (tile_bytes / 4), tile_bytes, &bars[0]);
+    unsigned unit = 0;
+    for (int sub = 0; sub < nsub * (128 / TILE_N); ++sub) {  // TILE_N-product tiles, each in nslab K slabs
+        for (int sl = 0; sl < nslab; ++sl, ++unit) {
+            const unsigned parity = unit & 1u;
+            if (tid == 0) {
+                mbar_expect_tx(&bars[0], tile_bytes);
+                bulk_g2s(b_tile, GTC + (size_t)unit * (tile_bytes / 4), tile_bytes, &bars[0]);
+            }
+            mbar_wait(&bars[0], parity);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_slab_mmas(tmem_base, smem_addr(a_tile), KC, sl, smem_addr(b_tile), KCs);
+                umma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], parity);   // the slab buffer is free again (and, after the last slab, D is complete)
         }
-        mbar_wait(&bars[0], parity);
-        if (tid == 0) {
-            tc_fence_after();
-            issue_tile_mmas(tmem_base, smem_addr(a_tile), smem_addr(b_tile), KC);
-            umma_commit(&bars[1]);
-        }
-        mbar_wait(&bars[1], parity);
         tc_fence_after();
         const int row = warp * 32 + lane;  // TMEM lane == user row
 #pragma unroll 1
@@ -112,11 +116,11 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
 cudaError_t launch_tc_logits(const rg_env_impl &e, const double *omega, const float *shift, float *out,
                              cudaStream_t stream) {
     using namespace tc;
-    const int KC = kt_chunks(e.dev.K);
-    const size_t smem = 2 * (size_t)KC * (CHUNK_BYTES + CHUNK_BYTES_B) + 64;
+    const int KC = e.dev.KC, KCs = e.dev.KCs, nslab = e.dev.nslab;
+    const size_t smem = 2 * (size_t)KC * CHUNK_BYTES + 2 * (size_t)KCs * CHUNK_BYTES_B + 64;
     cudaError_t ce = cudaFuncSetAttribute(tc_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
-    tc_logits_kernel<<<1, 128, smem, stream>>>(e.d_GTC, e.dev.nsub, KC, e.dev.K, omega, shift, out);
+    tc_logits_kernel<<<1, 128, smem, stream>>>(e.d_GTC, e.dev.nsub, KC, KCs, nslab, e.dev.K, omega, shift, out);
     return cudaGetLastError();
 }
 

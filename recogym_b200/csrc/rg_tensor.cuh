@@ -32,6 +32,17 @@ __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks
     return (kc + 1) & ~1;
 }
 
+// K slabs.  The K dimension (K + 2 columns, padded) is cut into `nslab` slabs of `KCs` 16-byte chunks: one slab of a B
+// tile is the unit the TMA ring streams and one group of UMMAs consumes, all slabs of a tile accumulating into the same
+// TMEM columns.  Small K (<= 8 chunks, e.g. K = 20 -> 6) is a single slab; larger K uses 6-chunk slabs, so that the ring
+// stage stays 24 KB (K = 64 -> 3 slabs).  KC = nslab * KCs is the padded total the A tile is built with.
+__host__ __device__ inline void kt_slabs(int K, int *KC, int *KCs, int *nslab) {
+    const int kc0 = kt_chunks(K);
+    if (kc0 <= 8) { *KCs = kc0; *nslab = 1; }
+    else { *KCs = 6; *nslab = (kc0 + 5) / 6; }
+    *KC = *KCs * *nslab;
+}
+
 __host__ __device__ inline float tf32_hi(float x) {
     union { float f; uint32_t u; } v;
     v.f = x;
@@ -109,16 +120,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-// One thread: the three-term tf32 contraction of one 128 x 64 tile into TMEM columns [tmem_d, tmem_d+64)
-__device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int KC) {
-    const uint32_t aterm = (uint32_t)KC * CHUNK_BYTES, bterm = (uint32_t)KC * CHUNK_BYTES_B;  // hi -> lo term
-    uint32_t acc = 0;
+// One thread: the three-term tf32 contraction of ONE K SLAB of one 128 x TILE_N tile into TMEM columns
+// [tmem_d, tmem_d + TILE_N).  a_saddr: the whole A tile ([2 terms][KC chunks]); b_saddr: this slab of the B tile
+// ([2 terms][KCs chunks]).  Slab 0 overwrites the accumulator, the others add to it.
+__device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_d, uint32_t a_saddr, int KC, int slab, uint32_t b_saddr,
+                                                int KCs) {
+    const uint32_t aterm = (uint32_t)KC * CHUNK_BYTES, bterm = (uint32_t)KCs * CHUNK_BYTES_B;  // hi -> lo term
+    const uint32_t aoff = (uint32_t)(slab * KCs) * CHUNK_BYTES;
+    uint32_t acc = slab > 0 ? 1u : 0u;
     // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll 1
     for (int pair = 0; pair < 3; ++pair) {
-        const uint32_t a0 = a_saddr + (pair == 0 ? aterm : 0u);
+        const uint32_t a0 = a_saddr + aoff + (pair == 0 ? aterm : 0u);
         const uint32_t b0 = b_saddr + (pair == 1 ? bterm : 0u);
-        for (int s = 0; s < KC / 2; ++s) {
+        for (int s = 0; s < KCs / 2; ++s) {
             umma_tf32(tmem_d, umma_desc(a0 + (uint32_t)s * 2u * CHUNK_BYTES, CHUNK_BYTES),
                       umma_desc(b0 + (uint32_t)s * 2u * CHUNK_BYTES_B, CHUNK_BYTES_B), kIdescTf32, acc);
             acc = 1;
