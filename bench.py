@@ -361,6 +361,7 @@ def main():
                    "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
                    "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
                    "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7]),
+                   "pass1_cycles_per_128_draws": round(float(ev[11]) / max(1.0, float(ev[2])) * 128.0, 1),
                    "phase_cycle_share": dict(zip(("compact", "pass1", "pass2", "resample", "advance", "omega"),
                                                  [round(float(x) / max(1.0, float(ev[10:16].sum())), 4) for x in ev[10:16]]))},
         "clocks": clocks,

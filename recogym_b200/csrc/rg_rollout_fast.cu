@@ -172,6 +172,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// (One CTA per SM -- no co-resident CTA at all -- still needs 2280 cycles per 128 x 128 tile in pass 1 (two CTAs: 3035 each),
+// against 1100 of MUFU and 610 of tensor time: pass 1 is a latency chain, not a throughput limit.  Re-measured after the
+// TMA loader thread was decoupled: software-pipelined tcgen05.ld and the exponentials-first ordering still change nothing.)
 // (Measured and dropped, all on 1xB200 at C3 with 5.9e8 user-steps/s as the baseline: software-pipelining the tcgen05.ld
 // of the next 32 columns under the exponentials of the current ones (5.86e8); issuing the 32 exponentials of a chunk
 // before any addition (5.90e8); 64-product UMMA tiles with 4-6 ring stages (4.4e8); one pass-1 token per SM so that the
