@@ -1463,8 +1463,9 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     int best_stage = 0;
     // (CUDA-core form) when P x K is too large for one CTA's shared memory, the partial sums of the re-sampling sweeps,
     // then also the binary64 omega rows, move to an L2-resident global scratch (C4: P = 100 000, K = 64)
+    static const bool force_one = [] { const char *v = getenv("RG_FORCE_ONE_CTA"); return v && v[0] == '1'; }();   // experiment knob
     for (int spill = 0; spill <= (tensor ? 0 : 2) && !best_stage; ++spill)
-    for (int pass = 0; pass < 2 && !best_stage; ++pass) {
+    for (int pass = force_one ? 1 : 0; pass < 2 && !best_stage; ++pass) {
         p.spill = spill;
         const int limit = pass == 0 ? two_ctas : 227 * 1024;
         // asynchronous re-sampling (warps 5-7 underneath pass 1) is correct but measured SLOWER at C3 (3.2e8 vs
@@ -1497,6 +1498,13 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
                             : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
     if (ce != cudaSuccess) return ce;
     int ctas_per_sm = p.L.total <= two_ctas ? 2 : 1;
+    if (force_one && ctas_per_sm == 2) {   // deepest ring that fits, padded so that only one CTA is resident per SM
+        ctas_per_sm = 1;
+        p.L.total = two_ctas + 1024;
+        ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
+                    : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+        if (ce != cudaSuccess) return ce;
+    }
     long long blocks = (n_total + TU - 1) / TU;
     const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
     if (blocks > max_blocks) blocks = max_blocks;
