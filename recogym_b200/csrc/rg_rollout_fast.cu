@@ -1017,8 +1017,120 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
 
-        // ---- C: pass 2b, one warp per live user: recompute the located record tile, index and margins
-        for (int i = warp; i < nlive; i += NWARP) {
+        // ---- C: pass 2b (tensor mode), one warp per UI live users at a time: locate the crossing 32-product group with
+        // the pass-1 group sums the epilogue kept, recompute only that group (one product per lane) for the index and its
+        // margins, filter.  Every step is a latency chain (L2 loads, shuffles, binary64 adds): UI users are interleaved.
+        if constexpr (TC) {
+            constexpr int UI = 4;
+            for (int ib = warp * UI; ib < nlive; ib += NWARP * UI) {
+                int ii[UI], rs[UI], p0[UI], ngr[UI], gsel[UI], found[UI];
+                double cum[UI], lower[UI], upper[UI];
+#pragma unroll
+                for (int u = 0; u < UI; ++u) {
+                    ii[u] = min(ib + u, nlive - 1);          // surplus lanes of the last group repeat the last user
+                    rs[u] = s_rsel[ii[u]];
+                    cum[u] = s_cum[ii[u]];
+                    p0[u] = max(rs[u], 0) * p.rec_sub * SUB;
+                    ngr[u] = (min(p0[u] + p.rec_sub * SUB, nsub * SUB) - p0[u]) / 32;
+                    gsel[u] = -1; found[u] = -1; lower[u] = 0.0; upper[u] = 0.0;
+                }
+                // the 32-product groups of the record tile (these group sums are the very terms the record-tile sum
+                // was built from, up to the fp32 rounding of that chain, which the mass-error bound accounts for)
+                const int ngr_max = p.rec_sub * (SUB / 32);
+                for (int g0 = 0; g0 < ngr_max; g0 += 32) {
+                    double x[UI];
+#pragma unroll
+                    for (int u = 0; u < UI; ++u) {
+                        const int gi = g0 + lane;
+                        const bool need = rs[u] >= 0 && gsel[u] < 0 && gi < ngr[u];
+                        x[u] = need ? (double)__ldcg(gsum_cta + (size_t)(p0[u] / 32 + gi) * TU + ii[u]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UI; ++u) {
+                        if (rs[u] < 0 || gsel[u] >= 0 || g0 >= ngr[u]) continue;   // warp-uniform
+                        const double own = x[u];
+                        double xs = own;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const double y = __shfl_up_sync(0xffffffffu, xs, d);
+                            if (lane >= d) xs += y;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, (cum[u] + xs > s_tau[ii[u]]) && (g0 + lane < ngr[u]));
+                        if (m) {
+                            const int fl = __ffs(m) - 1;
+                            gsel[u] = g0 + fl;
+                            cum[u] += __shfl_sync(0xffffffffu, xs - own, fl);   // groups before the crossing one
+                        } else {
+                            cum[u] += __shfl_sync(0xffffffffu, xs, 31);
+                        }
+                    }
+                }
+                // recompute the crossing group of each user: UI independent FFMA chains, UI loads in flight per k
+                float acc[UI];
+                const float *gp[UI];
+#pragma unroll
+                for (int u = 0; u < UI; ++u) {
+                    const int pj = p0[u] + max(gsel[u], 0) * 32 + lane;
+                    gp[u] = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & (SUB - 1));
+                    acc[u] = 0.f;
+                }
+#pragma unroll 7
+                for (int k = 0; k < K1; ++k) {   // 7 x UI L2 loads in flight
+#pragma unroll
+                    for (int u = 0; u < UI; ++u) acc[u] = fmaf(om32[k * TU + ii[u]], __ldg(gp[u] + k * SUB), acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < UI; ++u) {
+                    if (gsel[u] < 0) continue;                 // warp-uniform
+                    const double tau = s_tau[ii[u]];
+                    double x = (double)ex2_approx(acc[u] - s_shift[ii[u]]);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y = __shfl_up_sync(0xffffffffu, x, d);
+                        if (lane >= d) x += y;
+                    }
+                    const double pre = cum[u] + x;
+                    const int pj = p0[u] + gsel[u] * 32 + lane;
+                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
+                    if (m) {
+                        const int fl = __ffs(m) - 1;
+                        found[u] = p0[u] + gsel[u] * 32 + fl;
+                        upper[u] = __shfl_sync(0xffffffffu, pre, fl);
+                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
+                        lower[u] = fl > 0 ? below : cum[u];
+                    }   // else: the recomputed group is lighter than its pass-1 sum by a rounding: ambiguous
+                }
+                if (lane < UI && ib + lane < nlive) {   // lane u finishes user u: filter, view, re-sampling queue
+                    int fnd = found[0];
+                    double lo = lower[0], up = upper[0];
+#pragma unroll
+                    for (int u = 1; u < UI; ++u)
+                        if (lane == u) { fnd = found[u]; lo = lower[u]; up = upper[u]; }
+                    const int i = ib + lane, slot = pos2slot[i];
+                    const double Z = s_Z[i], tau = s_tau[i];
+                    bool amb = fnd < 0;
+                    if (!amb) {
+                        // Filter (see the CUDA-core form below for the derivation): the tolerance is
+                        // d [ (1-u) S + u (Z - S) + 2u m(T) ] with T the crossing record tile
+                        const double dlt = (double)s_eps[i], uu = s_u[i];
+                        const double tmass = (double)tilesum[(size_t)i * p.nrec_pad + s_rsel[i]];
+                        const double tl = dlt * ((1.0 - uu) * lo + uu * fmax(Z - lo, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
+                        const double tu = dlt * ((1.0 - uu) * up + uu * fmax(Z - up, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
+                        amb = (tau - lo < tl && fnd > 0) || (up - tau < tu && fnd < P - 1);
+                    }
+                    s_view[slot] = fnd;
+                    if (amb) {
+                        const double lse = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
+                        const int e = atomicAdd(&misc[6], 1);
+                        rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
+                        s_wait[slot] = ASYNC ? 2 : 1;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- C: pass 2b (CUDA-core form), one warp per live user: recompute the located record tile, index and margins
+        for (int i = warp; i < (TC ? 0 : nlive); i += NWARP) {
             const int slot = pos2slot[i];
             const double Z = s_Z[i], tau = s_tau[i];
             double cum = s_cum[i];
