@@ -366,7 +366,7 @@ def main():
                                                  [round(float(x) / max(1.0, float(ev[10:16].sum())), 4) for x in ev[10:16]]))},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * len(policies),
+        "gpu_launches": args.steps * len(policies) * (4 if (args.math != "exact" and U >= 4 * 296 * 128) else 1),  # rollout (+ 3 schedule kernels)
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": measured_traffic(launch_events), "peak_source": peak_src,
                      "algorithmic_bytes_per_user_step": alg_bytes,

@@ -51,6 +51,7 @@ struct Params {
     long long user_begin, n_organic_users, n_total;
     RolloutOutDev out;
     unsigned long long *queue;
+    const int32_t *perm;    // longest-first schedule: ticket q -> user index perm[q] (nullptr: identity)
     int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
     int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
     int async2;             // tc: tier 2/3 re-sampling runs on warps 5-7 underneath the next round's pass 1
@@ -542,6 +543,80 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
     gsync();
 }
 
+// ---- longest-first schedule --------------------------------------------------------------------------------------------
+// A launch ends with a tail: when the ticket queue is empty every CTA still has to finish the episodes its slots hold, and
+// a round costs the same with 3 live users as with 128 (13 % of a 1M-user launch at C3).  Episodes that start last should
+// therefore be the shortest ones.  The number of organic draws of a user is ESTIMATED by replaying its Markov chain alone
+// -- the transition uniforms are a function of (user, t) -- with clicks guessed from the click uniform (a click needs
+// u >= 1 - ff, ff in [0.0045, 0.0293]; the guess uses the policy's mean click probability at omega = 0), users are bucketed by
+// the estimate, and tickets are handed out from the longest bucket down.  Only the ORDER in which users are simulated
+// changes: every result is a pure function of (seed, user).
+constexpr int LPT_BUCKETS = 256;
+
+// mean click probability of the acting policy at omega = 0: (1/P) sum_v ff(mu_bandit[a(v)]) with a(v) the table's action
+// (table policies) or v itself (uniform / user_views) -- the click-guess threshold of the estimate
+__global__ void lpt_ctr_kernel(const EnvDev env, const PolicyDev pol, double *__restrict__ ctr_mean) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int v = threadIdx.x; v < env.P; v += blockDim.x) {
+        const int a = pol.kind == RG_POLICY_TABLE ? __ldg(pol.table + v) : v;
+        s += ff64(__ldg(env.mu_b + a));
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        *ctr_mean = t / (double)env.P;
+    }
+}
+
+__global__ void lpt_estimate_kernel(const EnvDev env, long long user_begin, long long n_organic_users, long long n_total,
+                                    const double *__restrict__ ctr_mean, unsigned char *__restrict__ est,
+                                    unsigned *__restrict__ hist) {
+    const double click_thr = 1.0 - *ctr_mean;
+    __shared__ unsigned sh[LPT_BUCKETS];
+    for (int b = threadIdx.x; b < LPT_BUCKETS; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) {
+        const uint64_t user = (uint64_t)(user_begin + i);
+        const bool organic_only = i < n_organic_users;
+        int state = RG_ORGANIC, n_org = 0;
+        for (uint32_t t = 0; t < 8192u && state != RG_STOP; ++t) {
+            const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
+            const int was = state;
+            state = next_state(env, was, uniform53(w.z, w.w));
+            if (was == RG_ORGANIC) {
+                n_org += 1;
+                if (organic_only && state != RG_ORGANIC) break;
+            } else if (uniform53(w.x, w.y) >= click_thr) {
+                state = RG_ORGANIC;   // guessed click (abstract.py:180-181)
+            }
+        }
+        const int b = n_org < LPT_BUCKETS ? n_org : LPT_BUCKETS - 1;
+        est[i] = (unsigned char)b;
+        atomicAdd(&sh[b], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < LPT_BUCKETS; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+__global__ void lpt_cursor_kernel(unsigned *__restrict__ hist) {   // in place: first ticket of each bucket, longest first
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = LPT_BUCKETS - 1; b >= 0; --b) { const unsigned c = hist[b]; hist[b] = run; run += c; }
+    }
+}
+
+__global__ void lpt_scatter_kernel(const unsigned char *__restrict__ est, long long n_total, unsigned *__restrict__ cursor,
+                                   int32_t *__restrict__ perm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) perm[atomicAdd(&cursor[est[i]], 1u)] = (int32_t)i;
+}
+
 template <bool TC>
 __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     // TC pass 1: warps 0-3 run the epilogue (thread = TMEM lane = user), warp 4 is the TMA producer / MMA issuer,
@@ -638,7 +713,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             s_live[slot] = 0;
             return false;
         }
-        const uint64_t user = (uint64_t)(p.user_begin + (long long)q);
+        const uint64_t user = (uint64_t)(p.user_begin + (long long)(p.perm ? p.perm[q] : (long long)q));
         s_user[slot] = user;
         s_hash[slot] = kHashInit;
         s_t[slot] = 0u;
@@ -1644,6 +1719,26 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
         }
         p.om_scratch = e.d_om_scratch;
     }
+    // longest-first schedule for launches that fill the machine several times over (see lpt_estimate_kernel)
+    static const bool no_lpt = [] { const char *v = getenv("RG_NO_LPT"); return v && v[0] == '1'; }();
+    char *lpt_arena = nullptr;
+    p.perm = nullptr;
+    if (!no_lpt && n_total >= 4 * max_blocks * TU && n_total < 2000000000ll) {
+        const size_t o_est = 2048, o_perm = (o_est + (size_t)n_total + 255) & ~(size_t)255;
+        ce = cudaMallocAsync((void **)&lpt_arena, o_perm + 4 * (size_t)n_total, stream);
+        if (ce != cudaSuccess) return ce;
+        unsigned *hist = (unsigned *)lpt_arena;
+        unsigned char *est = (unsigned char *)(lpt_arena + o_est);
+        int32_t *perm = (int32_t *)(lpt_arena + o_perm);
+        cudaMemsetAsync(hist, 0, 1024, stream);
+        const unsigned nb = (unsigned)((n_total + 255) / 256);
+        lpt_ctr_kernel<<<1, 256, 0, stream>>>(e.dev, pol, (double *)(lpt_arena + 1024));
+        lpt_estimate_kernel<<<nb, 256, 0, stream>>>(e.dev, user_begin, n_organic_users, n_total,
+                                                    (const double *)(lpt_arena + 1024), est, hist);
+        lpt_cursor_kernel<<<1, 32, 0, stream>>>(hist);
+        lpt_scatter_kernel<<<nb, 256, 0, stream>>>(est, n_total, hist, perm);
+        p.perm = perm;
+    }
     if (tensor) {
         const size_t need_g = sizeof(float) * (size_t)max_blocks * (size_t)e.dev.nsub * 4 * TU;
         if (e.gsum_bytes < need_g) {       // pass-1 group sums of every resident slot (48 MB at C3: L2-resident)
@@ -1659,7 +1754,9 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     } else {
         rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     }
-    return cudaGetLastError();
+    ce = cudaGetLastError();
+    if (lpt_arena) cudaFreeAsync(lpt_arena, stream);
+    return ce;
 }
 
 }  // namespace rg
