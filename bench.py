@@ -377,7 +377,7 @@ def main():
     if args.math == "tensor":
         # tensor mode: the contraction is on tcgen05; the binding unit of pass 1 is the MUFU pipe
         # (one ex2 per product per organic draw; 16 ex2/clk/SM)
-        mufu_peak = 148 * 16 * sm_max * 1e6
+        mufu_peak = 148 * 15.8 * sm_max * 1e6     # measured: scripts/micro/mufu_rate.cu, profiles/r01_mufu_rate.txt (nominal 16)
         line["roofline_mufu"] = {"bound": "mufu-ex2", "achieved": organic_per_s * P / 1e12, "peak": mufu_peak / 1e12,
                                  "unit": "Tex2/s", "frac": organic_per_s * P / mufu_peak,
                                  "ex2_per_organic_draw": P}
