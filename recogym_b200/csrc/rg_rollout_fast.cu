@@ -1,25 +1,29 @@
-// rg_rollout_fast.cu -- RG_MATH_FAST: the CTA-batched fused rollout kernel.
+// rg_rollout_fast.cu -- RG_MATH_FAST / RG_MATH_TENSOR: the CTA-batched fused rollout kernel.
 //
 // A persistent CTA owns TU=128 user slots.  Work proceeds in rounds; at the start of a round every
 // live slot is in the ORGANIC state, so the expensive part of the model -- the product-view draw
 // from Categorical(softmax(Gamma omega + mu)) (reco_env_v1.py:119-128) -- is one dense
-// [128 users] x [P products] x [K] fp32 contraction per round:
+// [128 users] x [P products] x [K] contraction per round:
 //
-//   pass 1  Gamma tiles (128 products x (K+1) floats, pre-scaled by log2 e, mu as row K) stream
-//           L2 -> shared memory through a ring of TMA bulk copies (cp.async.bulk + mbarrier);
-//           each thread owns an 8-user x 8-product register tile, 64 FFMA per 4 LDS.128; the
-//           epilogue turns logits into masses with a bare ex2 (shifted by a per-user upper bound of
-//           the logits, so no running maximum is needed) and keeps per-user partial sums per
-//           "record tile" in shared memory.
-//   pass 2  one warp per user: total mass, tau = u * Z, locate the record tile, recompute only that
-//           tile in natural product order with a warp scan -> candidate index + its CDF margins.
-//   filter  the margins are compared with a rigorous bound of the fp32 error (DESIGN.md "fast
-//           sampler"); a draw that could be affected is re-sampled in binary64 by the whole CTA.
-//           Every discrete result therefore equals the all-binary64 sampler (RG_MATH_EXACT).
-//   advance one thread per slot: transition, omega drift, then the whole run of cheap bandit events
-//           (policy action, click ~ Bernoulli(ff(beta_a.omega + mu_a)), transition) until the user is
-//           organic again or stops; stopped users are written out and the slot claims the next
-//           user id from a global queue.
+//   pass 1  CUDA cores (RG_MATH_FAST): Gamma tiles (128 products x (K+1) floats, pre-scaled by log2 e, mu as row K)
+//           stream L2 -> shared memory through a ring of TMA bulk copies (cp.async.bulk + mbarrier); each thread owns
+//           an 8-user x 8-product register tile.  Tensor cores (RG_MATH_TENSOR): the contraction is a tcgen05 UMMA
+//           (tf32 hi/lo split, three terms, K slabs for large K) with accumulators in TMEM; warp 4 issues the MMAs,
+//           warp 5 refills the B ring, warps 0-3 run the epilogue (thread = TMEM lane = user).  Either way the epilogue
+//           turns logits into masses with a bare ex2 (shifted by a per-user upper bound of the logits, so no running
+//           maximum is needed) and keeps per-user partial sums per "record tile" in shared memory (tensor mode: also
+//           per 32-product group in an L2-resident scratch).
+//   pass 2  total mass, tau = u * Z, locate the record tile (thread per user), then recompute only the crossing tile
+//           (CUDA cores) / the crossing 32-product group (tensor mode, four users interleaved per warp) in natural
+//           product order with a warp scan -> candidate index + its CDF margins.
+//   filter  the margins are compared with a rigorous bound of the fp32 error in which the errors common to the prefix
+//           sum and the total cancel (DESIGN.md "three-tier sampler"); a draw that could be affected waits in a queue
+//           until 8 of them share one re-sampling sweep: tier 2 (binary64 logits on DMMA, fp32 ex2, a-posteriori
+//           bound), tier 3 (all binary64).  Every discrete result therefore equals RG_MATH_EXACT.
+//   advance D1 (thread per slot): bookkeeping of the view, transition; D2 (warp per user): the whole run of cheap
+//           bandit events (policy action, click ~ Bernoulli(ff(beta_a.omega + mu_a)), transition), 32 candidate events
+//           per turn; stopped users are written out and the slot claims the next user from a global ticket queue
+//           (longest-first schedule for large launches); omega updates are batched over the CTA.
 //
 // All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
 #include <cstdlib>

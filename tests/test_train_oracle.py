@@ -62,3 +62,49 @@ def test_evolution_warmup_stats_match_reference_evaluate_agent(oracle):
     assert np.array_equal(co, g["oc_all_warm_co"])
     co0, pulls0, _, _ = T.count_stats(env.P, r["log"], 0, mode=0)
     assert not np.array_equal(pulls0, pulls) and not np.array_equal(co0, co)      # the modes really differ
+
+
+def test_host_count_agents_match_reference_agents():
+    """recogym_b200's host OrganicCount / BanditCount (train / act, CPU only) fed with the reference's training log,
+    call by call as test_agent's loop does, end in the reference agents' statistics and acting tables."""
+    import recogym_b200 as rg
+    from oracle import train_oracle as T
+    from recogym_b200.envs.context import DefaultContext
+    from recogym_b200.envs.observation import Observation
+    from recogym_b200.envs.session import OrganicSessions
+    g = load_golden(CASE)
+    P = g["Gamma"].shape[0]
+    oc = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
+    bc = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": P}))
+    for user, session, action, reward in T.iter_train_calls(golden_log(g), int(g["n_organic_users"])):
+        s = OrganicSessions()
+        for v in session:
+            s.next(DefaultContext(0, user), v)
+        obs = Observation(DefaultContext(0, user), s)
+        act = None if action is None else {"t": 0, "u": user, "a": action, "ps": 1.0, "ps-a": ()}
+        oc.train(obs, act, reward, action is None)
+        bc.train(obs, act, reward, action is None)
+    assert np.array_equal(oc.co_counts, g["co_counts"])
+    assert np.array_equal(bc.pulls_a, g["pulls_a"]) and np.array_equal(bc.clicks_a, g["clicks_a"])
+    assert np.array_equal(bc.ctr, g["ctr"]) and bc.last_product_viewed == int(g["bandit_lpv"])
+    assert np.array_equal(oc.device_policy()["table"], g["co_counts"].argmax(axis=1))
+    pol = bc.device_policy()
+    assert np.array_equal(pol["table"], g["ctr"].argmax(axis=1)) and np.array_equal(pol["ps_table"], g["ctr"].max(axis=1))
+    # act() on an observation whose last view is v == the table
+    s = OrganicSessions(); s.next(DefaultContext(0, 0), 7)
+    a = oc.act(Observation(DefaultContext(1, 0), s), 0, False)
+    assert a["a"] == g["co_counts"][7].argmax() and a["ps"] == 1.0
+
+
+def test_bandit_mf_table_equals_probing_act():
+    """BanditMFSquare.device_policy (block-wise arg-max) == probing its unchanged act() once per last view."""
+    import torch
+    import recogym_b200 as rg
+    from recogym_b200.policy import probe_last_view_table
+    torch.manual_seed(3)
+    ag = rg.agents.BanditMFSquare(rg.Configuration({**rg.agents.bandit_mf_square_args, "num_products": 300}))
+    pol = ag.device_policy(rows_per_block=64)
+    assert np.array_equal(pol["table"], probe_last_view_table(ag, 300))
+    with torch.no_grad():
+        ag.last_product_viewed = 5
+        assert float(ag.get_logits()[pol["table"][5]]) == float(pol["ps_table"][5])
