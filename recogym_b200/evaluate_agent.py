@@ -263,3 +263,97 @@ def gather_exploration_stats(env, env_args, extra_env_args, agents_init_data, tr
                 EvolutionCase.FAILURE_GREEDY, EvolutionCase.ACTIONS)}
         out[agent_key] = agent_stats
     return out
+
+
+# ---- off-policy estimators over a logged DataFrame (reference: recogym/evaluate_agent.py:753-908) ---------------------
+def to_categorical(y, num_classes=None, dtype="float32"):
+    """One-hot rows (the Keras helper the reference carries, evaluate_agent.py:36-48)."""
+    import numpy as np
+    y = np.array(y, dtype="int")
+    input_shape = y.shape
+    if input_shape and input_shape[-1] == 1 and len(input_shape) > 1:
+        input_shape = tuple(input_shape[:-1])
+    y = y.ravel()
+    if not num_classes:
+        num_classes = np.max(y) + 1
+    out = np.zeros((y.shape[0], num_classes), dtype=dtype)
+    out[np.arange(y.shape[0]), y] = 1
+    return out.reshape(input_shape + (num_classes,))
+
+
+def _replay_policy_probabilities(agent, reco_log):
+    """Per bandit row of the users 0 .. max(u)-1 (the reference's `for u in range(max(reco_log.u))` leaves the last user
+    out): (reward c, pi(a | context) of `agent`, logged ps, top-k helper).  Table agents (`device_policy()` is a
+    last-view table) are evaluated in one vectorised pass -- pi = [a == table[last view]], the last view carried by
+    `Agent.update_lpv` -- any other agent is replayed row by row through its own act() with 'ps-a', as the reference
+    does (evaluate_agent.py:753-811)."""
+    import numpy as np
+    import pandas as pd
+    from .envs.context import DefaultContext
+    from .envs.observation import Observation
+    from .envs.session import OrganicSessions
+    u = reco_log["u"].to_numpy(dtype="int64")
+    keep = u < int(u.max())
+    z = (reco_log["z"].to_numpy() == "bandit")
+    pol = agent.device_policy() if hasattr(agent, "device_policy") else None
+    if pol is not None and pol.get("policy") == "table":
+        table = np.asarray(pol["table"].cpu().numpy() if hasattr(pol["table"], "cpu") else pol["table"])
+        v = reco_log["v"].to_numpy(dtype="float64", na_value=np.nan)
+        lv = pd.Series(np.where(z, np.nan, v)).groupby(u).ffill().to_numpy()
+        rows = np.flatnonzero(z & keep)
+        a = reco_log["a"].to_numpy(dtype="float64", na_value=np.nan)[rows].astype(np.int64)
+        pi = (table[lv[rows].astype(np.int64)] == a).astype(np.float64)
+        return (reco_log["c"].to_numpy(dtype="float64")[rows], pi, reco_log["ps"].to_numpy(dtype="float64")[rows])
+    rewards, probs, pss = [], [], []
+    for user in range(int(u.max())):
+        rows = reco_log[reco_log["u"] == user]
+        session = OrganicSessions()
+        agent.reset()
+        for t, zz, v, a, c, ps in zip(rows["t"], rows["z"], rows["v"], rows["a"], rows["c"], rows["ps"]):
+            if zz == "organic":
+                session.next(DefaultContext(t, user), int(v))
+            else:
+                prob = agent.act(Observation(DefaultContext(t, user), session), 0, False)["ps-a"]
+                if len(prob):
+                    rewards.append(float(c)); probs.append(float(prob[int(a)])); pss.append(float(ps))
+                session = OrganicSessions()
+    return np.array(rewards), np.array(probs), np.array(pss)
+
+
+def evaluate_IPS(agent, reco_log):
+    """Per-row inverse-propensity terms c * pi(a) / ps (evaluate_agent.py:753-781)."""
+    c, pi, ps = _replay_policy_probabilities(agent, reco_log)
+    return list(c * pi / ps)
+
+
+def evaluate_SNIPS(agent, reco_log):
+    """-> (rewards, p_ratio) (evaluate_agent.py:784-811)."""
+    c, pi, ps = _replay_policy_probabilities(agent, reco_log)
+    return list(c), list(pi / ps)
+
+
+def _estimator_frame(rows):
+    import pandas as pd
+    return pd.DataFrame().from_dict({"Agent": [r[0] for r in rows], "0.025": [r[1] - 2 * r[2] for r in rows],
+                                     "0.500": [r[1] for r in rows], "0.975": [r[1] + 2 * r[2] for r in rows]})
+
+
+def verify_agents_IPS(reco_log, agents):
+    """evaluate_agent.py:813-828: mean +- 2 standard errors of the IPS terms per agent."""
+    import numpy as np
+    rows = []
+    for agent_id, agent in agents.items():
+        ee = np.asarray(evaluate_IPS(agent, reco_log))
+        rows.append((agent_id, np.mean(ee), np.std(ee) / np.sqrt(len(ee))))
+    return _estimator_frame(rows)
+
+
+def verify_agents_SNIPS(reco_log, agents):
+    """evaluate_agent.py:831-848: self-normalised estimate sum(c * ratio) / sum(ratio)."""
+    import numpy as np
+    rows = []
+    for agent_id, agent in agents.items():
+        rewards, ratio = (np.asarray(x) for x in evaluate_SNIPS(agent, reco_log))
+        ee = rewards * ratio
+        rows.append((agent_id, np.sum(ee) / np.sum(ratio), np.std(ee) / np.sqrt(len(ee))))
+    return _estimator_frame(rows)

@@ -108,3 +108,39 @@ def test_bandit_mf_table_equals_probing_act():
     with torch.no_grad():
         ag.last_product_viewed = 5
         assert float(ag.get_logits()[pol["table"][5]]) == float(pol["ps_table"][5])
+
+
+def test_host_ips_snips_estimators_match_reference():
+    """recogym_b200.verify_agents_SNIPS / evaluate_SNIPS / evaluate_IPS on the reference's logged DataFrame (rebuilt from
+    the golden columns) == the reference's own numbers, through the vectorised table path AND the row-by-row replay."""
+    import pandas as pd
+    import recogym_b200 as rg
+    g = load_golden(CASE)
+    P = g["Gamma"].shape[0]
+    z = g["ipslog_z"]
+    df = pd.DataFrame({
+        "t": g["ipslog_t"].astype(np.float32), "u": pd.array(g["ipslog_u"], dtype=pd.Int32Dtype()),
+        "z": np.where(z == 0, "organic", "bandit"),
+        "v": pd.array(np.where(z == 0, g["ipslog_v"], 0), dtype=pd.Int32Dtype()),
+        "a": pd.array(np.where(z == 1, g["ipslog_a"], 0), dtype=pd.Int32Dtype()),
+        "c": np.where(z == 1, g["ipslog_c"], np.nan).astype(np.float32), "ps": np.where(z == 1, 1.0 / P, np.nan)})
+    df.loc[z == 1, "v"] = pd.NA
+    df.loc[z == 0, "a"] = pd.NA
+    oc = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
+    oc.co_counts = g["co_counts"].copy()
+    rewards, ratio = rg.evaluate_SNIPS(oc, df)                   # vectorised table path
+    assert np.array_equal(rewards, g["ips_rewards"]) and np.array_equal(ratio, g["ips_p_ratio"])
+    assert np.array_equal(rg.evaluate_IPS(oc, df), g["ips_rewards"] * g["ips_p_ratio"])
+    out = rg.verify_agents_SNIPS(df, {"oc": oc})
+    assert list(out.columns) == ["Agent", "0.025", "0.500", "0.975"]
+    assert np.allclose([out["0.025"][0], out["0.500"][0], out["0.975"][0]], g["snips"], rtol=0, atol=1e-15)
+
+    class Replay(rg.agents.OrganicCount):                        # no table -> the reference's row-by-row replay
+        def device_policy(self):
+            return None
+    rp = Replay(rg.Configuration({**rg.agents.organic_count_args, "num_products": P, "with_ps_all": True}))
+    rp.co_counts = g["co_counts"].copy()
+    r2, q2 = rg.evaluate_SNIPS(rp, df[df["u"] < 6])
+    m = g["ipslog_u"][g["ipslog_z"] == 1]
+    nrow = int(((m < 5)).sum())                                  # users 0..4: the last user of the sub-log is left out
+    assert np.array_equal(r2, g["ips_rewards"][:nrow]) and np.array_equal(q2, g["ips_p_ratio"][:nrow])
