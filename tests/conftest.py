@@ -30,6 +30,14 @@ T2_CASES = [
 ]
 
 
+# more reference goldens for the CPU oracle only (degenerate shapes, unusual transition matrices)
+T2_CASES_ORACLE_ONLY = [
+    "t2_seed31_P1_K2_u80",
+    "t2_seed32_P7_K1_u80_o6",
+    "t2_seed33_P20_K3_u120_fastleave",
+]
+
+
 def oracle_env_from_golden(g):
     from oracle import oracle as O
     return O.OracleEnv(g["Gamma"], g["mu_organic"], g["beta"], g["mu_bandit"], g["state_transition"],

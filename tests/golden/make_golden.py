@@ -118,6 +118,9 @@ def main():
     if "--evolution-only" in sys.argv:
         evolution_case()
         return
+    if "--edge-only" in sys.argv:
+        edge_cases()
+        return
     t1_static_and_stats()
     t2_case("t2_seed42_P10_K5_u100", {"random_seed": 42}, 100)
     t2_case("t2_seed7_P100_K5_u60_o5", {"random_seed": 7, "num_products": 100, "K": 5}, 60, n_organic=5)
@@ -133,6 +136,7 @@ def main():
     user_views_cases()
     train_case()
     evolution_case()
+    edge_cases()
 
 
 def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
@@ -217,6 +221,16 @@ def evolution_case(name="t2_evolution_seed8_P30_K5"):
     save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=0, **sp, **out)
+
+
+def edge_cases():
+    """Degenerate shapes and unusual transition matrices through the UNMODIFIED reference (T2 streams)."""
+    t2_case("t2_seed31_P1_K2_u80", {"random_seed": 31, "num_products": 1, "K": 2}, 80)
+    t2_case("t2_seed32_P7_K1_u80_o6", {"random_seed": 32, "num_products": 7, "K": 1, "sigma_omega": 1.5,
+                                        "sigma_omega_initial": 2.0}, 80, n_organic=6)
+    t2_case("t2_seed33_P20_K3_u120_fastleave",
+            {"random_seed": 33, "num_products": 20, "K": 3, "prob_leave_organic": 0.3, "prob_leave_bandit": 0.2,
+             "prob_organic_to_bandit": 0.6, "prob_bandit_to_organic": 0.7, "sigma_mu_organic": 0.5}, 120)
 
 
 def user_views_cases():

@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import T2_CASES, load_golden, oracle_env_from_golden
+from conftest import T2_CASES, T2_CASES_ORACLE_ONLY, load_golden, oracle_env_from_golden
 
 
 def test_philox_known_answers(oracle):
@@ -50,7 +50,7 @@ def test_uniform_and_normal_streams(oracle):
     assert stats.chisquare(np.bincount(a, minlength=10)).pvalue > 1e-3
 
 
-@pytest.mark.parametrize("case", T2_CASES)
+@pytest.mark.parametrize("case", T2_CASES + T2_CASES_ORACLE_ONLY)
 def test_rollout_matches_reference_logic(oracle, case):
     """T2: reference code + injected Philox RNG.  Every discrete log column must be identical."""
     g = load_golden(case)
