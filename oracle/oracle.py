@@ -34,7 +34,7 @@ class _Env(C.Structure):
 
 
 class _Policy(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("table", C.c_void_p)]
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("table", C.c_void_p), ("epsilon", C.c_double)]
 
 
 class _Log(C.Structure):
@@ -141,7 +141,7 @@ class OracleEnv:
         return out
 
 
-def make_policy(kind="uniform", table=None):
+def make_policy(kind="uniform", table=None, epsilon=0.0):
     pol = _Policy()
     if kind == "uniform":
         pol.kind = 0
@@ -153,16 +153,21 @@ def make_policy(kind="uniform", table=None):
     elif kind == "user_views":
         pol.kind = 2
         keep = None
+    elif kind == "eps_table":       # EpsilonGreedy around a table agent (oracle only)
+        pol.kind = 3
+        pol.epsilon = float(epsilon)
+        keep = np.ascontiguousarray(table, np.int32)
+        pol.table = _p(keep)
     else:
         raise ValueError(kind)
     return pol, keep
 
 
 def rollout(env, user_begin, n_users, policy="uniform", table=None, n_organic_users=0, log=False, log_cap=None,
-            hist=False, omega=False, threads=1):
+            hist=False, omega=False, threads=1, epsilon=0.0):
     """generate_logs(n_users, agent, n_organic_users) on the oracle. Returns dict of numpy arrays."""
     total = n_users + n_organic_users
-    pol, keep = make_policy(policy, table)
+    pol, keep = make_policy(policy, table, epsilon)
     res = {
         "n_events": np.zeros(total, np.int32), "n_organic": np.zeros(total, np.int32),
         "n_bandit": np.zeros(total, np.int32), "n_clicks": np.zeros(total, np.int32),

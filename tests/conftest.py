@@ -35,6 +35,7 @@ T2_CASES_ORACLE_ONLY = [
     "t2_seed31_P1_K2_u80",
     "t2_seed32_P7_K1_u80_o6",
     "t2_seed33_P20_K3_u120_fastleave",
+    "t2_seed41_P25_K4_u60_eps_organic_count",   # the reference's EpsilonGreedy(OrganicCount), epsilon = 0.25
 ]
 
 

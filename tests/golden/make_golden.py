@@ -69,7 +69,9 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
     if agent_kind is not None:
         ref = H.load_reference()
         from recogym.agents import OrganicCount, organic_count_args, BanditCount, bandit_count_args
-        if agent_kind == "organic_user_count":
+        if agent_kind == "eps_organic_count":
+            agent = OrganicCount(ref.Configuration({**organic_count_args, "num_products": cfg.num_products}))  # wrapped below
+        elif agent_kind == "organic_user_count":
             from recogym.agents import OrganicUserEventCounterAgent, organic_user_count_args
             agent = OrganicUserEventCounterAgent(ref.Configuration(
                 {**organic_user_count_args, "num_products": cfg.num_products, "random_seed": cfg.random_seed}))
@@ -92,7 +94,14 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
             old_obs = new_obs
             action, _, reward, done, _ = train_env.step_offline(old_obs, reward, done)
             agent.train(old_obs, action, reward, True)
-        if agent_kind == "organic_count":
+        if agent_kind == "eps_organic_count":
+            from recogym.agents import EpsilonGreedy, epsilon_greedy_args
+            extra["table"] = agent.co_counts.argmax(axis=1).astype(np.int32)
+            extra["epsilon"] = 0.25
+            agent = EpsilonGreedy(ref.Configuration({**epsilon_greedy_args, "num_products": cfg.num_products,
+                                                     "epsilon": 0.25, "random_seed": cfg.random_seed}), agent)
+            agent.rng = H.PhiloxAgentRNG(env, cfg.random_seed)
+        elif agent_kind == "organic_count":
             extra["table"] = agent.co_counts.argmax(axis=1).astype(np.int32)
         elif agent_kind == "bandit_count":
             extra["table"] = agent.ctr.argmax(axis=1).astype(np.int32)
@@ -101,7 +110,8 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
     save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_organic,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=int(bool(cfg.change_omega_for_bandits)),
-         policy=("user_views" if agent_kind == "organic_user_count" else "table" if agent is not None else "uniform"),
+         policy=("user_views" if agent_kind == "organic_user_count" else "eps_table" if agent_kind == "eps_organic_count"
+                 else "table" if agent is not None else "uniform"),
          **sp, **{"log_" + k: v for k, v in A.items()}, **extra)
     print(name, "rows", len(df), "clicks", int((A["c"] == 1).sum()))
 
@@ -121,6 +131,9 @@ def main():
     if "--edge-only" in sys.argv:
         edge_cases()
         return
+    if "--eps-only" in sys.argv:
+        eps_greedy_case()
+        return
     t1_static_and_stats()
     t2_case("t2_seed42_P10_K5_u100", {"random_seed": 42}, 100)
     t2_case("t2_seed7_P100_K5_u60_o5", {"random_seed": 7, "num_products": 100, "K": 5}, 60, n_organic=5)
@@ -137,6 +150,7 @@ def main():
     train_case()
     evolution_case()
     edge_cases()
+    eps_greedy_case()
 
 
 def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
@@ -221,6 +235,11 @@ def evolution_case(name="t2_evolution_seed8_P30_K5"):
     save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=0, **sp, **out)
+
+
+def eps_greedy_case():
+    t2_case("t2_seed41_P25_K4_u60_eps_organic_count", {"random_seed": 41, "num_products": 25, "K": 4}, 60,
+            agent_kind="eps_organic_count", n_train=40)
 
 
 def edge_cases():

@@ -56,8 +56,9 @@ def test_rollout_matches_reference_logic(oracle, case):
     g = load_golden(case)
     env = oracle_env_from_golden(g)
     table = g["table"] if "table" in g.files else None
+    eps = float(g["epsilon"]) if "epsilon" in g.files else 0.0
     r = oracle.rollout(env, 0, int(g["n_users"]), policy=str(g["policy"]), table=table,
-                       n_organic_users=int(g["n_organic_users"]), log=True, hist=True)
+                       n_organic_users=int(g["n_organic_users"]), log=True, hist=True, epsilon=eps)
     L = r["log"]
     for k in "utzvac":
         assert np.array_equal(L[k], g["log_" + k]), k
@@ -71,7 +72,7 @@ def test_rollout_matches_reference_logic(oracle, case):
     assert np.array_equal(r["view_hist"], np.bincount(g["log_v"][z == 0], minlength=env.P))
     # multi-threaded run gives the same per-user results
     r4 = oracle.rollout(env, 0, int(g["n_users"]), policy=str(g["policy"]), table=table,
-                        n_organic_users=int(g["n_organic_users"]), threads=4)
+                        n_organic_users=int(g["n_organic_users"]), threads=4, epsilon=eps)
     for k in ("n_events", "n_organic", "n_bandit", "n_clicks", "hash", "last_view"):
         assert np.array_equal(r[k], r4[k]), k
 
