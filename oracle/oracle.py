@@ -230,3 +230,33 @@ def batch_step(env, st, action, sess_cap=None):
                              _p(st["last_view"]), _p(st["omega"]), _p(reward), _p(off), _p(sv), cap)
     assert n <= cap
     return reward, off, sv[:n].copy()
+
+
+# --- groundwork for a device EpsilonGreedy policy ---------------------------------------------------------------------
+def hole_cdf_table(P):
+    """S[m] = the m-th partial sum of numpy's sequential cumsum over m copies of 1/(P-1) (binary64).  The cdf of
+    EpsilonGreedy's exploring distribution (ones(P) with a 0 at the greedy action g, / sum; agents/epsilon_greedy.py:
+    36-43) is then cdf[j] = S[j+1] for j < g and S[j] for j >= g: adding the hole's exact 0 changes nothing, so ONE table
+    per P serves every g, and choice(P, p) becomes a binary search in S instead of P sequential additions per draw."""
+    c = 1.0 / float(P - 1)
+    S = np.zeros(P, np.float64)
+    acc = 0.0
+    for m in range(1, P):
+        acc = acc + c
+        S[m] = acc
+    return S
+
+
+def hole_choice(S, g, u):
+    """numpy legacy choice(P, p=uniform-with-hole-at-g) on the uniform u, from the table of hole_cdf_table."""
+    P = len(S)
+    last = S[P - 1]
+    lo, hi = 0, P                       # smallest j with cdf[j] / last > u
+    while lo < hi:
+        mid = (lo + hi) // 2
+        cdf = S[mid + 1] if mid < g else S[mid]
+        if cdf / last <= u:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo

@@ -120,3 +120,19 @@ def test_t1_statistics_are_plausible_under_oracle(oracle):
     p = r["view_hist"] / r["view_hist"].sum()
     q = g["view_hist"] / g["view_hist"].sum()
     assert 0.5 * np.abs(p - q).sum() < 0.08
+
+
+def test_hole_cdf_table_equals_numpy_choice(oracle):
+    """The table form of EpsilonGreedy's exploring draw (groundwork for the device policy) == numpy's legacy
+    choice(P, p) algorithm (cumsum, /= cdf[-1], searchsorted right) for every greedy action and many uniforms."""
+    rs = np.random.RandomState(3)
+    for P in (2, 3, 10, 257, 1000):
+        S = oracle.hole_cdf_table(P)
+        for g in sorted(set([0, 1, P // 2, P - 2, P - 1]) & set(range(P))):
+            p = np.ones(P); p[g] = 0.0; p = p / np.sum(p)
+            cdf = p.cumsum(); cdf /= cdf[-1]
+            us = np.concatenate([rs.random_sample(300), cdf[:-1], np.nextafter(cdf[:-1], 0), [0.0, 1 - 2.0 ** -53]])
+            ref = cdf.searchsorted(us, side="right")
+            got = np.array([oracle.hole_choice(S, g, float(u)) for u in us])
+            assert np.array_equal(got, ref), (P, g)
+            assert (got != g).all()
