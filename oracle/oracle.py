@@ -30,6 +30,7 @@ class _Env(C.Structure):
         ("sigma_omega_initial", C.c_double), ("sigma_omega", C.c_double),
         ("change_omega_for_bandits", C.c_int32), ("_pad", C.c_int32),
         ("seed", C.c_uint64),
+        ("time_mode", C.c_int32), ("_pad2", C.c_int32), ("time_mu", C.c_double), ("time_sigma", C.c_double),
     ]
 
 
@@ -40,7 +41,7 @@ class _Policy(C.Structure):
 class _Log(C.Structure):
     _fields_ = [("cap", C.c_int64), ("n", C.c_int64),
                 ("u", C.c_void_p), ("t", C.c_void_p), ("v", C.c_void_p), ("a", C.c_void_p),
-                ("z", C.c_void_p), ("c", C.c_void_p)]
+                ("z", C.c_void_p), ("c", C.c_void_p), ("tf", C.c_void_p)]
 
 
 class _Outputs(C.Structure):
@@ -67,6 +68,8 @@ def lib():
         L.rgo_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.rgo_policy_uniform_action.restype = C.c_int32
         L.rgo_policy_uniform_action.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32]
+        L.rgo_time_normal.restype = C.c_double
+        L.rgo_time_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.rgo_policy_uniform53.restype = C.c_double
         L.rgo_policy_uniform53.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]
         L.rgo_rollout.restype = None
@@ -101,6 +104,9 @@ def event_uniform(seed, user, t, which): return lib().rgo_event_uniform(int(seed
 def policy_uniform_action(seed, user, t, P): return lib().rgo_policy_uniform_action(int(seed), int(user), int(t), int(P))
 
 
+def time_normal(seed, user, call): return lib().rgo_time_normal(int(seed), int(user), int(call))
+
+
 def policy_uniform53(seed, user, t, which): return lib().rgo_policy_uniform53(int(seed), int(user), int(t), int(which))
 
 
@@ -115,7 +121,8 @@ class OracleEnv:
     """Static parameters of one reco-gym-v1 environment (host arrays, f64) + the seed."""
 
     def __init__(self, Gamma, mu_organic, beta, mu_bandit, trans, sigma_omega_initial, sigma_omega,
-                 seed, change_omega_for_bandits=False):
+                 seed, change_omega_for_bandits=False, normal_time=None):
+        """normal_time=(mu, sigma): NormalTimeGenerator clock (oracle only); None: the default event clock."""
         self.Gamma = np.ascontiguousarray(Gamma, np.float64)
         self.P, self.K = self.Gamma.shape
         self.mu_organic = np.ascontiguousarray(np.ravel(mu_organic), np.float64)
@@ -133,6 +140,8 @@ class OracleEnv:
         self.c.sigma_omega = float(sigma_omega)
         self.c.change_omega_for_bandits = int(bool(change_omega_for_bandits))
         self.c.seed = int(seed)
+        self.c.time_mode = 0 if normal_time is None else 1
+        self.c.time_mu, self.c.time_sigma = (0.0, 1.0) if normal_time is None else (float(normal_time[0]), float(normal_time[1]))
 
     def view_probs(self, omega):
         omega = np.ascontiguousarray(omega, np.float64).ravel()
@@ -190,7 +199,8 @@ def rollout(env, user_begin, n_users, policy="uniform", table=None, n_organic_us
         lg = _Log()
         lg.cap, lg.n = cap, 0
         cols = {"u": np.zeros(cap, np.int32), "t": np.zeros(cap, np.int32), "v": np.zeros(cap, np.int32),
-                "a": np.zeros(cap, np.int32), "z": np.zeros(cap, np.int8), "c": np.zeros(cap, np.int8)}
+                "a": np.zeros(cap, np.int32), "z": np.zeros(cap, np.int8), "c": np.zeros(cap, np.int8),
+                "tf": np.zeros(cap, np.float64)}
         for k, v in cols.items():
             setattr(lg, k, _p(v))
         out.log = C.pointer(lg)

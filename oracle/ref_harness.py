@@ -120,6 +120,11 @@ class PhiloxUserRNG:
         return O
 
     def _ut(self):
+        # streams are keyed by the EVENT INDEX: the clock value under the default clock, the number of new_time() calls
+        # since reset() minus one under the (float) NormalTimeGenerator clock
+        trng = getattr(self.env.time_generator, "rng", None)
+        if isinstance(trng, PhiloxTimeRNG):
+            return int(self.env.current_user_id), trng.calls - 1
         return int(self.env.current_user_id), int(self.env.current_time)
 
     def normal(self, loc=0.0, scale=1.0, size=None):
@@ -145,6 +150,22 @@ class PhiloxUserRNG:
         return idx if np.isscalar(a) or isinstance(a, (int, np.integer)) else a[idx]
 
 
+class PhiloxTimeRNG:
+    """Drop-in for NormalTimeGenerator.rng (normal_time_generator.py:23,27): the i-th new_time() call since reset() of
+    user u draws mu + sigma * z(seed, u, i, time slot)."""
+
+    def __init__(self, seed):
+        self.seed = int(seed)
+        self.user = 0
+        self.calls = 0
+
+    def normal(self, loc=0.0, scale=1.0):
+        from oracle import oracle as O
+        z = O.time_normal(self.seed, self.user, self.calls)
+        self.calls += 1
+        return loc + scale * z
+
+
 class PhiloxAgentRNG:
     """Drop-in for the `rng` of an agent's model (e.g. OrganicUserEventCounterModel.rng,
     agents/organic_user_count.py:43): draws come from the POLICY stream of the RNG spec at the env's
@@ -157,7 +178,8 @@ class PhiloxAgentRNG:
 
     def choice(self, a, p=None):
         from oracle import oracle as O
-        u, t = int(self.env.current_user_id), int(self.env.current_time)
+        u, t = self.env.rng._ut() if isinstance(self.env.rng, PhiloxUserRNG) else (int(self.env.current_user_id),
+                                                                                     int(self.env.current_time))
         is_coin = not (np.isscalar(a) or isinstance(a, (int, np.integer)))
         x = O.policy_uniform53(self.seed, u, t, 0 if is_coin else 1)
         cdf = np.asarray(p, dtype=np.float64).cumsum()
@@ -166,13 +188,32 @@ class PhiloxAgentRNG:
         return a[idx] if is_coin else idx
 
 
-def make_env(args, tier):
-    """Build the reference RecoEnv1 with `args` merged over env_1_args. tier: 'T1' | 'T2'."""
+def make_env(args, tier, normal_time=None):
+    """Build the reference RecoEnv1 with `args` merged over env_1_args. tier: 'T1' | 'T2'.
+    normal_time=(mu, sigma): the reference's NormalTimeGenerator as the env's clock (T2: its rng re-keyed)."""
     ref = load_reference()
     from copy import deepcopy
     env = ref.envs.reco_env_v1.RecoEnv1()
     full = {**deepcopy(ref.env_1_args), **args}
+    if normal_time is not None:
+        full["normal_time_mu"], full["normal_time_sigma"] = normal_time
+        full["time_generator"] = ref.NormalTimeGenerator(ref.Configuration(full))
     env.init_gym(full)
+    if normal_time is not None and tier == "T2":
+        tg = env.time_generator
+        tg.rng = PhiloxTimeRNG(full["random_seed"])
+        tg_reset, env_reset = tg.reset, env.reset
+
+        def reset_clock(_tg=tg, _orig=tg_reset):      # time_generator.reset() also restarts the call counter
+            _orig()
+            _tg.rng.calls = 0
+
+        def reset_env(user_id=0, _tg=tg, _orig=env_reset):
+            _tg.rng.user = int(user_id)               # AbstractEnv.reset draws the first increment BEFORE it stores user_id
+            return _orig(user_id)
+
+        tg.reset = reset_clock
+        env.reset = reset_env
     if tier == "T2":
         # static parameters stay the literal reference's (drawn from RandomState(seed) in
         # init_gym); only the dynamics stream is replaced.  reset_random_seed(epoch) re-keys.

@@ -36,6 +36,7 @@ T2_CASES_ORACLE_ONLY = [
     "t2_seed32_P7_K1_u80_o6",
     "t2_seed33_P20_K3_u120_fastleave",
     "t2_seed41_P25_K4_u60_eps_organic_count",   # the reference's EpsilonGreedy(OrganicCount), epsilon = 0.25
+    "t2_seed51_P30_K4_u50_o4_normal_time",      # the reference's NormalTimeGenerator clock (mu 0.5, sigma 2)
 ]
 
 
@@ -43,7 +44,8 @@ def oracle_env_from_golden(g):
     from oracle import oracle as O
     return O.OracleEnv(g["Gamma"], g["mu_organic"], g["beta"], g["mu_bandit"], g["state_transition"],
                        float(g["sigma_omega_initial"]), float(g["sigma_omega"]), int(g["seed"]),
-                       bool(int(g["change_omega_for_bandits"])))
+                       bool(int(g["change_omega_for_bandits"])),
+                       normal_time=tuple(g["normal_time"]) if "normal_time" in g.files else None)
 
 
 @pytest.fixture(scope="session")

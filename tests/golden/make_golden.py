@@ -60,8 +60,8 @@ def t1_static_and_stats():
              **H.static_params(env))
 
 
-def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
-    env = H.make_env(args, "T2")
+def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0, normal_time=None):
+    env = H.make_env(args, "T2", normal_time=normal_time)
     sp = H.static_params(env)
     cfg = env.config
     extra = {}
@@ -107,6 +107,9 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0):
             extra["table"] = agent.ctr.argmax(axis=1).astype(np.int32)
     df = env.generate_logs(n_users, agent=agent, num_organic_offline_users=n_organic)
     A = H.logs_to_arrays(df)
+    if normal_time is not None:
+        extra["normal_time"] = np.array(normal_time, np.float64)
+        extra["log_tf"] = df["t"].to_numpy().astype(np.float32)       # the DataFrame's float32 clock column
     save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_organic,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=int(bool(cfg.change_omega_for_bandits)),
@@ -134,6 +137,9 @@ def main():
     if "--eps-only" in sys.argv:
         eps_greedy_case()
         return
+    if "--time-only" in sys.argv:
+        normal_time_case()
+        return
     t1_static_and_stats()
     t2_case("t2_seed42_P10_K5_u100", {"random_seed": 42}, 100)
     t2_case("t2_seed7_P100_K5_u60_o5", {"random_seed": 7, "num_products": 100, "K": 5}, 60, n_organic=5)
@@ -151,6 +157,7 @@ def main():
     evolution_case()
     edge_cases()
     eps_greedy_case()
+    normal_time_case()
 
 
 def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
@@ -235,6 +242,11 @@ def evolution_case(name="t2_evolution_seed8_P30_K5"):
     save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=0, **sp, **out)
+
+
+def normal_time_case():
+    t2_case("t2_seed51_P30_K4_u50_o4_normal_time",
+            {"random_seed": 51, "num_products": 30, "K": 4, "sigma_omega": 0.3}, 50, n_organic=4, normal_time=(0.5, 2.0))
 
 
 def eps_greedy_case():

@@ -60,7 +60,9 @@ def test_rollout_matches_reference_logic(oracle, case):
     r = oracle.rollout(env, 0, int(g["n_users"]), policy=str(g["policy"]), table=table,
                        n_organic_users=int(g["n_organic_users"]), log=True, hist=True, epsilon=eps)
     L = r["log"]
-    for k in "utzvac":
+    if "normal_time" in g.files:     # float clock: the DataFrame's float32 't' column, rows keyed by the event index
+        assert np.array_equal(L["tf"].astype(np.float32), g["log_tf"]), "t (float clock)"
+    for k in ("uzvac" if "normal_time" in g.files else "utzvac"):
         assert np.array_equal(L[k], g["log_" + k]), k
     # counters are consistent with the log
     z, c = g["log_z"], g["log_c"]
