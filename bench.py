@@ -5,12 +5,18 @@
     python bench.py --impl reference --steps K --warmup W    # CPU baseline on the box's host cores
     torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, weak scaling
 
-Workload (BASELINE.json configs[2], the one the metric "reco-env-v1, P=10k" is quoted on):
+Default workload `c3` (BASELINE.json configs[2], the one the metric "reco-env-v1, P=10k" is quoted on):
 num_products=10000, K=20, 1M users per GPU per step, organic_count agent (trained with the
 reference-compatible OrganicCount.train on logged users, compiled to a device table).
 A step = one fused rollout of `users_per_gpu` fresh users to the end of their episodes on every
 rank + the all-reduce of the CTR counters.  1 user-step = one Markov event of one user
-(SURVEY.md 8d).  Prints ONE JSON line on rank 0.
+(SURVEY.md 8d).  Prints ONE JSON line on rank 0: `value` = device-resident throughput (CUDA events on the launching
+stream, L2 flushed between steps), `e2e` = the same through the host C ABI (`rg_rollout_host`: table H2D, counters D2H
+inside the timed region), `roofline` (HBM, as BASELINE.json asks; the fused rollout keeps user state on chip),
+`roofline_mufu` / `roofline_fp32` (the units that actually bound the kernel), `cpu_baseline` (the C oracle port of the
+reference algorithm on all host cores, bounded sample), `clocks`, `gpu_launches`.
+Other workloads (`--workload`): c2 (P=100, K=5, uniform logging policy), c4 (P=100 000, K=64, bandit_count table),
+c5 (A/B sweep: RandomAgent, OrganicCount, BanditCount, OrganicUserEventCounter, BanditMFSquare over the same users).
 """
 import argparse
 import json
