@@ -28,7 +28,12 @@ struct EnvDev {
     int KC, KCs, nslab;        // 16-byte K chunks per operand row: padded total, per slab, slabs (KC = KCs * nslab)
     int change_omega_for_bandits;
     uint64_t seed;
+    // tier 4 (oracle-order re-draw of the draws no binary64 summation order can separate, warp_sample_view_oracle_order)
+    double *t4_buf;            // [kT4Slots][Ppad] scratch of masses, one slot per concurrent re-draw
+    int *t4_lock;              // [kT4Slots] spin locks (0 free)
+    int force_t4;              // test hook (rg_debug_force_tier4): every binary64 draw takes the oracle-order path
 };
+constexpr int kT4Slots = 32;
 
 struct PolicyDev {
     int kind;
@@ -127,14 +132,109 @@ __device__ __forceinline__ double ctr_of_action(const EnvDev &env, const double 
     return ff64(acc + __ldg(env.mu_b + a));
 }
 
+// numpy's DOUBLE_pairwise_sum (contiguous input; numpy/core/src/umath/loops_utils.h) by ONE thread: blocks of at most
+// 128 elements are summed with 8 strided accumulators, larger ranges are split at n/2 rounded down to a multiple of 8.
+// The recursion is unrolled on an explicit stack (depth <= log2(n / 128) + 2).
+__device__ inline double np_pairwise_leaf(const double *a, long long n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (long long i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    long long i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+__device__ inline double np_pairwise_sum_dev(const double *a, long long n) {
+    long long off[40], len[40];
+    double left[40];
+    int stage[40];
+    int sp = 0;
+    double ret = 0.0;
+    off[0] = 0; len[0] = n; stage[0] = 0; sp = 1;
+    while (sp > 0) {
+        const int f = sp - 1;
+        if (len[f] <= 128) { ret = np_pairwise_leaf(a + off[f], len[f]); --sp; continue; }
+        long long n2 = len[f] / 2;
+        n2 -= n2 % 8;
+        if (stage[f] == 0) {
+            stage[f] = 1;
+            off[sp] = off[f]; len[sp] = n2; stage[sp] = 0; ++sp;
+        } else if (stage[f] == 1) {
+            left[f] = ret;
+            stage[f] = 2;
+            off[sp] = off[f] + n2; len[sp] = len[f] - n2; stage[sp] = 0; ++sp;
+        } else {
+            ret = left[f] + ret;
+            --sp;
+        }
+    }
+    return ret;
+}
+
+// TIER 4: the organic view of ONE user by ONE warp in the ORACLE'S OWN operation order (oracle/rg_oracle.c
+// user_product_view, i.e. reco_env_v1.py:119-128 + numpy's choice): logits by sequential fma chains, shift by their
+// MAXIMUM, exp, s = numpy pairwise sum, cdf = sequential cumsum of e/s, cdf /= cdf[-1], first index with cdf > u.
+// Used for the draws whose uniform lies so close to a CDF boundary that the summation order of the parallel samplers
+// could decide the index (about 1 per 10^7 draws): with it every discrete output equals the oracle by construction.
+// The masses go through a global scratch slot (env.t4_buf) guarded by a spin lock; the sequential part runs on lane 0.
+__device__ __noinline__ int warp_sample_view_oracle_order(const EnvDev &env, const double *omega, double u, int lane) {
+    const int K = env.K, P = env.P, Ppad = env.Ppad;
+    const int slot = (int)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kT4Slots);
+    double *e = env.t4_buf + (size_t)slot * Ppad;
+    if (lane == 0) {
+        while (atomicCAS(env.t4_lock + slot, 0, 1) != 0) { __nanosleep(200); }
+        __threadfence();
+    }
+    __syncwarp();
+    double mx = -INFINITY;
+    for (int p = lane; p < P; p += 32) {
+        const double *g = env.GammaT + p;
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc = fma(__ldg(g + (size_t)k * Ppad), omega[k], acc);
+        const double l = acc + __ldg(env.mu_o + p);
+        e[p] = l;
+        mx = fmax(mx, l);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    for (int p = lane; p < P; p += 32) e[p] = exp64(e[p] - mx);
+    __syncwarp();
+    int found = P - 1;
+    if (lane == 0) {
+        const double s = np_pairwise_sum_dev(e, P);
+        double c = 0.0;
+        for (int p = 0; p < P; ++p) c += e[p] / s;
+        const double last = c;
+        c = 0.0;
+        for (int p = 0; p < P; ++p) {
+            c += e[p] / s;
+            if (c / last > u) { found = p; break; }
+        }
+        __threadfence();
+        atomicExch(env.t4_lock + slot, 0);
+    }
+    found = __shfl_sync(0xffffffffu, found, 0);
+    return found;
+}
+
 // Exact (binary64) organic view sample for ONE user by ONE warp (reco_env_v1.py:119-128).
 // All products are visited in natural order, lane = product mod 32.  exp is shifted by an upper
 // bound of the logits instead of their maximum (the draw is invariant to the shift in exact
 // arithmetic; binary64 keeps ~1e-16 relative accuracy either way).  The inverse CDF is located in
 // two levels: 1024-product partial sums recorded in `sc` (shared, >= Ppad/1024+1 doubles), then a
 // 32-wide inclusive scan inside the crossing super-chunk.
-// *ambig is incremented when the uniform falls within 1e-11 (relative to the total mass) of a CDF
-// boundary: only there could a different binary64 summation order change the index.
+// When the uniform falls within 1e-11 (relative to the total mass; binary64 sums of P <= 10^5 terms agree to
+// P 2^-53 <= 1.2e-11) of a CDF boundary -- only there could a different binary64 summation order change the index --
+// the draw is repeated in the oracle's own order (tier 4, warp_sample_view_oracle_order) and counted in *ambig.
 __device__ inline int warp_sample_view_exact(const EnvDev &env, const double *omega, double *sc, double u,
                                              int lane, unsigned &ambig) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
@@ -195,16 +295,17 @@ __device__ inline int warp_sample_view_exact(const EnvDev &env, const double *om
         }
         cum = __shfl_sync(0xffffffffu, pre, 31);
     }
+    bool amb = env.force_t4 != 0;
     if (found < 0) {  // tau >= recomputed mass of the crossing super-chunk: rounding-level tie
-        found = min(end, P) - 1;
-        ambig += 1;
+        amb = true;
     } else {
-        const double tol = 1e-11 * Z;
-        if (tau - lower < tol || upper - tau < tol) {
-            // a boundary at distance < tol matters only if it is a real boundary (index > 0 below,
-            // index < P-1 above)
-            if ((tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1)) ambig += 1;
-        }
+        const double tol = fmax(1e-11, 4.0 * (double)P * 1.1102230246251565e-16) * Z;
+        // a boundary at distance < tol matters only if it is a real boundary (index > 0 below, index < P-1 above)
+        if ((tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1)) amb = true;
+    }
+    if (amb) {   // warp-uniform
+        found = warp_sample_view_oracle_order(env, omega, u, lane);
+        ambig += 1;
     }
     return found;
 }

@@ -35,6 +35,15 @@
 namespace rg {
 namespace fast {
 
+// RG_PROF (experiment builds only, `make prof`): cycle counters of the pass-1 hand-shakes and a time line of one round
+#ifdef RG_PROF
+__device__ unsigned long long g_prof[64];
+__device__ long long g_trace[8192];
+#define RG_PROF_ONLY(...) __VA_ARGS__
+#else
+#define RG_PROF_ONLY(...)
+#endif
+
 constexpr int TU = 128;     // user slots per CTA
 constexpr int SUB = 128;    // products per shared-memory tile
 constexpr int NT = 256;     // threads per CTA
@@ -519,7 +528,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
                 }
             }
         }
-        bool amb = false;
+        bool amb = !T2 && env.force_t4 != 0;
         if (found < 0) {
             found = min(end, P) - 1;
             amb = true;
@@ -527,13 +536,15 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
             // tier 2: the a-posteriori bound E of sum_p |e_p| enters S^ - u Z^ as (1-u) e(<=j) - u e(>j), i.e. at most
             // max(u, 1-u) E, plus twice the crossing chunk's share (its masses are recomputed here, the sweep's
             // values sit in Z^); tier 3: binary64 summation-order level
-            double tol = 1e-11 * Z;
+            double tol = fmax(1e-11, 4.0 * (double)P * 1.1102230246251565e-16) * Z;
             if (T2) {
                 const double uu = us[f];
                 tol = 1.01 * (fmax(uu, 1.0 - uu) * E + 2.0 * uu * esum[(size_t)f * ncs + csel]) + 1e-12 * Z;
             }
-            amb = (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
+            amb = amb || (tau - lower < tol && found > 0) || (upper - tau < tol && found < P - 1);
         }
+        if (!T2 && amb)   // warp-uniform: neither binary64 order can be trusted -> the oracle's own order (tier 4)
+            found = warp_sample_view_oracle_order(env, omega, us[f], lane);
         if (lane == 0) {
             if (T2) {
                 unresolved[f] = amb ? 1 : 0;
@@ -796,7 +807,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
     const int tx = tid & 15, ty = tid >> 4;
 
+    RG_PROF_ONLY(int round_no = 0; unsigned long long pf[16]; for (int i = 0; i < 16; ++i) pf[i] = 0ull;)
     for (;;) {
+        RG_PROF_ONLY(++round_no; const bool tr_on = blockIdx.x == 0 && round_no == 30;)
         long long tk0 = clock64();   // diagnostic: cycles per phase as seen by thread 0 (totals[10..15])
         // ---- A: compact the live slots into positions 0..nlive-1 (no data moves: pos2slot indirection)
         if (warp == 0) {
@@ -813,6 +826,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
         __syncthreads();
         const int nlive = misc[0];
+        RG_PROF_ONLY(if (tid == 0) { pf[12] += (unsigned long long)nlive; pf[13] += 1ull; })
         const int nq = misc[6];  // draws waiting for a re-sampling sweep (tier 2) ...
         const int nq3 = misc[4]; // ... and for a tier-3 sweep
         if (nlive == 0 && nq == 0 && nq3 == 0) break;
@@ -901,13 +915,18 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         const unsigned st = gs % (unsigned)nstage;
                         const int tt = uu / nslab, sl = uu - tt * nslab;
                         const unsigned gt = tile_use + (unsigned)tt, buf = gt % NBUF, use = gt / NBUF;
+                        RG_PROF_ONLY(const long long pa = clock64();)
                         mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
+                        RG_PROF_ONLY(const long long pb = clock64();)
                         if (sl == 0 && use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
+                        RG_PROF_ONLY(const long long pc = clock64();)
                         tc::tc_fence_after();
                         tc::issue_slab_mmas(tmem_base + buf * (uint32_t)tc::TILE_N, a_saddr, KC, sl,
                                             ring_saddr + st * tile_bytes, KCs);
                         tc::umma_commit(&sfree[st]);                       // this ring stage may be refilled ...
                         if (sl == nslab - 1) tc::umma_commit(&dfull[buf]);  // ... and the accumulator tile is complete
+                        RG_PROF_ONLY(const long long pd = clock64(); pf[0] += pb - pa; pf[1] += pc - pb; pf[2] += pd - pc; pf[3] += 1ull;
+                                     if (tr_on && uu < 1000) { g_trace[uu * 8 + 0] = pb; g_trace[uu * 8 + 1] = pc; g_trace[uu * 8 + 2] = pd; })
                         if (ASYNC && uu > 0 && uu - 1 + nstage < nunit) {   // (ASYNC: no free warp for the loader)
                             const unsigned gp = gs - 1u;
                             mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
@@ -924,8 +943,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 if (lane == 0) {
                     for (int uu = 0; uu + nstage < nunit; ++uu) {
                         const unsigned gp = seq_use + (unsigned)uu;
+                        RG_PROF_ONLY(const long long pa = clock64();)
                         mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
                         issue_load(gp + (unsigned)nstage);
+                        RG_PROF_ONLY(const long long pb = clock64(); pf[4] += pb - pa; pf[5] += 1ull;
+                                     if (tr_on && uu < 1000) g_trace[uu * 8 + 6] = pb;)
                     }
                 }
                 __syncwarp();
@@ -975,7 +997,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 for (int tt = 0; tt < ntile; ++tt) {
                     const unsigned gs = tile_use + (unsigned)tt;
                     const unsigned buf = gs % NBUF;
+                    RG_PROF_ONLY(const long long pa = clock64();)
                     mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
+                    RG_PROF_ONLY(const long long pb = clock64(); long long pld = 0;)
                     tc::tc_fence_after();
                     constexpr int HALF = tc::TILE_N;  // columns of this thread (the whole tile row)
                     float *gs_out = gsum_cta + (size_t)tt * (tc::TILE_N / 32) * TU + pos;
@@ -983,8 +1007,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     for (int c = 0; c < HALF; c += 32) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                         float v[32];
+                        RG_PROF_ONLY(const long long pl0 = clock64();)
                         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)tc::TILE_N +
                                           (uint32_t)c, v);
+                        RG_PROF_ONLY(pld += clock64() - pl0;)
                         if (c + 32 >= HALF) {  // last read of this tile: hand the accumulator back before the math
                             tc::tc_fence_before();
                             __syncwarp();
@@ -1008,6 +1034,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         part = 0.f;
                         ++rec;
                     }
+                    RG_PROF_ONLY(if (lane == 0) { const long long pe = clock64(); pf[6] += pb - pa; pf[7] += pld; pf[8] += pe - pb; pf[9] += 1ull;
+                                     if (tr_on && tt < 1000 && (q == 0 || q == 3)) { g_trace[tt * 8 + (q == 0 ? 3 : 5)] = pb; g_trace[tt * 8 + (q == 0 ? 4 : 7)] = pe; } })
                 }
             }
             tc::tc_fence_before();
@@ -1598,6 +1626,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
     }
 
+    RG_PROF_ONLY(if (lane == 0) { for (int i = 0; i < 16; ++i) if (pf[i]) atomicAdd(&g_prof[(warp < 4 ? 0 : warp == 4 ? 16 : 32) + i], pf[i]); })
     // ---- totals: warp reduction, one atomic per counter per warp
     if (p.out.totals) {
         if (tid == 0) {   // SM cycles thread 0 of this CTA spent in each phase (diagnostic, summed over the CTAs)
@@ -1617,6 +1646,18 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 }
 
 }  // namespace fast
+
+#ifdef RG_PROF
+extern "C" int rg_prof_read(unsigned long long *prof64, long long *trace8192, int reset) {
+    if (prof64) cudaMemcpyFromSymbol(prof64, fast::g_prof, sizeof(fast::g_prof));
+    if (trace8192) cudaMemcpyFromSymbol(trace8192, fast::g_trace, sizeof(fast::g_trace));
+    if (reset) {
+        static unsigned long long z[64];
+        cudaMemcpyToSymbol(fast::g_prof, z, sizeof(z));
+    }
+    return (int)cudaGetLastError();
+}
+#endif
 
 cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long user_begin,
                                 long long n_organic_users, long long n_total, const RolloutOutDev &out,
