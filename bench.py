@@ -78,18 +78,22 @@ def static_params(P, K):
     return cfg, draw_static_params(cfg)
 
 
-def build_policies(kinds, P, K, n_train):
+def build_policies(kinds, P, K, n_train, device=0):
     """-> [(kind, device policy name, table or None)].  Trainable agents are trained exactly as test_agent does
-    (bench_agents.py:176-190) on the SAME n_train logged users through the RecoEnv1 facade (GPU, default uniform
-    logging policy), then compiled to device policies (recogym_b200/policy.py)."""
+    (bench_agents.py:169-190) on the SAME n_train users logged under the default uniform policy: the count agents by
+    the device training path (fused rollout -> ordered log -> scatter-add -> arg-max table; recogym_b200/logs.py),
+    BanditMFSquare through the RecoEnv1 facade (its train() is torch code), then compiled to device policies
+    (recogym_b200/policy.py).  Everything runs on CUDA device `device` (the rank's own GPU)."""
     import recogym_b200 as rg
+    from recogym_b200 import _lib as L
+    from recogym_b200.logs import generate_logs_device
     A = rg.agents
     agents = {}
     for kind in kinds:
         if kind == "organic_count":
             agents[kind] = A.OrganicCount(rg.Configuration({**A.organic_count_args, "num_products": P}))
         elif kind == "bandit_count":
-            agents[kind] = _SparseBanditCount(P)
+            agents[kind] = A.BanditCount(rg.Configuration({**A.bandit_count_args, "num_products": P}))
         elif kind == "bandit_mf":
             import torch
             torch.manual_seed(SEED)
@@ -101,56 +105,100 @@ def build_policies(kinds, P, K, n_train):
             agents[kind] = A.RandomAgent(rg.Configuration({**A.random_args, "num_products": P, "random_seed": SEED}))
         else:
             raise ValueError(kind)
-    trainable = [a for k, a in agents.items() if k in ("organic_count", "bandit_count", "bandit_mf")]
-    if trainable:
+    count_agents = [a for k, a in agents.items() if k in ("organic_count", "bandit_count")]
+    facade_agents = [a for k, a in agents.items() if k == "bandit_mf"]
+    if count_agents or facade_agents:
         env = rg.make("reco-gym-v1")
-        env.init_gym({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED})
-        for uid in range(n_train):
+        env.init_gym({**rg.env_1_args, "num_products": P, "K": K, "random_seed": SEED, "device": device})
+        for a in count_agents:
+            prev = a.device_last_view() if hasattr(a, "device_last_view") else -1
+            log = generate_logs_device(env.device_env, n_train, "uniform", None, None, 0, 0, L.MATH_TENSOR,
+                                       prev_last_view=prev, train_mode=L.TRAIN_TEST_AGENT)
+            a.device_train(log)
+            del log
+        n_facade = min(n_train, 200)      # one launch per gym step: the facade is the compatibility path, not the fast one
+        for uid in range(n_facade if facade_agents else 0):
             env.reset(uid)
             new_obs, _, done, reward = env.step(None)
             while not done:
                 old_obs = new_obs
                 action, new_obs, reward, done, _ = env.step_offline(old_obs, reward, done)
-                for a in trainable:
+                for a in facade_agents:
                     a.train(old_obs, action, reward, False)
             old_obs = new_obs
             action, _, reward, done, _ = env.step_offline(old_obs, reward, done)
-            for a in trainable:
+            for a in facade_agents:
                 a.train(old_obs, action, reward, True)
     out = []
     for kind in kinds:
         pol = agents[kind].device_policy()
-        out.append((kind, pol["policy"], pol.get("table")))
+        table = pol.get("table")
+        if table is not None and hasattr(table, "cpu"):
+            table = table.cpu().numpy()
+        out.append((kind, pol["policy"], table))
     return out
 
 
-class _SparseBanditCount:
-    """BanditCount (agents/bandit_count.py) with the P x P matrices held sparsely: dense is
-    3 x 80 GB at P=100k.  Same update rule, same argmax with the (0+1)/(0+2) prior."""
+def host_info():
+    """CPU model / cores / load of the box the CPU arm runs on (the same 128-thread sample swung 6x between two hosts
+    in round 1: the line now says what it ran on)."""
+    model = "?"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        nodes = None
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count()
+    try:
+        load = [round(x, 1) for x in os.getloadavg()]
+    except Exception:
+        load = None
+    return {"cpu_model": model, "logical_cpus": os.cpu_count(), "affinity": aff, "numa_nodes": nodes, "loadavg": load}
 
-    def __init__(self, P):
-        self.P, self.pulls, self.clicks, self.lpv = P, {}, {}, None
 
-    def train(self, observation, action, reward, done=False):
-        if action is not None and reward is not None:
-            ix, jx = self.lpv, int(action["a"])
-            if observation.sessions():
-                self.lpv = observation.sessions()[-1]["v"]
-            if ix is not None:
-                self.pulls[(ix, jx)] = self.pulls.get((ix, jx), 0) + 1
-                self.clicks[(ix, jx)] = self.clicks.get((ix, jx), 0) + reward
+def cpu_policy(wl, n_train):
+    """The acting policy of the CPU arm == the GPU arm's: the count agents' tables are recomputed from the ORACLE's
+    own log of the same n_train training users (oracle/train_oracle.py), so that no kernel of ours is on the CPU arm's
+    path; bench.py checks them against the device-trained tables when both exist."""
+    from oracle import oracle as O
+    from oracle import train_oracle as T
+    kinds = wl["policy"] if isinstance(wl["policy"], list) else [wl["policy"]]
+    kind = "organic_user_count" if "organic_user_count" in kinds else kinds[0]
+    if kind in ("uniform", "random"):
+        return "uniform", None
+    if kind == "organic_user_count":
+        return "user_views", None
+    cfg, sp = static_params(wl["P"], wl["K"])
+    oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                     cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
+    log = O.rollout(oe, 0, n_train, policy="uniform", log=True, threads=os.cpu_count() or 1)["log"]
+    return "table", T.sparse_count_table(kind, wl["P"], log, 0)
 
-    def device_policy(self):
-        table = np.zeros(self.P, np.int32)
-        best = {}
-        for (ix, jx), n in self.pulls.items():
-            ctr = (self.clicks[(ix, jx)] + 1) / (n + 2)
-            cur = best.get(ix)
-            if ctr > 0.5 and (cur is None or ctr > cur[0] or (ctr == cur[0] and jx < cur[1])):
-                best[ix] = (ctr, jx)
-        for ix, (_, jx) in best.items():
-            table[ix] = jx
-        return {"policy": "table", "table": table}
+
+def cpu_reference_sample(wl, policy, table, threads, seconds, user0=0):
+    """Times the CPU oracle port of the reference algorithm on `threads` host threads for about `seconds` on users
+    user0.. of the workload; -> (user-steps/s, users simulated, seconds)."""
+    from oracle import oracle as O
+    cfg, sp = static_params(wl["P"], wl["K"])
+    oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                     cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
+    chunk = max(1, {100: 4096, 10000: 64, 100000: 8}.get(wl["P"], 64) * threads // (1 if threads > 1 else 16))
+    n_cpu, ev_cpu, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        rc = O.rollout(oe, user0 + n_cpu, chunk, policy=policy, table=table, threads=threads)
+        n_cpu += chunk
+        ev_cpu += int(rc["totals"][1])
+    dt = time.perf_counter() - t0
+    return ev_cpu / dt, n_cpu, dt
 
 
 class ClockSampler:
@@ -198,35 +246,27 @@ class ClockSampler:
 def run_reference(args, wl):
     """--impl reference: the reference's algorithm on the box's host cores.  The reference itself is
     Python and does not travel to the GPU box, so this is the C oracle port (oracle/rg_oracle.c),
-    all host threads, each step a bounded sample of the same workload."""
-    from oracle import oracle as O
-    cfg, sp = static_params(wl["P"], wl["K"])
-    oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
-                     cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
+    all host threads, each step a bounded sample (a few seconds) of the same workload: same parameters, same users
+    0.., same acting policy (trained table) as the GPU arm and its `cpu_baseline` leg."""
     cores = os.cpu_count() or 1
-    policy, table = ("uniform", None)
-    if isinstance(wl["policy"], list):
-        policy = "user_views"      # the most expensive acting policy of the sweep on the CPU (dense P-vector per act)
-    elif wl["policy"] != "uniform":
-        policy, table = "table", np.random.RandomState(SEED).randint(0, wl["P"], wl["P"]).astype(np.int32)
-    users = {100: 8192, 10000: 96, 100000: 12}.get(wl["P"], 96) * cores   # a few seconds per step on all cores
-    base = 10_000_000
+    policy, table = cpu_policy(wl, args.train_users)
+    secs = 4.0
     for w in range(args.warmup):
-        O.rollout(oe, base + w * users, max(cores, users // 8), policy=policy, table=table, threads=cores)
-    events = 0
-    t0 = time.perf_counter()
+        cpu_reference_sample(wl, policy, table, cores, 1.0, user0=50_000_000)
+    events_s, users, dt_all = [], 0, 0.0
     for s in range(args.steps):
-        r = O.rollout(oe, s * users, users, policy=policy, table=table, threads=cores)
-        events += int(r["totals"][1])
-    dt = time.perf_counter() - t0
-    val = events / dt
-    sample = "%d users/step x %d steps of the same workload, users 0.." % (users, args.steps)
+        v, n, dt = cpu_reference_sample(wl, policy, table, cores, secs, user0=users)
+        events_s.append(v * dt); users += n; dt_all += dt
+    val = sum(events_s) / dt_all
+    one, n1, dt1 = cpu_reference_sample(wl, policy, table, 1, 4.0)
+    sample = "users 0..%d of the same workload, %d steps of ~%.0f s, trained table of the GPU arm" % (users - 1, args.steps, secs)
     line = {
         "impl": "reference", "metric": "simulated user-steps/sec", "value": val, "unit": "user-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_all / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["label"], "users_per_step": users, "seed": SEED},
-        "cpu_baseline": {"value": val, "unit": "user-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["label"], "users_timed": users, "seed": SEED, "host": host_info()},
+        "cpu_baseline": {"value": val, "unit": "user-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "one_core": {"value": one, "users": n1}},
         "e2e": {"value": val, "unit": "user-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,7 +282,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--users", type=int, default=0, help="users per GPU per step (default: workload's)")
     ap.add_argument("--math", default="tensor", choices=["fast", "exact", "tensor"])
-    ap.add_argument("--train-users", type=int, default=200)
+    ap.add_argument("--train-users", type=int, default=1000, help="logged users the agents are trained on (SURVEY 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

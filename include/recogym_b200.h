@@ -102,8 +102,9 @@ typedef struct rg_rollout_out {
     int64_t *action_hist;/* [P] accumulated (delivered actions) */
     int64_t *click_hist; /* [P] accumulated (clicked actions; evaluate_agent.py:121-124) */
     int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
-                            [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] binary64-ambiguous
-                            samples (diagnostic, ~1e-7 of the views), [8] draws tier 2 sent to tier 3, [9] RG_POLICY_USER_VIEWS:
+                            [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] draws whose uniform lay within
+                            binary64 rounding distance of a CDF boundary and were therefore re-drawn in the oracle's own operation
+                            order (tier 4; ~1e-7 of the views; correct by construction, reported for information), [8] draws tier 2 sent to tier 3, [9] RG_POLICY_USER_VIEWS:
                             users whose distinct views overflowed the device list (must be 0); [10..15] diagnostic, CTA-batched
                             kernels: SM cycles per phase (compact, pass 1, pass 2, re-sampling, advance, omega) */
     /* Event log == the rows of the generate_logs DataFrame (abstract.py:256-327), unordered: one int32x4
@@ -228,6 +229,11 @@ int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *ou
  * omega: device [128][K] double, shift: device [128] float (log2 units). */
 int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *shift_device, float *out_device,
                         void *stream);
+
+/* Test hook: on != 0 sends every draw that reaches a binary64 sampler (all draws of RG_MATH_EXACT, tier 3 of the fast
+ * modes) through the oracle-order re-draw (tier 4), so that small runs exercise the path that otherwise serves ~1e-7 of
+ * the draws.  Process-wide; returns the previous value.  (oracle/rg_oracle.c user_product_view = reco_env_v1.py:119-128.) */
+int rg_debug_force_tier4(int on);
 
 int rg_device_count(void);              /* 0 when no usable GPU: callers must fail, not fall back */
 int rg_version(void);

@@ -59,6 +59,7 @@ EXPORTS = (
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
     "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
     "rg_spec_eval_device", "rg_tc_logits_device", "rg_device_count", "rg_version", "rg_last_error",
+    "rg_debug_force_tier4",
 )
 
 
@@ -114,6 +115,8 @@ def lib():
     L.rg_spec_policy_uniform_action.argtypes = [u64, u64, u32, i32]
     L.rg_spec_eval_device.restype = C.c_int
     L.rg_spec_eval_device.argtypes = [C.c_int, i64, vp, vp, vp]
+    L.rg_debug_force_tier4.restype = C.c_int
+    L.rg_debug_force_tier4.argtypes = [C.c_int]
     L.rg_tc_logits_device.restype = C.c_int
     L.rg_tc_logits_device.argtypes = [vp, vp, vp, vp, vp]
     _lib = L

@@ -40,8 +40,10 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_env(rg_env_impl &e) {
     cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
-    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_csum_scratch); cudaFree(e.d_gsum); cudaFree(e.d_views); cudaFree(e.diag);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_csum_scratch); cudaFree(e.d_gsum); cudaFree(e.d_views); cudaFree(e.diag); cudaFree(e.d_t4); cudaFree(e.d_host_arena);
 }
+
+int g_force_t4 = 0;   // rg_debug_force_tier4
 
 rg::RolloutOutDev to_dev(const rg_rollout_out &o) {
     rg::RolloutOutDev d;
@@ -201,6 +203,9 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     if (ce == cudaSuccess) ce = upload(&e.d_Gamma32, G32);
     if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.diag, sizeof(unsigned long long) * 64);
     if (ce == cudaSuccess) ce = cudaMemset(e.diag, 0, sizeof(unsigned long long) * 64);
+    const size_t t4_bytes = sizeof(double) * (size_t)rg::kT4Slots * Ppad + sizeof(int) * rg::kT4Slots;
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&e.d_t4, t4_bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(e.d_t4, 0, t4_bytes);
     if (ce != cudaSuccess) {
         free_env(e);
         delete env;
@@ -233,8 +238,17 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     v.nslab = nslab;
     v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
     v.seed = d->seed;
+    v.t4_buf = e.d_t4;
+    v.t4_lock = (int *)(e.d_t4 + (size_t)rg::kT4Slots * Ppad);
+    v.force_t4 = 0;
     *out = env;
     return RG_OK;
+}
+
+int rg_debug_force_tier4(int on) {
+    const int was = g_force_t4;
+    g_force_t4 = on ? 1 : 0;
+    return was;
 }
 
 int rg_env_set_seed(rg_env *env, uint64_t seed) {
@@ -256,6 +270,7 @@ int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, 
     int rc = check_rollout_args(env, policy, n_organic_users, n_users, out, math_mode);
     if (rc != RG_OK) return rc;
     RG_CUDA(cudaSetDevice(env->impl.device));
+    env->impl.dev.force_t4 = g_force_t4;
     rg::PolicyDev pol{policy->kind, policy->table, nullptr, 0, nullptr};
     const rg::RolloutOutDev od = to_dev(*out);
     if (policy->kind == RG_POLICY_USER_VIEWS) {
@@ -311,10 +326,24 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     const size_t o_lc = add(out->log && out->log_count ? out->log_count : nullptr, 8, true);
     const size_t o_tab = total;
     if (policy->kind == RG_POLICY_TABLE) total += ((size_t)4 * P + 255) & ~(size_t)255;
-    char *arena = nullptr;
+    // The staging arena belongs to the env and only ever grows: no cudaMalloc / cudaFree (an implicit device
+    // synchronisation each) on the call path.  Only the ACCUMULATED outputs need zeroing -- every per-user entry and
+    // every log row below *log_count is written by the kernel.
     if (total == 0) total = 256;
-    RG_CUDA(cudaMalloc((void **)&arena, total));
-    cudaError_t ce = cudaMemsetAsync(arena, 0, total, 0);
+    rg_env_impl &e = env->impl;
+    if (e.host_arena_bytes < total) {
+        if (e.d_host_arena) cudaFree(e.d_host_arena);
+        e.d_host_arena = nullptr;
+        e.host_arena_bytes = 0;
+        const size_t want = total + total / 4 + (1u << 20);
+        cudaError_t ae = cudaMalloc((void **)&e.d_host_arena, want);
+        if (ae != cudaSuccess) return fail(RG_ENOMEM, "rollout staging arena (%zu bytes): %s", want, cudaGetErrorString(ae));
+        e.host_arena_bytes = want;
+    }
+    char *arena = e.d_host_arena;
+    cudaError_t ce = cudaSuccess;
+    for (const Seg &s : segs)
+        if (s.accumulate && ce == cudaSuccess) ce = cudaMemsetAsync(arena + s.off, 0, s.bytes, 0);
     rg_policy pd = *policy;
     if (ce == cudaSuccess && policy->kind == RG_POLICY_TABLE) {
         ce = cudaMemcpyAsync(arena + o_tab, policy->table, (size_t)4 * P, cudaMemcpyHostToDevice, 0);
@@ -340,8 +369,9 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     }
     if (ce == cudaSuccess) {
         rc = rg_rollout_device(env, &pd, user_begin, n_organic_users, n_users, &dv, math_mode, nullptr);
-        if (rc != RG_OK) { cudaFree(arena); return rc; }
+        if (rc != RG_OK) return rc;
     }
+    // D2H on the same (legacy default) stream: each copy waits for the rollout and returns when the bytes are on the host
     std::vector<int64_t> tmp;
     for (const Seg &s : segs) {
         if (ce != cudaSuccess) break;
@@ -354,8 +384,7 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
                 for (size_t i = 0; i < tmp.size(); ++i) ((int64_t *)s.host)[i] += tmp[i];
         }
     }
-    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
-    cudaFree(arena);
+    if (ce == cudaSuccess && segs.empty()) ce = cudaStreamSynchronize(0);
     if (ce != cudaSuccess) return fail(RG_ECUDA, "rollout failed: %s", cudaGetErrorString(ce));
     return RG_OK;
 }
@@ -467,6 +496,7 @@ static int batch_common(rg_env *env, int mode, int64_t N, const int64_t *user_id
     if (sess_cap < 1) return fail(RG_EINVAL, "sess_cap must be >= 1");
     if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST) return fail(RG_EINVAL, "unknown math mode");
     RG_CUDA(cudaSetDevice(env->impl.device));
+    env->impl.dev.force_t4 = g_force_t4;
     RG_CUDA(rg::launch_batch(env->impl, mode, N, (const long long *)user_id, action, state, t, last_view, omega,
                              reward, sess_v, sess_len, sess_cap, n_unfinished, (cudaStream_t)stream));
     return RG_OK;

@@ -153,17 +153,17 @@ __device__ inline double np_pairwise_leaf(const double *a, long long n) {
     for (; i < n; ++i) res += a[i];
     return res;
 }
-__device__ inline double np_pairwise_sum_dev(const double *a, long long n) {
-    long long off[40], len[40];
-    double left[40];
-    int stage[40];
+__device__ inline double np_pairwise_sum_dev(const double *a, int n) {
+    int off[24], len[24];      // depth <= log2(n / 128) + 2 <= 24 for n < 2^31 / 128
+    double left[24];
+    int stage[24];
     int sp = 0;
     double ret = 0.0;
     off[0] = 0; len[0] = n; stage[0] = 0; sp = 1;
     while (sp > 0) {
         const int f = sp - 1;
         if (len[f] <= 128) { ret = np_pairwise_leaf(a + off[f], len[f]); --sp; continue; }
-        long long n2 = len[f] / 2;
+        int n2 = len[f] / 2;
         n2 -= n2 % 8;
         if (stage[f] == 0) {
             stage[f] = 1;
@@ -186,7 +186,7 @@ __device__ inline double np_pairwise_sum_dev(const double *a, long long n) {
 // Used for the draws whose uniform lies so close to a CDF boundary that the summation order of the parallel samplers
 // could decide the index (about 1 per 10^7 draws): with it every discrete output equals the oracle by construction.
 // The masses go through a global scratch slot (env.t4_buf) guarded by a spin lock; the sequential part runs on lane 0.
-__device__ __noinline__ int warp_sample_view_oracle_order(const EnvDev &env, const double *omega, double u, int lane) {
+static __device__ __noinline__ int warp_sample_view_oracle_order(const EnvDev &env, const double *omega, double u, int lane) {
     const int K = env.K, P = env.P, Ppad = env.Ppad;
     const int slot = (int)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kT4Slots);
     double *e = env.t4_buf + (size_t)slot * Ppad;

@@ -23,6 +23,9 @@ struct rg_env_impl {
     size_t views_lists = 0;              // lists allocated (each view_cap entries)
     int view_cap = 0;
     unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
+    char *d_host_arena = nullptr;        // rg_rollout_host: device staging of the table and the outputs, grown on demand
+    size_t host_arena_bytes = 0;
+    double *d_t4 = nullptr;              // tier 4 (oracle-order re-draw): [kT4Slots][Ppad] masses + kT4Slots int locks
 };
 
 struct rg_env {

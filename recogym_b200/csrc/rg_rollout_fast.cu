@@ -180,6 +180,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+// the same on a raw shared-memory address (the single-thread issuer / loader loops keep their barrier addresses in registers)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar_saddr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar_saddr, uint32_t issue) {   // converged warp, one issuing lane
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_saddr), "r"(issue)
+        : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -834,13 +853,13 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
         // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
         // bytes with the B ring, so it is built after pass 1.)
-        auto build_om32 = [&]() {
-            for (int idx = tid; idx < K1 * TU; idx += NTH) {
-                const int k = idx / TU, i = idx - k * TU;
-                float v = 0.f;
-                if (i < nlive) v = (k < K) ? (float)om64[(size_t)pos2slot[i] * KP + k] : 1.f;
-                om32[idx] = v;
-            }
+        auto build_om32 = [&]() {   // thread = (user position, half of the rows): the omega loads of a user pipeline
+            const int i = tid & (TU - 1), kh = tid >> 7, kmid = (K1 + 1) / 2;
+            const bool alive = i < nlive;
+            const double *om = om64 + (size_t)(alive ? pos2slot[i] : 0) * KP;
+            const int k0 = kh ? kmid : 0, k1 = kh ? K1 : kmid;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) om32[k * TU + i] = alive ? (k < K ? (float)om[k] : 1.f) : 0.f;
         };
         if (!TC) build_om32();
         if (tid < TU) {
@@ -884,18 +903,29 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             // Thread 0 issues the three-term MMA of tile s+1 before the CTA runs the epilogue of tile s:
             // thread (lane quarter q, column half h) owns user 32q+lane and 64 columns; per logit the epilogue is
             // one ex2 and one add.
-            const int KT = KC * 4;
-            for (int idx = tid; idx < TU * KT; idx += NTH) {
-                const int row = idx / KT, k = idx - row * KT;
-                float x = 0.f;
-                if (row < nlive) {
-                    if (k < K) x = (float)om64[(size_t)pos2slot[row] * KP + k];
-                    else if (k == K) x = 1.f;
-                    else if (k == K + 1) x = -s_shift[row];
+            {   // thread = (row, half of the K chunks): one 16-byte chunk (4 consecutive k of the row) per step, the
+                // chunk's four omega loads in flight together, float4 stores (consecutive rows -> consecutive 16 bytes)
+                static_assert(NT == 2 * TU, "A-tile build: two threads per row");
+                const int row = tid & (TU - 1), c0 = (tid >> 7) * (KC / 2);   // KC is even
+                const bool alive = row < nlive;
+                const double *om = om64 + (size_t)(alive ? pos2slot[row] : 0) * KP;
+                const float nshift = alive ? -s_shift[row] : 0.f;
+                for (int c = c0; c < c0 + KC / 2; ++c) {
+                    float x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * c + j;
+                        float v = 0.f;
+                        if (alive) v = k < K ? (float)om[k] : (k == K ? 1.f : (k == K + 1 ? nshift : 0.f));
+                        x[j] = v;
+                    }
+                    float4 hi, lo;
+                    hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
+                    lo.x = tc::tf32_hi(x[0] - hi.x); lo.y = tc::tf32_hi(x[1] - hi.y);
+                    lo.z = tc::tf32_hi(x[2] - hi.z); lo.w = tc::tf32_hi(x[3] - hi.w);
+                    *reinterpret_cast<float4 *>(a_tile + tc::tile_index(0, KC, row, 4 * c)) = hi;
+                    *reinterpret_cast<float4 *>(a_tile + tc::tile_index(1, KC, row, 4 * c)) = lo;
                 }
-                const float hi = tc::tf32_hi(x);
-                a_tile[tc::tile_index(0, KC, row, k)] = hi;
-                a_tile[tc::tile_index(1, KC, row, k)] = tc::tf32_hi(x - hi);
             }
             tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core
             tc::tc_fence_before();
@@ -908,30 +938,51 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 // ---- producer / MMA issuer (one thread): B tile landed -> accumulator buffer drained -> three-term
                 // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
                 // has completed, i.e. independently of the epilogue.
-                if (lane == 0) {
+                {   // the whole warp runs the loop (converged, warp-uniform values); one elected lane issues
+                    // Every scalar instruction of this loop is on the critical path of pass 1 (r02 profile: 650 cycles of
+                    // index arithmetic + 1170 of descriptor building per tile against 576 of tensor time): ring stage,
+                    // accumulator buffer and their phase bits are carried incrementally, descriptors are additions to
+                    // a precomputed low word, the MMA sequence is unrolled at compile time for the slab size.
+                    unsigned st = seq_use % (unsigned)nstage, stph = (seq_use / (unsigned)nstage) & 1u;
                     const unsigned tile_use = seq_use / (unsigned)nslab;   // accumulator tiles consumed so far
-                    for (int uu = 0; uu < nunit; ++uu) {   // ring units: K slab sl of product tile tt
-                        const unsigned gs = seq_use + (unsigned)uu;
-                        const unsigned st = gs % (unsigned)nstage;
-                        const int tt = uu / nslab, sl = uu - tt * nslab;
-                        const unsigned gt = tile_use + (unsigned)tt, buf = gt % NBUF, use = gt / NBUF;
+                    unsigned buf = tile_use % NBUF, use = tile_use / NBUF;
+                    int sl = 0;
+                    const uint32_t mbar_s = smem_u32(mbar), sfree_s = smem_u32(sfree), dfull_s = smem_u32(dfull),
+                                   dempty_s = smem_u32(dempty);
+                    const uint32_t a_lo0 = tc::umma_desc_lo(a_saddr, tc::CHUNK_BYTES);
+                    const uint32_t b_lo0 = tc::umma_desc_lo(ring_saddr, tc::CHUNK_BYTES_B);
+                    const uint32_t a_term16 = (uint32_t)KC * tc::CHUNK_BYTES / 16u, a_slab16 = (uint32_t)KCs * tc::CHUNK_BYTES / 16u;
+                    const uint32_t b_stage16 = tile_bytes / 16u;
+                    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+                    const uint32_t el = tc::elect_one();
+                    for (int uu = 0; uu < nunit; ++uu) {   // ring units: K slab sl of a product tile
                         RG_PROF_ONLY(const long long pa = clock64();)
-                        mbar_wait(&mbar[st], (gs / (unsigned)nstage) & 1u);
+                        mbar_wait_s(mbar_s + st * 8u, stph);
                         RG_PROF_ONLY(const long long pb = clock64();)
-                        if (sl == 0 && use > 0) mbar_wait(&dempty[buf], (use - 1u) & 1u);
+                        if (sl == 0 && use > 0) mbar_wait_s(dempty_s + buf * 8u, (use - 1u) & 1u);
                         RG_PROF_ONLY(const long long pc = clock64();)
                         tc::tc_fence_after();
-                        tc::issue_slab_mmas(tmem_base + buf * (uint32_t)tc::TILE_N, a_saddr, KC, sl,
-                                            ring_saddr + st * tile_bytes, KCs);
-                        tc::umma_commit(&sfree[st]);                       // this ring stage may be refilled ...
-                        if (sl == nslab - 1) tc::umma_commit(&dfull[buf]);  // ... and the accumulator tile is complete
+                        const uint32_t td = tmem_u + buf * (uint32_t)tc::TILE_N;
+                        const uint32_t a_lo = a_lo0 + (uint32_t)sl * a_slab16, b_lo = b_lo0 + st * b_stage16;
+                        const uint32_t accf = sl > 0 ? 1u : 0u;
+                        switch (KCs) {
+                            case 2: tc::issue_slab_mmas_lean<2>(td, a_lo, a_term16, b_lo, accf, el); break;
+                            case 4: tc::issue_slab_mmas_lean<4>(td, a_lo, a_term16, b_lo, accf, el); break;
+                            case 6: tc::issue_slab_mmas_lean<6>(td, a_lo, a_term16, b_lo, accf, el); break;
+                            default: tc::issue_slab_mmas_lean<8>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        }
+                        umma_commit_s(sfree_s + st * 8u, el);                        // this ring stage may be refilled ...
+                        if (sl == nslab - 1) umma_commit_s(dfull_s + buf * 8u, el);  // ... and the accumulator tile is complete
                         RG_PROF_ONLY(const long long pd = clock64(); pf[0] += pb - pa; pf[1] += pc - pb; pf[2] += pd - pc; pf[3] += 1ull;
-                                     if (tr_on && uu < 1000) { g_trace[uu * 8 + 0] = pb; g_trace[uu * 8 + 1] = pc; g_trace[uu * 8 + 2] = pd; })
-                        if (ASYNC && uu > 0 && uu - 1 + nstage < nunit) {   // (ASYNC: no free warp for the loader)
-                            const unsigned gp = gs - 1u;
+                                     if (tr_on && uu < 1000 && lane == 0) { g_trace[uu * 8 + 0] = pb; g_trace[uu * 8 + 1] = pc; g_trace[uu * 8 + 2] = pd; })
+                        if (ASYNC && lane == 0 && uu > 0 && uu - 1 + nstage < nunit) {   // (ASYNC: no free warp for the loader)
+                            const unsigned gp = seq_use + (unsigned)uu - 1u;
                             mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
                             issue_load(gp + (unsigned)nstage);
                         }
+                        if (ASYNC) __syncwarp();
+                        if (++st == (unsigned)nstage) { st = 0u; stph ^= 1u; }
+                        if (++sl == nslab) { sl = 0; if (++buf == NBUF) { buf = 0u; ++use; } }
                     }
                 }
                 __syncwarp();
@@ -941,13 +992,20 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 // refill issued from there would start a full TMA latency late.  sfree[stage] flips once per use of
                 // the stage and the next use needs this thread's load, so a phase can never be missed.
                 if (lane == 0) {
+                    // seq_use is a multiple of nunit, so ring unit uu + nstage of this round goes into the stage unit uu used
+                    unsigned st = seq_use % (unsigned)nstage, stph = (seq_use / (unsigned)nstage) & 1u;
+                    const uint32_t mbar_s = smem_u32(mbar), sfree_s = smem_u32(sfree);
+                    const unsigned char *src = (const unsigned char *)env.GTC + (size_t)nstage * tile_bytes;
                     for (int uu = 0; uu + nstage < nunit; ++uu) {
-                        const unsigned gp = seq_use + (unsigned)uu;
                         RG_PROF_ONLY(const long long pa = clock64();)
-                        mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
-                        issue_load(gp + (unsigned)nstage);
+                        mbar_wait_s(sfree_s + st * 8u, stph);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s + st * 8u), "r"(tile_bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         ring_saddr + st * tile_bytes), "l"(src), "r"(tile_bytes), "r"(mbar_s + st * 8u) : "memory");
+                        src += tile_bytes;
                         RG_PROF_ONLY(const long long pb = clock64(); pf[4] += pb - pa; pf[5] += 1ull;
                                      if (tr_on && uu < 1000) g_trace[uu * 8 + 6] = pb;)
+                        if (++st == (unsigned)nstage) { st = 0u; stph ^= 1u; }
                     }
                 }
                 __syncwarp();
@@ -992,7 +1050,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 const int pos = q * 32 + lane;
                 const bool act = pos < nlive;
                 float part = 0.f;
-                int rec = 0;
+                int rec = 0, in_rec = 0;
+                const int tiles_per_rec = p.rec_sub * (128 / tc::TILE_N);
                 const unsigned tile_use = seq_use / (unsigned)nslab;
                 for (int tt = 0; tt < ntile; ++tt) {
                     const unsigned gs = tile_use + (unsigned)tt;
@@ -1029,9 +1088,10 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         gs_out[(size_t)(c / 32) * TU] = cs;
                         part += cs;
                     }
-                    if ((tt + 1) % (p.rec_sub * (128 / tc::TILE_N)) == 0 || tt == ntile - 1) {
+                    if (++in_rec == tiles_per_rec || tt == ntile - 1) {
                         if (act) tilesum[(size_t)pos * p.nrec_pad + rec] = part;
                         part = 0.f;
+                        in_rec = 0;
                         ++rec;
                     }
                     RG_PROF_ONLY(if (lane == 0) { const long long pe = clock64(); pf[6] += pb - pa; pf[7] += pld; pf[8] += pe - pb; pf[9] += 1ull;

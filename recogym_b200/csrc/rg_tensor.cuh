@@ -120,6 +120,62 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Lean descriptor arithmetic for the MMA issuer (ONE thread issues every UMMA of the kernel: each scalar instruction on
+// its path costs ~5 cycles of latency).  Only the address field of a descriptor changes from MMA to MMA: the low word is
+// (saddr >> 4) | (LBO >> 4) << 16, the high word (SBO = 128 B, version 1) is the same for every operand tile, and an
+// operand offset is an addition to the low word (shared-memory addresses stay below 2^18, so nothing carries into LBO).
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+__host__ __device__ inline uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) { return (uint64_t)lo | ((uint64_t)kDescHi << 32); }
+// tcgen05.mma executed by a CONVERGED warp with warp-uniform operands, issued by the lane(s) whose `issue` is non-zero
+// (exactly one: elect_one()).  Keeping the warp converged lets the compiler move the descriptors to uniform registers
+// once instead of running a per-lane uniformisation loop (ELECT / R2UR / BRA.U.ANY) around every MMA.
+__device__ __forceinline__ void umma_tf32_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t issue) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {   // 1 in exactly one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+// The three-term contraction of one K slab (KCS chunks) with everything folded at compile time: a_lo / b_lo are the
+// descriptor low words of chunk 0 of this slab, "hi" term; a_term16 = 16-byte units between A's hi and lo terms.
+// Called by a converged warp; `issue` selects the issuing lane.
+template <int KCS>
+__device__ __forceinline__ void issue_slab_mmas_lean(uint32_t tmem_d, uint32_t a_lo, uint32_t a_term16, uint32_t b_lo,
+                                                     uint32_t accumulate, uint32_t issue) {
+    constexpr uint32_t b_term16 = (uint32_t)KCS * CHUNK_BYTES_B / 16u;
+    constexpr uint32_t a_step16 = 2u * CHUNK_BYTES / 16u, b_step16 = 2u * CHUNK_BYTES_B / 16u;
+    uint32_t acc = accumulate;
+    // small terms first: lo*hi, hi*lo, then hi*hi
+#pragma unroll
+    for (int pair = 0; pair < 3; ++pair) {
+        const uint32_t a0 = a_lo + (pair == 0 ? a_term16 : 0u);
+        const uint32_t b0 = b_lo + (pair == 1 ? b_term16 : 0u);
+#pragma unroll
+        for (int s = 0; s < KCS / 2; ++s) {
+            umma_tf32_pred(tmem_d, umma_desc_from_lo(a0 + (uint32_t)s * a_step16),
+                           umma_desc_from_lo(b0 + (uint32_t)s * b_step16), kIdescTf32, acc, issue);
+            acc = 1u;
+        }
+    }
+}
+#endif
+
 // One thread: the three-term tf32 contraction of ONE K SLAB of one 128 x TILE_N tile into TMEM columns
 // [tmem_d, tmem_d + TILE_N).  a_saddr: the whole A tile ([2 terms][KC chunks]); b_saddr: this slab of the B tile
 // ([2 terms][KCs chunks]).  Slab 0 overwrites the accumulator, the others add to it.

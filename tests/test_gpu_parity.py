@@ -44,12 +44,14 @@ def both_envs(P, K, seed, **over):
 PER_USER = ("n_events", "n_organic", "n_bandit", "n_clicks", "last_view")
 
 
-def assert_rollout_equal(r_gpu, r_cpu, hist=True, omega=True):
+def assert_rollout_equal(r_gpu, r_cpu, hist=True, omega=True, ambiguous_ok=False):
+    """totals[7] counts the draws that were re-drawn in the oracle's own operation order (tier 4): correct by
+    construction, but at these sizes none is expected unless the test forces the path (ambiguous_ok)."""
     for k in PER_USER:
         assert np.array_equal(r_gpu[k], r_cpu[k]), k
     assert np.array_equal(np.asarray(r_gpu["hash"]).view(np.uint64), r_cpu["hash"]), "hash"
     assert np.array_equal(r_gpu["totals"][:6], r_cpu["totals"][:6]), (r_gpu["totals"], r_cpu["totals"])
-    assert r_gpu["totals"][7] == 0, "binary64-ambiguous samples reported"
+    assert ambiguous_ok or r_gpu["totals"][7] == 0, "oracle-order re-draws at a size where none is expected"
     if hist:
         for k in ("view_hist", "action_hist", "click_hist"):
             assert np.array_equal(r_gpu[k], r_cpu[k]), k
@@ -237,9 +239,9 @@ def test_c3_shape_fast_equals_exact_on_device():
 
 
 def test_c4_shape_fast_equals_exact_on_device():
-    """P=100000, K=64 (BASELINE C4): the CTA-batched kernel needs its global-memory spill of the re-sampling sums and of
-    the omega rows (one CTA per SM); RG_MATH_TENSOR falls back to the CUDA-core contraction for this K.  Discrete
-    results must equal the all-binary64 sampler."""
+    """P=100000, K=64 (BASELINE C4): RG_MATH_FAST needs its global-memory spill of the re-sampling sums and of the omega
+    rows (one CTA per SM); RG_MATH_TENSOR runs the contraction on tcgen05 in three K slabs per product tile.  Discrete
+    results must equal the all-binary64 sampler (the oracle comparison at this shape: tests/test_gpu_bench_scale.py)."""
     from recogym_b200 import DeviceEnv
     cfg, sp = synthetic_env(100000, 64, 42)
     de = DeviceEnv(sp, 1, 0.1, 42)
@@ -250,7 +252,6 @@ def test_c4_shape_fast_equals_exact_on_device():
         for k in PER_USER + ("hash", "view_hist", "action_hist", "click_hist", "omega"):
             assert np.array_equal(a[k], b[k]), (mode, k)
         assert np.array_equal(a["totals"][:6], b["totals"][:6])
-        assert a["totals"][7] == 0 and b["totals"][7] == 0
     de.close()
 
 
