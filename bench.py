@@ -64,7 +64,9 @@ def measured_traffic(user_steps_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the committed ncu --set full
     capture (profiles/r01_roofline_traffic.json), scaled from the captured launch to this launch's size."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
+        prof = os.path.join(ROOT, "profiles")
+        name = "r02_roofline_traffic.json" if os.path.exists(os.path.join(prof, "r02_roofline_traffic.json")) else "r01_roofline_traffic.json"
+        t = json.load(open(os.path.join(prof, name)))
         per_step = (t["dram_bytes_read"] + t["dram_bytes_write"]) / float(t["user_steps_in_captured_launch"])
         return per_step * user_steps_per_launch
     except Exception:
@@ -315,52 +317,77 @@ def main():
 
     cfg, sp = static_params(P, K)
     kinds = wl["policy"] if isinstance(wl["policy"], list) else [wl["policy"]]
-    policies = build_policies(kinds, P, K, args.train_users)
+    policies = build_policies(kinds, P, K, args.train_users, device=local_rank)
     de = rg.DeviceEnv(sp, cfg.sigma_omega_initial, cfg.sigma_omega, SEED, device=local_rank)
     tables_dev = [torch.as_tensor(t, device=dev) if t is not None else None for _, _, t in policies]
-    policy, table = policies[0][1], policies[0][2]          # cpu_baseline leg: the first policy of the workload
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step_tots = torch.zeros((args.steps, 16), dtype=torch.int64, device=dev)
+    job_tot = torch.zeros(16, dtype=torch.int64, device=dev)
 
     def step(s, tot):
-        """one fused rollout of U fresh users on this rank + the all-reduce of the CTR counters"""
+        """one fused rollout of U fresh users on this rank (every agent of an A/B sweep sees the same users); the
+        counters accumulate on the device"""
         first = (s * world + rank) * U
-        for (_, pol, _), tdev in zip(policies, tables_dev):   # every agent of an A/B sweep sees the same users
+        for (_, pol, _), tdev in zip(policies, tables_dev):
             de.rollout_device(U, pol, tdev, first, 0, math_mode, per_user=False, totals=tot)
-        allreduce_counters(tot)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    warm_tot = torch.zeros(16, dtype=torch.int64, device=dev)
     for w in range(args.warmup):
-        step(1000 + w, torch.zeros(16, dtype=torch.int64, device=dev))
+        step(1000 + w, warm_tot)
+    allreduce_counters(warm_tot)          # warms the collective up as well
     barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # The timed region: K steps (L2 flushed before each) + ONE all-reduce of the job's CTR counters at the end -- the
+    # only collective of the path (SURVEY 8e).  Ranks are not synchronised between steps (round 1 all-reduced after
+    # every step, which made every rank wait for the slowest launch tail 8 times per second).
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    ev0.record()
     for s in range(args.steps):
-        flush.fill_(s & 0xFF)              # L2 flush between timed iterations (outside the event pair)
+        flush.fill_(s & 0xFF)              # L2 flush between timed iterations (40 us of 256 MiB writes, inside the bracket)
         evs[s][0].record()
-        step(s, step_tots[s])
+        step(s, job_tot)
         evs[s][1].record()
+    allreduce_counters(job_tot)
+    ev1.record()
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms = float(t_dev.item())
     clocks = sampler.stop() if rank == 0 else None
-    ev = step_tots.sum(0).cpu().numpy()   # every row was all-reduced: job-wide counters of the timed steps
+    ev = job_tot.cpu().numpy()            # all-reduced: job-wide counters of the timed steps
     events = int(ev[1])
     value = events / (total_ms * 1e-3)
 
+    # ---- rank-count invariance (SURVEY 8e): the counters of a fixed user range do not depend on how it is sharded
+    rank_invariant = None
+    if world > 1:
+        from recogym_b200.parallel import shard_range
+        n_fix = 1_000_000 if P <= 10000 else 100_000
+        first, count = shard_range(n_fix, rank, world, 7_000_000)
+        part = de.rollout_device(count, policies[0][1], tables_dev[0], first, 0, math_mode, per_user=False, hist=True)
+        red = [part["totals"], part["view_hist"], part["action_hist"], part["click_hist"]]
+        allreduce_counters(*red)
+        if rank == 0:
+            whole = de.rollout_device(n_fix, policies[0][1], tables_dev[0], 7_000_000, 0, math_mode, per_user=False, hist=True)
+            rank_invariant = bool(torch.equal(whole["totals"][:10], part["totals"][:10]) and
+                                  all(torch.equal(whole[k], part[k]) for k in ("view_hist", "action_hist", "click_hist")))
+        barrier()
+
     # ---- e2e: the reference-facing host API (C ABI with HOST buffers), copies inside the timed region
+    for _, pol, tab in policies:          # untimed: grows the env's staging arena once
+        de.rollout_host(1024, pol, tab, 9_000_000, 0, math_mode, per_user=False)
     barrier()
     t0 = time.perf_counter()
     e2e_events = 0
@@ -405,6 +432,8 @@ def main():
         "config": {"workload": wl["label"], "num_products": P, "K": K, "users_per_gpu_per_step": U,
                    "policy": wl["policy"], "device_policies": [p for _, p, _ in policies], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
                    "l2": "flushed between timed iterations (256 MiB write); Gamma is L2-resident by design within a launch",
+                   "train_users": args.train_users, "step_ms_min_max": [round(min(step_ms), 3), round(max(step_ms), 3)],
+                   "rank_invariant_counters": rank_invariant,
                    "events_timed": events, "ctr": float(ev[4]) / max(1.0, float(ev[3])),
                    "fast_path_fallbacks": int(ev[6]), "tier3_resamples": int(ev[8]), "f64_ambiguous": int(ev[7]),
                    "pass1_cycles_per_128_draws": round(float(ev[11]) / max(1.0, float(ev[2])) * 128.0, 1),
@@ -412,7 +441,7 @@ def main():
                                                  [round(float(x) / max(1.0, float(ev[10:16].sum())), 4) for x in ev[10:16]]))},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "user-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * len(policies) * (4 if (args.math != "exact" and U >= 4 * 296 * 128) else 1),  # rollout (+ 3 schedule kernels)
+        "gpu_launches": args.steps * len(policies) * (5 if (args.math != "exact" and U >= 4 * 296 * 128) else 1),  # rollout (+ 4 schedule kernels)
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": measured_traffic(launch_events), "peak_source": peak_src,
                      "algorithmic_bytes_per_user_step": alg_bytes,
@@ -436,20 +465,18 @@ def main():
                                  "frac": per_gpu_steps_s * flops_per_step / fp32_peak,
                                  "flops_per_user_step": flops_per_step}
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
-                         cfg.sigma_omega_initial, cfg.sigma_omega, SEED)
         cores = os.cpu_count() or 1
-        chunk = {100: 4096, 10000: 64, 100000: 8}.get(P, 64) * cores   # bounded sample: stop after ~12 s
-        n_cpu, ev_cpu, t0 = 0, 0, time.perf_counter()
-        while time.perf_counter() - t0 < 12.0:
-            rc = O.rollout(oe, n_cpu, chunk, policy=policy, table=table, threads=cores)
-            n_cpu += chunk
-            ev_cpu += int(rc["totals"][1])
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": ev_cpu / dt, "unit": "user-steps/s", "cores": cores, "kind": "port",
-                                "sample": "users 0..%d of the same workload (%.1f s; C oracle port of the reference "
-                                "algorithm, oracle/rg_oracle.c, %d host threads)" % (n_cpu - 1, dt, cores)}
+        cpol, ctab = cpu_policy(wl, args.train_users)
+        if ctab is not None and policies[0][2] is not None and cpol == "table" and policies[0][1] == "table":
+            # the table the oracle derives from ITS log of the training users == the device-trained table
+            line["config"]["device_trained_table_equals_oracle"] = bool(np.array_equal(ctab, policies[0][2]))
+        v_all, n_all, dt_all = cpu_reference_sample(wl, cpol, ctab, cores, 12.0)
+        v_one, n_one, dt_one = cpu_reference_sample(wl, cpol, ctab, 1, 5.0)
+        line["cpu_baseline"] = {"value": v_all, "unit": "user-steps/s", "cores": cores, "kind": "port",
+                                "sample": "users 0..%d of the same workload, same trained table (%.1f s; C oracle port of "
+                                          "the reference algorithm, oracle/rg_oracle.c, %d host threads)" % (n_all - 1, dt_all, cores),
+                                "one_core": {"value": v_one, "users": n_one, "seconds": round(dt_one, 1)},
+                                "host": host_info()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

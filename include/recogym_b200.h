@@ -169,17 +169,41 @@ int rg_generate_logs_device(rg_env *env, const rg_policy *policy, const double *
                             int32_t *carry_device, const rg_log_columns *cols_device, int64_t *row_offset_device, int32_t *last_view_device,
                             int64_t *rows_device, int64_t *totals_device, int math_mode, void *stream);
 
-/* Agent.train over a whole log, as scatter-adds of the count agents' sufficient statistics (all int32 [P][P], nullable,
- * accumulated): co_counts += b b^T per organic session (OrganicCount.train, agents/organic_count.py:74-82);
- * pulls[lvp][a] += 1, clicks[lvp][a] += c per bandit row (BanditCount.train, agents/bandit_count.py:49-62).
- * train_mode must be the one the columns were generated with.  Needs the columns z, v, a, c, lvp, sess, flags. */
+/* Agent.train over a whole log, as scatter-adds of the count agents' sufficient statistics (all int64 [P][P], nullable,
+ * accumulated; the reference holds them as float64): co_counts += b b^T per organic session (OrganicCount.train,
+ * agents/organic_count.py:74-82); pulls[lvp][a] += 1, clicks[lvp][a] += c per bandit row (BanditCount.train,
+ * agents/bandit_count.py:49-62).  train_mode must be the one the columns were generated with.
+ * Needs the columns z, v, a, c, lvp, sess, flags. */
 int rg_count_stats_device(const rg_log_columns *cols_device, int64_t rows, int32_t P, int train_mode,
-                          int32_t *co_counts, int32_t *pulls, int32_t *clicks, void *stream);
+                          int64_t *co_counts, int64_t *pulls, int64_t *clicks, void *stream);
 /* The acting table of a count agent: kind 0 = OrganicCount.act, table[v] = argmax_j A[v][j] (A = co_counts, B unused);
  * kind 1 = BanditCount.act, table[v] = argmax_j (B[v][j] + 1) / (A[v][j] + 2) (A = pulls, B = clicks), ps[v] = that
  * ratio.  First maximum wins (numpy.argmax). */
-int rg_count_policy_device(int kind, int32_t P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+int rg_count_policy_device(int kind, int32_t P, const int64_t *A, const int64_t *B, int32_t *table, double *ps,
                            void *stream);
+
+/* The same statistics for num_products too large for [P][P] (BASELINE configs[3]: P = 100 000 -> 3 x 80 GB dense): a
+ * device hash table, open addressing with linear probing, key = row * 2^32 + col.  All pointers are DEVICE memory owned by
+ * the caller: keys[capacity] initialised to 0xFF bytes (empty), a / b [capacity] and row_a / row_b [P] and stats[2] to 0. */
+typedef struct rg_sparse_counts {
+    int64_t capacity;   /* slots, a power of two */
+    uint64_t *keys;
+    int64_t *a;         /* co_counts | pulls */
+    int64_t *b;         /* (unused)  | clicks */
+    int64_t *row_a;     /* BanditCount only, [P]: pulls added to EVERY cell of a row -- numpy's `pulls_a[None, a] += 1` while */
+    int64_t *row_b;     /*   last_product_viewed is still None (agents/bandit_count.py:54-57) -- and the clicks likewise */
+    int64_t *stats;     /* [0] occupied slots, [1] failures: insertions that found the table full / rows the policy could
+                           not resolve (must stay 0; grow the table and train again otherwise) */
+} rg_sparse_counts;
+/* rg_count_stats_device into hash tables (either may be NULL). */
+int rg_sparse_count_stats_device(const rg_log_columns *cols_device, int64_t rows, int train_mode,
+                                 const rg_sparse_counts *co_counts, const rg_sparse_counts *bandit, void *stream);
+/* Growth: adds every occupied cell of `from` to `to` (an empty, larger table); the caller copies row_a / row_b. */
+int rg_sparse_rehash_device(const rg_sparse_counts *from, const rg_sparse_counts *to, void *stream);
+/* rg_count_policy_device from a hash table: identical tables (numpy.argmax over the dense rows, first maximum wins;
+ * untouched cells count 0 for kind 0 and (row_b + 1) / (row_a + 2) for kind 1). */
+int rg_sparse_count_policy_device(int kind, int32_t P, const rg_sparse_counts *counts, int32_t *table, double *ps,
+                                  void *stream);
 /* evaluate_IPS / evaluate_SNIPS (evaluate_agent.py:753-835) of a deterministic table policy over the bandit rows of the
  * users < u_end: out4_device = {sum ee, sum ee^2, sum pi/ps, rows} with ee = c * [a == target[lv]] / ps.
  * Needs the columns z, u, a, c, ps, lv. */

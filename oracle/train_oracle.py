@@ -113,3 +113,85 @@ def ips_summary(ee, rewards, ratio):
     se = np.std(ee) / np.sqrt(len(ee))
     return {"ips_mean": float(np.mean(ee)), "ips_se": float(se),
             "snips_mean": float(np.sum(rewards * ratio) / np.sum(ratio)), "snips_se": float(se)}
+
+
+# ---- the same statistics held sparsely (P x P is 80 GB at P = 100 000: BASELINE configs[3]) -----------------------------
+def sparse_count_stats(P, log, n_organic_users, user_begin=0, last_product_viewed=None, mode=0):
+    """count_stats with dict-of-keys matrices: co[(i, j)], pulls[(i, j)], clicks[(i, j)], plus the whole-row increments
+    numpy makes while BanditCount.last_product_viewed is still None (`pulls_a[None, jx] += 1` adds 1 to every cell of
+    ROW jx): row_pulls[jx], row_clicks[jx].  -> (co, pulls, clicks, row_pulls, row_clicks, last_product_viewed)."""
+    co, pulls, clicks, row_pulls, row_clicks = {}, {}, {}, {}, {}
+    lpv = last_product_viewed
+    for _, session, action, reward in iter_train_calls(log, n_organic_users, user_begin, mode):
+        if session:
+            views, cnt = np.unique(np.asarray(session, np.int64), return_counts=True)
+            for vi, ci in zip(views.tolist(), cnt.tolist()):
+                for vj, cj in zip(views.tolist(), cnt.tolist()):
+                    co[(vi, vj)] = co.get((vi, vj), 0) + ci * cj
+        if action is not None and reward is not None:
+            ix, jx = lpv, action
+            if session:
+                lpv = session[-1]
+            if ix is None:
+                row_pulls[jx] = row_pulls.get(jx, 0) + 1
+                row_clicks[jx] = row_clicks.get(jx, 0) + reward
+            else:
+                pulls[(ix, jx)] = pulls.get((ix, jx), 0) + 1
+                clicks[(ix, jx)] = clicks.get((ix, jx), 0) + reward
+    return co, pulls, clicks, row_pulls, row_clicks, lpv
+
+
+def sparse_organic_count_table(P, co):
+    """co_counts.argmax(axis=1) (organic_count.py:56) from the sparse cells: the largest count of the row, the first
+    (lowest) column among ties; a row without cells is all zero -> 0."""
+    best = {}
+    for (i, j), n in co.items():
+        cur = best.get(i)
+        if n > 0 and (cur is None or n > cur[0] or (n == cur[0] and j < cur[1])):
+            best[i] = (n, j)
+    table = np.zeros(P, np.int32)
+    for i, (_, j) in best.items():
+        table[i] = j
+    return table
+
+
+def sparse_bandit_count_table(P, pulls, clicks, row_pulls=None, row_clicks=None):
+    """((clicks + 1) / (pulls + 2)).argmax(axis=1) and that maximum (bandit_count.py:26-47,59-61) from the sparse cells.
+    Every cell of row i that was never touched holds the row's base value b_i = (rc_i + 1) / (rp_i + 2) (0.5 without
+    whole-row increments); numpy.argmax returns the FIRST column attaining the maximum, so the answer is the best
+    touched cell when it beats b_i or when the whole row has been touched (lowest column among ties), else the lowest
+    column whose cell is not below b_i."""
+    row_pulls, row_clicks = row_pulls or {}, row_clicks or {}
+    rows = {}
+    for (i, j), n in pulls.items():
+        rows.setdefault(i, []).append(j)
+    table = np.zeros(P, np.int32)
+    ps = np.empty(P, np.float64)
+    for i in range(P):
+        rp, rc = row_pulls.get(i, 0), row_clicks.get(i, 0)
+        ps[i] = (rc + 1) / (rp + 2)
+    for i, cols in rows.items():
+        rp, rc = row_pulls.get(i, 0), row_clicks.get(i, 0)
+        base = (rc + 1) / (rp + 2)
+        val = {j: (clicks.get((i, j), 0) + rc + 1) / (pulls[(i, j)] + rp + 2) for j in cols}
+        vmax = max(val.values())
+        if vmax > base or len(val) == P:       # (a row with every cell touched has no cell left at the base value)
+            table[i] = min(j for j, x in val.items() if x == vmax)
+            ps[i] = vmax
+        else:
+            j = 0
+            while j in val and val[j] < base:
+                j += 1
+            table[i] = j
+            ps[i] = base
+    return table, ps
+
+
+def sparse_count_table(kind, P, log, n_organic_users, user_begin=0, mode=0):
+    """The acting table of OrganicCount / BanditCount after test_agent-style training on `log` (sparse statistics)."""
+    co, pulls, clicks, rp, rc, _ = sparse_count_stats(P, log, n_organic_users, user_begin, None, mode)
+    if kind == "organic_count":
+        return sparse_organic_count_table(P, co)
+    if kind == "bandit_count":
+        return sparse_bandit_count_table(P, pulls, clicks, rp, rc)[0]
+    raise ValueError(kind)

@@ -50,6 +50,10 @@ class LogColumns(C.Structure):
         "t", "u", "z", "v", "a", "c", "ps", "lv", "lvp", "sess", "flags")]
 
 
+class SparseCounts(C.Structure):
+    _fields_ = [("capacity", C.c_int64)] + [(n, C.c_void_p) for n in ("keys", "a", "b", "row_a", "row_b", "stats")]
+
+
 _lib = None
 
 EXPORTS = (
@@ -59,7 +63,8 @@ EXPORTS = (
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
     "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
     "rg_spec_eval_device", "rg_tc_logits_device", "rg_device_count", "rg_version", "rg_last_error",
-    "rg_debug_force_tier4",
+    "rg_debug_force_tier4", "rg_sparse_count_stats_device", "rg_sparse_count_policy_device",
+    "rg_sparse_rehash_device",
 )
 
 
@@ -94,6 +99,13 @@ def lib():
     L.rg_count_stats_device.argtypes = [C.POINTER(LogColumns), i64, i32, C.c_int, vp, vp, vp, vp]
     L.rg_count_policy_device.restype = C.c_int
     L.rg_count_policy_device.argtypes = [C.c_int, i32, vp, vp, vp, vp, vp]
+    L.rg_sparse_count_stats_device.restype = C.c_int
+    L.rg_sparse_count_stats_device.argtypes = [C.POINTER(LogColumns), i64, C.c_int, C.POINTER(SparseCounts),
+                                               C.POINTER(SparseCounts), vp]
+    L.rg_sparse_rehash_device.restype = C.c_int
+    L.rg_sparse_rehash_device.argtypes = [C.POINTER(SparseCounts), C.POINTER(SparseCounts), vp]
+    L.rg_sparse_count_policy_device.restype = C.c_int
+    L.rg_sparse_count_policy_device.argtypes = [C.c_int, i32, C.POINTER(SparseCounts), vp, vp, vp]
     L.rg_ips_device.restype = C.c_int
     L.rg_ips_device.argtypes = [C.POINTER(LogColumns), i64, i64, vp, vp, vp]
     L.rg_batch_reset_device.restype = C.c_int

@@ -1,6 +1,7 @@
 import numpy as np
 
 from ..envs.configuration import Configuration
+from ._sparse import HostSparseCounts
 from .abstract import Agent
 
 bandit_count_args = {
@@ -16,22 +17,32 @@ class BanditCount(Agent):
     def __init__(self, config=Configuration(bandit_count_args)):
         super().__init__(config)
         P = self.config.num_products
-        self.pulls_a = np.zeros((P, P))
-        self.clicks_a = np.zeros((P, P))
+        from ..logs import SPARSE_MIN_PRODUCTS
+        # large catalogues (BASELINE configs[3]: P = 100 000 -> 3 x 80 GB dense): sparse statistics, same argmax
+        self._sp = HostSparseCounts(P) if P >= SPARSE_MIN_PRODUCTS else None
         self.last_product_viewed = None
-        self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
+        if self._sp is None:
+            self.pulls_a = np.zeros((P, P))
+            self.clicks_a = np.zeros((P, P))
+            self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
+        else:
+            self.pulls_a = self.clicks_a = self.ctr = None
 
     def act(self, observation, reward, done):
         self.sync_host()
         self.update_lpv(observation)
-        row = self.ctr[self.last_product_viewed, :]
-        action = row.argmax()
+        if self._sp is not None:
+            action, ps = self._sp.bandit_argmax(self.last_product_viewed)
+        else:
+            row = self.ctr[self.last_product_viewed, :]
+            action = row.argmax()
+            ps = row[action]
         if self.config.with_ps_all:
             ps_all = np.zeros(self.config.num_products)
             ps_all[action] = 1.0
         else:
             ps_all = ()
-        return {**super().act(observation, reward, done), "a": action, "ps": row[action], "ps-a": ps_all}
+        return {**super().act(observation, reward, done), "a": action, "ps": ps, "ps-a": ps_all}
 
     def train(self, observation, action, reward, done=False):
         # NB the reference credits the pull to last_product_viewed BEFORE updating it from the
@@ -40,6 +51,12 @@ class BanditCount(Agent):
         if action is not None and reward is not None:
             ix, jx = self.last_product_viewed, action["a"]
             self.update_lpv(observation)
+            if self._sp is not None:
+                if ix is None:          # numpy's pulls_a[None, jx] += 1 touches the whole ROW jx
+                    self._sp.add_row(jx, 1, int(reward))
+                else:
+                    self._sp.add(ix, jx, 1, int(reward))
+                return
             self.pulls_a[ix, jx] += 1
             self.clicks_a[ix, jx] += reward
             self.ctr[ix, jx] = (self.clicks_a[ix, jx] + 1) / (self.pulls_a[ix, jx] + 2)
@@ -68,9 +85,13 @@ class BanditCount(Agent):
         from ..logs import CountStats
         import torch
         if self._stats is None:
-            self._stats = CountStats(self.config.num_products, log.env.device, organic=False, bandit=True)
-            self._stats.pulls.copy_(torch.as_tensor(self.pulls_a.astype(np.int32)))
-            self._stats.clicks.copy_(torch.as_tensor(self.clicks_a.astype(np.int32)))
+            self._stats = CountStats(self.config.num_products, log.env.device, organic=False, bandit=True,
+                                     sparse=self._sp is not None)
+            if self._sp is None:
+                self._stats.pulls.copy_(torch.as_tensor(self.pulls_a.astype(np.int64)))
+                self._stats.clicks.copy_(torch.as_tensor(self.clicks_a.astype(np.int64)))
+            elif self._sp.n_cells() or self._sp.row_a:
+                self._stats.load_host(None, self._sp)
         self._stats.train(log)
         self.last_product_viewed = None if self._stats.last_view < 0 else int(self._stats.last_view)
 
@@ -79,13 +100,19 @@ class BanditCount(Agent):
 
     def sync_host(self):
         if self._stats is not None:
-            self.pulls_a = self._stats.pulls.cpu().numpy().astype(np.float64)
-            self.clicks_a = self._stats.clicks.cpu().numpy().astype(np.float64)
-            self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
+            if self._sp is None:
+                self.pulls_a = self._stats.pulls.cpu().numpy().astype(np.float64)
+                self.clicks_a = self._stats.clicks.cpu().numpy().astype(np.float64)
+                self.ctr = (self.clicks_a + 1) / (self.pulls_a + 2)
+            else:
+                self._sp = self._stats.to_host()[1]
             self._stats = None
 
     def device_policy(self):
         if self._stats is not None:
             return self._stats.bandit_count_policy()
+        if self._sp is not None:
+            table, ps = self._sp.bandit_table()
+            return {"policy": "table", "table": table, "ps_table": ps}
         table = self.ctr.argmax(axis=1).astype(np.int32)
         return {"policy": "table", "table": table, "ps_table": self.ctr[np.arange(len(table)), table]}

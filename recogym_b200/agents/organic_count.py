@@ -1,6 +1,7 @@
 import numpy as np
 
 from ..envs.configuration import Configuration
+from ._sparse import HostSparseCounts
 from .abstract import Agent
 
 organic_count_args = {
@@ -17,13 +18,19 @@ class OrganicCount(Agent):
     def __init__(self, config=Configuration(organic_count_args)):
         super().__init__(config)
         P = self.config.num_products
-        self.co_counts = np.zeros((P, P))
+        from ..logs import SPARSE_MIN_PRODUCTS
+        # large catalogues: the P x P matrix (8 P^2 bytes) gives way to a sparse form with the same argmax (agents/_sparse.py)
+        self._sp = HostSparseCounts(P) if P >= SPARSE_MIN_PRODUCTS else None
+        self.co_counts = np.zeros((P, P)) if self._sp is None else None
         self.corr = None
 
     def act(self, observation, reward, done):
         self.sync_host()
         self.update_lpv(observation)
-        action = self.co_counts[self.last_product_viewed, :].argmax()
+        if self._sp is not None:
+            action = self._sp.organic_argmax(self.last_product_viewed)
+        else:
+            action = self.co_counts[self.last_product_viewed, :].argmax()
         if self.config.with_ps_all:
             ps_all = np.zeros(self.config.num_products)
             ps_all[action] = 1.0
@@ -38,6 +45,11 @@ class OrganicCount(Agent):
         sessions = observation.sessions()
         if sessions:
             views, cnt = np.unique(np.array([s["v"] for s in sessions], dtype=np.int64), return_counts=True)
+            if self._sp is not None:
+                for vi, ci in zip(views.tolist(), cnt.tolist()):
+                    for vj, cj in zip(views.tolist(), cnt.tolist()):
+                        self._sp.add(vi, vj, ci * cj)
+                return
             self.co_counts[np.ix_(views, views)] += np.outer(cnt, cnt).astype(self.co_counts.dtype)
 
     def update_lpv(self, observation):
@@ -53,17 +65,26 @@ class OrganicCount(Agent):
         from ..logs import CountStats
         import torch
         if self._stats is None:
-            self._stats = CountStats(self.config.num_products, log.env.device, organic=True, bandit=False)
-            self._stats.co_counts.copy_(torch.as_tensor(self.co_counts.astype(np.int32)))
+            self._stats = CountStats(self.config.num_products, log.env.device, organic=True, bandit=False,
+                                     sparse=self._sp is not None)
+            if self._sp is None:
+                self._stats.co_counts.copy_(torch.as_tensor(self.co_counts.astype(np.int64)))
+            elif self._sp.n_cells():
+                self._stats.load_host(self._sp, None)
         self._stats.train(log)
 
     def sync_host(self):
         if self._stats is not None:
-            self.co_counts = self._stats.co_counts.cpu().numpy().astype(np.float64)
+            if self._sp is None:
+                self.co_counts = self._stats.co_counts.cpu().numpy().astype(np.float64)
+            else:
+                self._sp = self._stats.to_host()[0]
             self._stats = None
 
     def device_policy(self):
         if self._stats is not None:
             pol = self._stats.organic_count_policy()
             return {"policy": "table", "table": pol["table"]}
+        if self._sp is not None:
+            return {"policy": "table", "table": self._sp.organic_table()}
         return {"policy": "table", "table": self.co_counts.argmax(axis=1).astype(np.int32)}

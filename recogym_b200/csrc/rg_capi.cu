@@ -449,8 +449,8 @@ int rg_generate_logs_device(rg_env *env, const rg_policy *policy, const double *
     return RG_OK;
 }
 
-int rg_count_stats_device(const rg_log_columns *cols, int64_t rows, int32_t P, int train_mode, int32_t *co_counts,
-                          int32_t *pulls, int32_t *clicks, void *stream) {
+int rg_count_stats_device(const rg_log_columns *cols, int64_t rows, int32_t P, int train_mode, int64_t *co_counts,
+                          int64_t *pulls, int64_t *clicks, void *stream) {
     if (!cols || rows < 0 || P < 1 || train_mode < 0 || train_mode > 2) return fail(RG_EINVAL, "bad argument");
     if (rows > cols->capacity) return fail(RG_EINVAL, "rows exceed the column capacity");
     if (!cols->z || !cols->v || !cols->a || !cols->c || !cols->lvp || !cols->sess || !cols->flags)
@@ -461,10 +461,53 @@ int rg_count_stats_device(const rg_log_columns *cols, int64_t rows, int32_t P, i
     return RG_OK;
 }
 
-int rg_count_policy_device(int kind, int32_t P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+int rg_count_policy_device(int kind, int32_t P, const int64_t *A, const int64_t *B, int32_t *table, double *ps,
                            void *stream) {
     if ((kind != 0 && kind != 1) || P < 1 || !A || !table || (kind == 1 && !B)) return fail(RG_EINVAL, "bad argument");
     RG_CUDA(rg::launch_row_argmax(kind, P, A, B, table, ps, (cudaStream_t)stream));
+    return RG_OK;
+}
+
+static int check_sparse(const rg_sparse_counts *s, bool bandit) {
+    if (!s->keys || !s->a || !s->stats || s->capacity < 2 || (s->capacity & (s->capacity - 1)))
+        return fail(RG_EINVAL, "sparse counts: keys / a / stats and a power-of-two capacity are required");
+    if (bandit && (!s->b || !s->row_a || !s->row_b)) return fail(RG_EINVAL, "sparse bandit counts need b, row_a, row_b");
+    return RG_OK;
+}
+
+int rg_sparse_count_stats_device(const rg_log_columns *cols, int64_t rows, int train_mode, const rg_sparse_counts *co,
+                                 const rg_sparse_counts *bandit, void *stream) {
+    if (!cols || rows < 0 || train_mode < 0 || train_mode > 2) return fail(RG_EINVAL, "bad argument");
+    if (rows > cols->capacity) return fail(RG_EINVAL, "rows exceed the column capacity");
+    if (!cols->z || !cols->v || !cols->a || !cols->c || !cols->lvp || !cols->sess || !cols->flags)
+        return fail(RG_EINVAL, "count statistics need the columns z, v, a, c, lvp, sess, flags");
+    int rc = RG_OK;
+    if (co && (rc = check_sparse(co, false)) != RG_OK) return rc;
+    if (bandit && (rc = check_sparse(bandit, true)) != RG_OK) return rc;
+    RG_CUDA(rg::launch_sparse_count_stats(*cols, rows, train_mode, co, bandit, current_num_sms(), (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_sparse_rehash_device(const rg_sparse_counts *from, const rg_sparse_counts *to, void *stream) {
+    if (!from || !to) return fail(RG_EINVAL, "null argument");
+    int rc = check_sparse(from, false);
+    if (rc == RG_OK) rc = check_sparse(to, false);
+    if (rc != RG_OK) return rc;
+    if ((from->b != nullptr) != (to->b != nullptr)) return fail(RG_EINVAL, "both tables must have (or lack) the b values");
+    RG_CUDA(rg::launch_sparse_rehash(*from, *to, current_num_sms(), (cudaStream_t)stream));
+    return RG_OK;
+}
+
+int rg_sparse_count_policy_device(int kind, int32_t P, const rg_sparse_counts *s, int32_t *table, double *ps, void *stream_) {
+    if ((kind != 0 && kind != 1) || P < 1 || !s || !table) return fail(RG_EINVAL, "bad argument");
+    int rc = check_sparse(s, kind == 1);
+    if (rc != RG_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *scratch = nullptr;
+    RG_CUDA(cudaMallocAsync((void **)&scratch, sizeof(unsigned long long) * 3 * (size_t)P, stream));
+    cudaError_t ce = rg::launch_sparse_policy(kind, P, *s, table, ps, scratch, current_num_sms(), stream);
+    cudaFreeAsync(scratch, stream);
+    if (ce != cudaSuccess) return fail(RG_ECUDA, "sparse policy failed: %s", cudaGetErrorString(ce));
     return RG_OK;
 }
 

@@ -54,10 +54,15 @@ cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, lon
                            long long n_organic_users, long long user_begin, const int32_t *last_view, int prev_last_view,
                            int policy_kind, int P, const double *ps_table, const rg_log_columns &c, int train_mode,
                            int32_t *carry_out, int num_sms, cudaStream_t stream);
-cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int32_t *co,
-                               int32_t *pulls, int32_t *clicks, int num_sms, cudaStream_t stream);
-cudaError_t launch_row_argmax(int kind, int P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int64_t *co,
+                               int64_t *pulls, int64_t *clicks, int num_sms, cudaStream_t stream);
+cudaError_t launch_row_argmax(int kind, int P, const int64_t *A, const int64_t *B, int32_t *table, double *ps,
                               cudaStream_t stream);
+cudaError_t launch_sparse_count_stats(const rg_log_columns &c, long long rows, int train_mode, const rg_sparse_counts *co,
+                                      const rg_sparse_counts *bandit, int num_sms, cudaStream_t stream);
+cudaError_t launch_sparse_rehash(const rg_sparse_counts &from, const rg_sparse_counts &to, int num_sms, cudaStream_t stream);
+cudaError_t launch_sparse_policy(int kind, int P, const rg_sparse_counts &s, int32_t *table, double *ps,
+                                 unsigned long long *scratch, int num_sms, cudaStream_t stream);
 cudaError_t launch_ips(const rg_log_columns &c, long long rows, long long u_end, const int32_t *target, double *part,
                        int nblocks, double *out, cudaStream_t stream);
 cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);

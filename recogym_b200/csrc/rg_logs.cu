@@ -264,7 +264,7 @@ __global__ void carry_kernel(const int4 *__restrict__ ordered, const long long *
 // session, and (r, r).
 __global__ void organic_pairs_kernel(const int8_t *__restrict__ z, const int32_t *__restrict__ v,
                                      const int32_t *__restrict__ sess, const int8_t *__restrict__ flags, int train_mode,
-                                     long long rows, int P, int32_t *__restrict__ co) {
+                                     long long rows, int P, unsigned long long *__restrict__ co) {
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
         if (z[r] != 0) continue;
         if (train_mode != 0) {   // the final session is only trained on by the warm-up loop's phantom call
@@ -272,11 +272,11 @@ __global__ void organic_pairs_kernel(const int8_t *__restrict__ z, const int32_t
             if ((f & FLAG_FINAL_SESSION) && !(train_mode == 2 && (f & FLAG_NO_REAL_BANDIT))) continue;
         }
         const int vr = v[r], s = sess[r];
-        atomicAdd(co + (size_t)vr * P + vr, 1);
+        atomicAdd(co + (size_t)vr * P + vr, 1ull);
         for (int k = 1; k <= s; ++k) {
             const int vj = v[r - k];
-            atomicAdd(co + (size_t)vr * P + vj, 1);
-            atomicAdd(co + (size_t)vj * P + vr, 1);
+            atomicAdd(co + (size_t)vr * P + vj, 1ull);
+            atomicAdd(co + (size_t)vj * P + vr, 1ull);
         }
     }
 }
@@ -287,7 +287,7 @@ __global__ void organic_pairs_kernel(const int8_t *__restrict__ z, const int32_t
 __global__ void bandit_stats_kernel(const int8_t *__restrict__ z, const int32_t *__restrict__ a,
                                     const float *__restrict__ c, const int32_t *__restrict__ lvp,
                                     const int8_t *__restrict__ flags, int train_mode, long long rows, int P,
-                                    int32_t *__restrict__ pulls, int32_t *__restrict__ clicks) {
+                                    unsigned long long *__restrict__ pulls, unsigned long long *__restrict__ clicks) {
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
         if (z[r] != 1) continue;
         if (train_mode != 0) {
@@ -297,12 +297,12 @@ __global__ void bandit_stats_kernel(const int8_t *__restrict__ z, const int32_t 
         const int ar = a[r], ix = lvp[r];
         const int rew = c[r] > 0.5f ? 1 : 0;
         if (ix >= 0) {
-            atomicAdd(pulls + (size_t)ix * P + ar, 1);
-            if (rew) atomicAdd(clicks + (size_t)ix * P + ar, 1);
+            atomicAdd(pulls + (size_t)ix * P + ar, 1ull);
+            if (rew) atomicAdd(clicks + (size_t)ix * P + ar, 1ull);
         } else {
             for (int p = 0; p < P; ++p) {
-                atomicAdd(pulls + (size_t)ar * P + p, 1);
-                if (rew) atomicAdd(clicks + (size_t)ar * P + p, 1);
+                atomicAdd(pulls + (size_t)ar * P + p, 1ull);
+                if (rew) atomicAdd(clicks + (size_t)ar * P + p, 1ull);
             }
         }
     }
@@ -311,8 +311,8 @@ __global__ void bandit_stats_kernel(const int8_t *__restrict__ z, const int32_t 
 // Row arg-max (first maximum wins, as numpy.argmax): one warp per row.
 //   kind 0: OrganicCount.act  -> argmax_j co[v][j]                       (organic_count.py:56)
 //   kind 1: BanditCount.act   -> argmax_j (clicks[v][j]+1)/(pulls[v][j]+2), ps = that ratio (bandit_count.py:30-33)
-__global__ void __launch_bounds__(256) row_argmax_kernel(int kind, int P, const int32_t *__restrict__ A,
-                                                         const int32_t *__restrict__ B, int32_t *__restrict__ table,
+__global__ void __launch_bounds__(256) row_argmax_kernel(int kind, int P, const int64_t *__restrict__ A,
+                                                         const int64_t *__restrict__ B, int32_t *__restrict__ table,
                                                          double *__restrict__ ps) {
     const int lane = threadIdx.x & 31;
     const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
@@ -335,6 +335,163 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(int kind, int P, const 
         table[row] = bj;
         if (ps) ps[row] = kind == 0 ? 1.0 : best;
     }
+}
+
+// ---- the same statistics in a device hash table (num_products too large for [P][P]: BASELINE configs[3], P = 100 000) ----
+// Open addressing, linear probing; key = row * 2^32 + col, empty = ~0; values int64 {a, b} accumulated with atomics.
+// stats[0] counts occupied slots, stats[1] insertions that found no slot (the caller grows the table and re-trains).
+__device__ __forceinline__ void sparse_add(const rg_sparse_counts &t, int row, int col, unsigned long long da,
+                                           unsigned long long db) {
+    const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    const unsigned long long mask = (unsigned long long)t.capacity - 1ull;
+    unsigned long long slot = h & mask;
+    for (long long probe = 0; probe < t.capacity; ++probe) {
+        unsigned long long k = t.keys[slot];
+        if (k != key) {
+            if (k != ~0ull) { slot = (slot + 1ull) & mask; continue; }
+            k = atomicCAS((unsigned long long *)t.keys + slot, ~0ull, key);
+            if (k == ~0ull) atomicAdd((unsigned long long *)t.stats, 1ull);
+            else if (k != key) { slot = (slot + 1ull) & mask; continue; }
+        }
+        if (da) atomicAdd((unsigned long long *)t.a + slot, da);
+        if (db && t.b) atomicAdd((unsigned long long *)t.b + slot, db);
+        return;
+    }
+    atomicAdd((unsigned long long *)t.stats + 1, 1ull);
+}
+
+__global__ void sparse_organic_pairs_kernel(const int8_t *__restrict__ z, const int32_t *__restrict__ v,
+                                            const int32_t *__restrict__ sess, const int8_t *__restrict__ flags,
+                                            int train_mode, long long rows, const rg_sparse_counts co) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        if (z[r] != 0) continue;
+        if (train_mode != 0) {
+            const int f = flags[r];
+            if ((f & FLAG_FINAL_SESSION) && !(train_mode == 2 && (f & FLAG_NO_REAL_BANDIT))) continue;
+        }
+        const int vr = v[r], s = sess[r];
+        sparse_add(co, vr, vr, 1ull, 0ull);
+        for (int k = 1; k <= s; ++k) {
+            const int vj = v[r - k];
+            sparse_add(co, vr, vj, 1ull, 0ull);
+            sparse_add(co, vj, vr, 1ull, 0ull);
+        }
+    }
+}
+
+__global__ void sparse_bandit_stats_kernel(const int8_t *__restrict__ z, const int32_t *__restrict__ a,
+                                           const float *__restrict__ c, const int32_t *__restrict__ lvp,
+                                           const int8_t *__restrict__ flags, int train_mode, long long rows,
+                                           const rg_sparse_counts t) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        if (z[r] != 1) continue;
+        if (train_mode != 0) {
+            const int f = flags[r];
+            if ((f & FLAG_PHANTOM) && !(train_mode == 2 && (f & FLAG_NO_REAL_BANDIT))) continue;
+        }
+        const int ar = a[r], ix = lvp[r];
+        const unsigned long long rew = c[r] > 0.5f ? 1ull : 0ull;
+        if (ix >= 0) {
+            sparse_add(t, ix, ar, 1ull, rew);
+        } else {   // last_product_viewed still None: numpy increments the whole ROW ar (see bandit_stats_kernel)
+            atomicAdd((unsigned long long *)t.row_a + ar, 1ull);
+            if (rew) atomicAdd((unsigned long long *)t.row_b + ar, 1ull);
+        }
+    }
+}
+
+// growth: every occupied cell of `from` is added to `to` (a larger table) through the same insertion path
+__global__ void sparse_rehash_kernel(const rg_sparse_counts from, const rg_sparse_counts to) {
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < from.capacity;
+         slot += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = from.keys[slot];
+        if (key == ~0ull) continue;
+        sparse_add(to, (int)(key >> 32), (int)(key & 0xFFFFFFFFull), (unsigned long long)from.a[slot],
+                   from.b ? (unsigned long long)from.b[slot] : 0ull);
+    }
+}
+
+// Acting table from the sparse cells == numpy's argmax over the dense row (first maximum wins):
+//   kind 0  OrganicCount: the largest count of the row, lowest column among ties; a row without cells -> 0;
+//   kind 1  BanditCount: every untouched cell of row i holds the base value b_i = (rc_i + 1) / (rp_i + 2) (rc, rp = the
+//           whole-row increments; 0.5 without them).  The best touched cell wins when it beats b_i or when every cell
+//           of the row has been touched (lowest column among ties); otherwise the answer is the lowest column whose cell
+//           is not BELOW b_i -- found with a bitmap of the "below" cells among the first 64 columns (a row whose first
+//           64 cells are all below base is reported in stats[1]: it cannot be resolved here).
+__device__ __forceinline__ double sparse_value(int kind, const rg_sparse_counts &s, long long slot, int row) {
+    if (kind == 0) return (double)s.a[slot];
+    const double rp = s.row_a ? (double)s.row_a[row] : 0.0, rc = s.row_b ? (double)s.row_b[row] : 0.0;
+    return ((double)s.b[slot] + rc + 1.0) / ((double)s.a[slot] + rp + 2.0);
+}
+__global__ void sparse_policy_init_kernel(int P, unsigned long long *__restrict__ colcnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) colcnt[i] = 0xFFFFFFFF00000000ull;    // high word: best column (min), low word: touched cells (count)
+}
+__global__ void sparse_policy_best_kernel(int kind, const rg_sparse_counts s, unsigned long long *__restrict__ best,
+                                          unsigned long long *__restrict__ blocked, unsigned long long *__restrict__ colcnt) {
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < s.capacity;
+         slot += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = s.keys[slot];
+        if (key == ~0ull) continue;
+        const int row = (int)(key >> 32), col = (int)(key & 0xFFFFFFFFull);
+        const double val = sparse_value(kind, s, slot, row);
+        atomicMax(best + row, (unsigned long long)__double_as_longlong(val));   // val > 0: the bit pattern is monotone
+        atomicAdd(colcnt + row, 1ull);
+        if (kind == 1 && col < 64) {
+            const double rp = s.row_a ? (double)s.row_a[row] : 0.0, rc = s.row_b ? (double)s.row_b[row] : 0.0;
+            if (val < (rc + 1.0) / (rp + 2.0)) atomicOr(blocked + row, 1ull << col);
+        }
+    }
+}
+__global__ void sparse_policy_col_kernel(int kind, const rg_sparse_counts s, const unsigned long long *__restrict__ best,
+                                         unsigned long long *__restrict__ colcnt) {
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < s.capacity;
+         slot += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = s.keys[slot];
+        if (key == ~0ull) continue;
+        const int row = (int)(key >> 32);
+        const unsigned long long col = key & 0xFFFFFFFFull;
+        if ((unsigned long long)__double_as_longlong(sparse_value(kind, s, slot, row)) != best[row]) continue;
+        // min over the high word, the low word (count) is left untouched: CAS loop
+        unsigned long long old = colcnt[row];
+        while ((old >> 32) > col) {
+            const unsigned long long want = (col << 32) | (old & 0xFFFFFFFFull);
+            const unsigned long long got = atomicCAS(colcnt + row, old, want);
+            if (got == old) break;
+            old = got;
+        }
+    }
+}
+__global__ void sparse_policy_final_kernel(int kind, int P, const rg_sparse_counts s, const unsigned long long *__restrict__ best,
+                                           const unsigned long long *__restrict__ blocked,
+                                           const unsigned long long *__restrict__ colcnt, int32_t *__restrict__ table,
+                                           double *__restrict__ ps) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= P) return;
+    const unsigned long long cc = colcnt[row];
+    const long long touched = (long long)(cc & 0xFFFFFFFFull);
+    const int bcol = (int)(cc >> 32);
+    const double vmax = __longlong_as_double((long long)best[row]);
+    int out = 0;
+    double p = 1.0;
+    if (kind == 0) {
+        out = (touched > 0 && vmax > 0.0) ? bcol : 0;
+    } else {
+        const double rp = s.row_a ? (double)s.row_a[row] : 0.0, rc = s.row_b ? (double)s.row_b[row] : 0.0;
+        const double base = (rc + 1.0) / (rp + 2.0);
+        if (touched > 0 && (vmax > base || touched >= (long long)P)) {
+            out = bcol; p = vmax;
+        } else {
+            const unsigned long long free_cols = ~blocked[row];
+            if (free_cols == 0ull) { atomicAdd((unsigned long long *)s.stats + 1, 1ull); out = 64 < P ? 64 : P - 1; }
+            else out = __ffsll((long long)free_cols) - 1;
+            p = base;
+        }
+    }
+    table[row] = out;
+    if (ps) ps[row] = p;
 }
 
 // IPS / SNIPS of a deterministic target policy pi(a | lv) = [a == target[lv]] over the bandit rows with u < u_end
@@ -415,16 +572,45 @@ cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, lon
     return cudaGetLastError();
 }
 
-cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int32_t *co,
-                               int32_t *pulls, int32_t *clicks, int num_sms, cudaStream_t stream) {
+cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int64_t *co,
+                               int64_t *pulls, int64_t *clicks, int num_sms, cudaStream_t stream) {
     if (rows <= 0) return cudaSuccess;
-    if (co) organic_pairs_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.v, c.sess, c.flags, train_mode, rows, P, co);
+    if (co) organic_pairs_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.v, c.sess, c.flags, train_mode, rows, P,
+                                                                  (unsigned long long *)co);
     if (pulls && clicks)
-        bandit_stats_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.a, c.c, c.lvp, c.flags, train_mode, rows, P, pulls, clicks);
+        bandit_stats_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.a, c.c, c.lvp, c.flags, train_mode, rows, P,
+                                                             (unsigned long long *)pulls, (unsigned long long *)clicks);
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_argmax(int kind, int P, const int32_t *A, const int32_t *B, int32_t *table, double *ps,
+cudaError_t launch_sparse_count_stats(const rg_log_columns &c, long long rows, int train_mode, const rg_sparse_counts *co,
+                                      const rg_sparse_counts *bandit, int num_sms, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    if (co) sparse_organic_pairs_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.v, c.sess, c.flags, train_mode, rows, *co);
+    if (bandit)
+        sparse_bandit_stats_kernel<<<num_sms * 8, 256, 0, stream>>>(c.z, c.a, c.c, c.lvp, c.flags, train_mode, rows, *bandit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_rehash(const rg_sparse_counts &from, const rg_sparse_counts &to, int num_sms, cudaStream_t stream) {
+    sparse_rehash_kernel<<<num_sms * 8, 256, 0, stream>>>(from, to);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_policy(int kind, int P, const rg_sparse_counts &s, int32_t *table, double *ps,
+                                 unsigned long long *scratch, int num_sms, cudaStream_t stream) {
+    // scratch: [3 P] best value bits | blocked-column bitmap | (best column, touched cells) packed
+    unsigned long long *best = scratch, *blocked = scratch + P, *colcnt = scratch + 2 * (size_t)P;
+    cudaError_t ce = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * 2 * (size_t)P, stream);
+    if (ce != cudaSuccess) return ce;
+    sparse_policy_init_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, colcnt);
+    sparse_policy_best_kernel<<<num_sms * 8, 256, 0, stream>>>(kind, s, best, blocked, colcnt);
+    sparse_policy_col_kernel<<<num_sms * 8, 256, 0, stream>>>(kind, s, best, colcnt);
+    sparse_policy_final_kernel<<<(P + 255) / 256, 256, 0, stream>>>(kind, P, s, best, blocked, colcnt, table, ps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_argmax(int kind, int P, const int64_t *A, const int64_t *B, int32_t *table, double *ps,
                               cudaStream_t stream) {
     const long long blocks = ((long long)P * 32 + 255) / 256;
     row_argmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(kind, P, A, B, table, ps);

@@ -169,15 +169,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Waiting threads are SUSPENDED by the hardware up to this many ns per try_wait instead of re-issuing the probe: the
+// issuer / loader warps share their scheduler with an epilogue warp, and their polling cost that warp ~10 % of its issue
+// slots (r02 profile: epilogue warp 0 took 2200 cycles per tile where warp 3 took 2050, and the slowest warp paces the tile).
+constexpr unsigned kSuspendHint = 1000000u;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(kSuspendHint)
         : "memory");
 }
 // the same on a raw shared-memory address (the single-thread issuer / loader loops keep their barrier addresses in registers)
@@ -185,12 +189,24 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, unsigned parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar_saddr),
-        "r"(parity)
+        "r"(parity), "r"(kSuspendHint)
         : "memory");
+}
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_test_s(uint32_t bar_saddr, unsigned parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_saddr), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void umma_commit_s(uint32_t bar_saddr, uint32_t issue) {   // converged warp, one issuing lane
     asm volatile(
@@ -934,6 +950,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
 
             const uint32_t a_saddr = tc::smem_addr(a_tile);
             const uint32_t ring_saddr = tc::smem_addr(gtile);
+            RG_PROF_ONLY(const long long pq0 = clock64(); if (tid == 0) pf[10] += (unsigned long long)(pq0 - tk0);)
             if (warp == 4) {
                 // ---- producer / MMA issuer (one thread): B tile landed -> accumulator buffer drained -> three-term
                 // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
@@ -1053,39 +1070,66 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 int rec = 0, in_rec = 0;
                 const int tiles_per_rec = p.rec_sub * (128 / tc::TILE_N);
                 const unsigned tile_use = seq_use / (unsigned)nslab;
+                const uint32_t dfull_s = smem_u32(dfull);
+                const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+                // Software pipeline: the tcgen05.ld of the next 32 columns (of this tile, or of the next tile when its
+                // accumulator is already complete) is in flight while the 32 exponentials of the current ones issue; one
+                // warp per scheduler then keeps the MUFU pipe busy without bubbles.  Dead rows (pos >= nlive) carry zero
+                // operands: their logits are finite, their masses are computed and never used (no branch in the loop).
+                uint32_t va[32], vb[32];
+                bool have_first = false;   // chunk 0 of the coming tile is already in flight (in va)
+                constexpr int NCH = tc::TILE_N / 32;
+                static_assert(NCH % 2 == 0, "the register double buffer alternates per 32-column chunk");
                 for (int tt = 0; tt < ntile; ++tt) {
                     const unsigned gs = tile_use + (unsigned)tt;
                     const unsigned buf = gs % NBUF;
+                    const uint32_t taddr = lane_taddr + buf * (uint32_t)tc::TILE_N;
                     RG_PROF_ONLY(const long long pa = clock64();)
-                    mbar_wait(&dfull[buf], (gs / NBUF) & 1u);
+                    if (!have_first) {
+                        mbar_wait_s(dfull_s + buf * 8u, (gs / NBUF) & 1u);
+                        tc::tc_fence_after();
+                        tc::tmem_ld32_issue(taddr, va);
+                    }
                     RG_PROF_ONLY(const long long pb = clock64(); long long pld = 0;)
-                    tc::tc_fence_after();
-                    constexpr int HALF = tc::TILE_N;  // columns of this thread (the whole tile row)
-                    float *gs_out = gsum_cta + (size_t)tt * (tc::TILE_N / 32) * TU + pos;
+                    have_first = false;
+                    float *gs_out = gsum_cta + (size_t)tt * NCH * TU + pos;
 #pragma unroll
-                    for (int c = 0; c < HALF; c += 32) {
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        float v[32];
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t(&cur)[32] = (c & 1) ? vb : va;
+                        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
                         RG_PROF_ONLY(const long long pl0 = clock64();)
-                        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)tc::TILE_N +
-                                          (uint32_t)c, v);
+                        tc::tmem_ld32_wait(cur);
                         RG_PROF_ONLY(pld += clock64() - pl0;)
-                        if (c + 32 >= HALF) {  // last read of this tile: hand the accumulator back before the math
+                        if (c + 1 < NCH) {
+                            tc::tmem_ld32_issue(taddr + (uint32_t)(32 * (c + 1)), nxt);
+                        } else {
+                            // every read of this accumulator has completed: hand it back before the math, and start on
+                            // the next tile if its accumulator is ready
                             tc::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&dempty[buf]);
-                        }
-                        if (act) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]);
-                                s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
+                            if (tt + 1 < ntile) {
+                                const unsigned gn = gs + 1u, bn = gn % NBUF;
+                                int ready = 0;
+                                if (lane == 0) ready = mbar_test_s(dfull_s + bn * 8u, (gn / NBUF) & 1u) ? 1 : 0;
+                                ready = __shfl_sync(0xffffffffu, ready, 0);
+                                if (ready) {
+                                    tc::tc_fence_after();
+                                    tc::tmem_ld32_issue(lane_taddr + bn * (uint32_t)tc::TILE_N, nxt);
+                                    have_first = true;
+                                }
                             }
+                        }
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            s0 += ex2_approx(__uint_as_float(cur[i])); s1 += ex2_approx(__uint_as_float(cur[i + 1]));
+                            s2 += ex2_approx(__uint_as_float(cur[i + 2])); s3 += ex2_approx(__uint_as_float(cur[i + 3]));
                         }
                         // the masses of this 32-product group: kept (coalesced over the 32 users of the warp) so that
                         // pass 2b only has to recompute ONE group of 32 products instead of the whole record tile
                         const float cs = (s0 + s1) + (s2 + s3);
-                        gs_out[(size_t)(c / 32) * TU] = cs;
+                        if (act) gs_out[(size_t)c * TU] = cs;
                         part += cs;
                     }
                     if (++in_rec == tiles_per_rec || tt == ntile - 1) {
@@ -1098,6 +1142,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                                      if (tr_on && tt < 1000 && (q == 0 || q == 3)) { g_trace[tt * 8 + (q == 0 ? 3 : 5)] = pb; g_trace[tt * 8 + (q == 0 ? 4 : 7)] = pe; } })
                 }
             }
+            RG_PROF_ONLY(const long long pq1 = clock64(); if (tid == 0) pf[11] += (unsigned long long)(pq1 - pq0);)
             tc::tc_fence_before();
             __syncthreads();
             tc::tc_fence_after();
@@ -1105,6 +1150,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             seq_use += (unsigned)nunit;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
             __syncthreads();
+            RG_PROF_ONLY(if (tid == 0) pf[14] += (unsigned long long)(clock64() - pq1);)
         } else {
             const bool warp_active = warp * 16 < nlive;
             float sh[8], part[8];

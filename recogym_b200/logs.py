@@ -127,18 +127,33 @@ def generate_logs_device(env, n_users, policy="uniform", table=None, ps_table=No
         log = None
 
 
-class CountStats:
-    """Sufficient statistics of OrganicCount (co_counts) and BanditCount (pulls, clicks) on the GPU, int32 [P][P].
+SPARSE_MIN_PRODUCTS = 16384   # above this the [P][P] statistics (8 P^2 bytes each) give way to device hash tables
+
+
+def CountStats(P, device=0, organic=True, bandit=True, sparse=None):
+    """Sufficient statistics of OrganicCount (co_counts) and BanditCount (pulls, clicks) on the GPU: dense int64 [P][P]
+    (`DenseCountStats`) or, for large catalogues, device hash tables (`SparseCountStats`; P = 100 000 would need
+    3 x 80 GB dense).  Same interface and the same acting tables either way."""
+    if sparse is None:
+        sparse = int(P) >= SPARSE_MIN_PRODUCTS
+    cls = SparseCountStats if sparse else DenseCountStats
+    return cls(P, device, organic, bandit)
+
+
+class DenseCountStats:
+    """int64 [P][P] matrices (the reference holds float64 ones: agents/organic_count.py:49, agents/bandit_count.py:22-24).
     Holds no environment handle, so agents that own one stay deep-copyable / picklable."""
+
+    sparse = False
 
     def __init__(self, P, device=0, organic=True, bandit=True):
         torch = _torch()
         self.P = int(P)
         self.device = int(device)
         dev = torch.device("cuda", self.device)
-        self.co_counts = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if organic else None
-        self.pulls = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if bandit else None
-        self.clicks = torch.zeros((self.P, self.P), dtype=torch.int32, device=dev) if bandit else None
+        self.co_counts = torch.zeros((self.P, self.P), dtype=torch.int64, device=dev) if organic else None
+        self.pulls = torch.zeros((self.P, self.P), dtype=torch.int64, device=dev) if bandit else None
+        self.clicks = torch.zeros((self.P, self.P), dtype=torch.int64, device=dev) if bandit else None
         self.last_view = -1     # BanditCount.last_product_viewed carried from one log to the next (-1 = None)
 
     def _stream(self):
@@ -172,6 +187,165 @@ class CountStats:
     def bandit_count_policy(self):
         """BanditCount.act as a device table, 'ps' = the smoothed click rate (agents/bandit_count.py:28-47)."""
         return self._policy(1, self.pulls, self.clicks)
+
+
+class _DeviceHash:
+    """One rg_sparse_counts table: keys / a / b [capacity], whole-row increments [P], stats[2] (device tensors)."""
+
+    def __init__(self, P, capacity, device, bandit):
+        torch = _torch()
+        dev = torch.device("cuda", device)
+        self.capacity = int(capacity)
+        self.keys = torch.full((self.capacity,), -1, dtype=torch.int64, device=dev)       # 0xFF.. = empty
+        self.a = torch.zeros(self.capacity, dtype=torch.int64, device=dev)
+        self.b = torch.zeros(self.capacity, dtype=torch.int64, device=dev) if bandit else None
+        self.row_a = torch.zeros(P, dtype=torch.int64, device=dev) if bandit else None
+        self.row_b = torch.zeros(P, dtype=torch.int64, device=dev) if bandit else None
+        self.stats = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def struct(self):
+        s = L.SparseCounts()
+        s.capacity = self.capacity
+        for n in ("keys", "a", "b", "row_a", "row_b", "stats"):
+            t = getattr(self, n)
+            setattr(s, n, t.data_ptr() if t is not None else None)
+        return s
+
+    def cells(self):
+        """host dict {(row, col): (a, b)} (tests, host synchronisation of small tables)."""
+        keys = self.keys.cpu().numpy()
+        used = keys != -1
+        k = keys[used].astype(np.uint64)
+        a = self.a.cpu().numpy()[used]
+        b = self.b.cpu().numpy()[used] if self.b is not None else np.zeros_like(a)
+        return {(int(x >> np.uint64(32)), int(x & np.uint64(0xFFFFFFFF))): (int(y), int(z)) for x, y, z in zip(k, a, b)}
+
+
+class SparseCountStats:
+    """The same statistics in device hash tables (open addressing, key = row * 2^32 + col; csrc/rg_logs.cu): what the
+    count agents need at P = 100 000 (BASELINE configs[3]).  Capacity is provisioned before every train(): room for the
+    worst case of that log (one new cell per trained bandit row / per ordered pair of a session), growing the table by
+    a device re-insertion when needed, so an insertion can never find the table full."""
+
+    sparse = True
+
+    def __init__(self, P, device=0, organic=True, bandit=True):
+        self.P = int(P)
+        self.device = int(device)
+        self._want = (bool(organic), bool(bandit))
+        self.co = None
+        self.bandit = None
+        self.last_view = -1
+
+    def _stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream)
+
+    def _room(self, table, bandit, new_cells):
+        """a table with at least 2 x (occupied + new_cells) slots: allocate, or grow by re-inserting the old cells"""
+        used = int(table.stats[0].item()) if table is not None else 0
+        need = 2 * (used + int(new_cells)) + 1024
+        if table is not None and table.capacity >= need:
+            return table
+        cap = 1 << max(10, int(need - 1).bit_length())
+        new = _DeviceHash(self.P, cap, self.device, bandit)
+        if table is not None:
+            _reinsert(table, new, self._stream())
+        return new
+
+    def train(self, log):
+        torch = _torch()
+        n = int(log.rows)
+        organic, bandit = self._want
+        if organic:
+            z = log.z[:n]
+            # ordered pairs a session of length s adds: s^2 (b b^T); the sum over views of (2 sess + 1)
+            pairs = int((2 * log.sess[:n].long() + 1)[z == 0].sum().item()) if n else 0
+            self.co = self._room(self.co, False, pairs)
+        if bandit:
+            self.bandit = self._room(self.bandit, True, n)
+        cols = log.struct()
+        co_s = self.co.struct() if organic else None
+        ba_s = self.bandit.struct() if bandit else None
+        L.check(L.lib().rg_sparse_count_stats_device(C.byref(cols), n, int(log.train_mode),
+                                                     C.byref(co_s) if co_s is not None else None,
+                                                     C.byref(ba_s) if ba_s is not None else None, self._stream()))
+        for t in (self.co, self.bandit):
+            if t is not None and int(t.stats[1].item()) != 0:
+                raise RuntimeError("sparse count statistics: hash table overflow (capacity %d)" % t.capacity)
+        self.last_view = int(log.carry.item())
+
+    def _policy(self, kind, table_obj):
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        table = torch.zeros(self.P, dtype=torch.int32, device=dev)
+        ps = torch.full((self.P,), 1.0 if kind == 0 else 0.5, dtype=torch.float64, device=dev)
+        if table_obj is not None:
+            st = table_obj.struct()
+            L.check(L.lib().rg_sparse_count_policy_device(kind, self.P, C.byref(st), C.c_void_p(table.data_ptr()),
+                                                          C.c_void_p(ps.data_ptr()), self._stream()))
+            if int(table_obj.stats[1].item()) != 0:
+                raise RuntimeError("sparse count policy: a row whose first 64 cells are all below its base value")
+        return {"policy": "table", "table": table, "ps_table": ps}
+
+    def organic_count_policy(self):
+        return self._policy(0, self.co)
+
+    def bandit_count_policy(self):
+        return self._policy(1, self.bandit)
+
+    # ---- host <-> device (agents/_sparse.py HostSparseCounts) --------------------------------------------------------
+    def load_host(self, co_host, bandit_host):
+        """statistics an agent accumulated on the host (facade training) -> device tables"""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        for host, is_bandit in ((co_host, False), (bandit_host, True)):
+            if host is None:
+                continue
+            keys, a, b = host.arrays()
+            # an un-hashed staging table (re-insertion only walks its slots), then the real one
+            cap = 1 << max(10, int(max(len(keys), 1) - 1).bit_length())
+            stage = _DeviceHash(self.P, cap, self.device, is_bandit)
+            n = len(keys)
+            stage.keys[:n] = torch.as_tensor(keys.view(np.int64), device=dev)
+            stage.a[:n] = torch.as_tensor(a, device=dev)
+            if is_bandit:
+                stage.b[:n] = torch.as_tensor(b, device=dev)
+                for i, v in host.row_a.items():
+                    stage.row_a[i] = v
+                for i, v in host.row_b.items():
+                    stage.row_b[i] = v
+            stage.stats[0] = n
+            table = _DeviceHash(self.P, 1 << max(10, int(2 * n + 1023).bit_length()), self.device, is_bandit)
+            _reinsert(stage, table, self._stream())
+            if is_bandit:
+                self.bandit = table
+            else:
+                self.co = table
+
+    def to_host(self):
+        """-> (HostSparseCounts of co_counts or None, HostSparseCounts of pulls/clicks or None)"""
+        from .agents._sparse import HostSparseCounts
+        co = HostSparseCounts.from_cells(self.P, self.co.cells()) if self.co is not None else (
+            HostSparseCounts(self.P) if self._want[0] else None)
+        ba = None
+        if self.bandit is not None:
+            ba = HostSparseCounts.from_cells(self.P, self.bandit.cells(), self.bandit.row_a.cpu().numpy(),
+                                             self.bandit.row_b.cpu().numpy())
+        elif self._want[1]:
+            ba = HostSparseCounts(self.P)
+        return co, ba
+
+
+def _reinsert(old, new, stream):
+    """growth of a hash table: one kernel adds every occupied cell of `old` to `new` through the device insertion path"""
+    so, sn = old.struct(), new.struct()
+    L.check(L.lib().rg_sparse_rehash_device(C.byref(so), C.byref(sn), stream))
+    if old.row_a is not None:
+        new.row_a.copy_(old.row_a)
+        new.row_b.copy_(old.row_b)
+    if int(new.stats[0].item()) != int(old.stats[0].item()) or int(new.stats[1].item()) != 0:
+        raise RuntimeError("sparse count statistics: growth lost cells")
 
 
 def ips_table_policy(log, target_table, u_end=None):

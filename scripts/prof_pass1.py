@@ -64,6 +64,8 @@ def main():
         out["loader_per_unit"] = {"wait_sfree_plus_issue": ld[4] / max(ld[5], 1.0), "units": ld[5]}
         out["epilogue_per_tile_per_warp"] = {"wait_dfull": ep[6] / ntile_e, "tmem_ld": ep[7] / ntile_e,
                                              "tile_total_after_dfull": ep[8] / ntile_e, "tiles_x_warps": ep[9]}
+        out["pass1_thread0_per_round"] = {"a_tile_build_and_sync": ep[10] / max(ep[13], 1.0), "tile_loop": ep[11] / max(ep[13], 1.0),
+                                          "tail_sync_and_omega_tile": ep[14] / max(ep[13], 1.0)}
         out["rounds"] = ep[13]
         out["mean_live_per_round"] = ep[12] / max(ep[13], 1.0)
         t = np.array(list(trace), dtype=np.int64).reshape(-1, 8)

@@ -237,3 +237,93 @@ def test_test_agent_device_training_equals_facade_training():
         dev = rg.test_agent(copy.deepcopy(env), copy.deepcopy(agent), 40, 3000, 6)
         host = rg.test_agent(copy.deepcopy(env), copy.deepcopy(agent), 40, 3000, 6, device_training=False)
         assert dev == host, ctor.__name__
+
+
+def _sparse_oracle_cells(T, P, cols, n_org, mode=0, lpv=None):
+    co, pulls, clicks, rp, rc, out_lpv = T.sparse_count_stats(P, cols, n_org, last_product_viewed=lpv, mode=mode)
+    return co, {k: (pulls[k], clicks.get(k, 0)) for k in pulls}, rp, rc, out_lpv
+
+
+def test_sparse_count_stats_equal_dense_and_reference(oracle):
+    """Device hash-table statistics (SparseCountStats) on the reference golden: cells == the dense matrices the
+    reference's own agents hold, acting tables and 'ps' == numpy's argmax over them, growth by re-insertion keeps
+    every cell, and a second log continues the statistics."""
+    from oracle import train_oracle as T
+    from recogym_b200.logs import CountStats, generate_logs_device
+    g = load_golden(CASE)
+    de = device_env_from_golden(g)
+    P = de.P
+    log = generate_logs_device(de, int(g["n_users"]), "uniform", None, None, 0, int(g["n_organic_users"]), 2)
+    st = CountStats(P, sparse=True)
+    assert st.sparse
+    st.train(log)
+    co = st.co.cells()
+    dense_co = np.zeros((P, P)); dense_p = np.zeros((P, P)); dense_c = np.zeros((P, P))
+    for (i, j), (a, _) in co.items():
+        dense_co[i, j] = a
+    ra, rb = st.bandit.row_a.cpu().numpy(), st.bandit.row_b.cpu().numpy()
+    for (i, j), (a, b) in st.bandit.cells().items():
+        dense_p[i, j] = a; dense_c[i, j] = b
+    dense_p += ra[:, None]; dense_c += rb[:, None]         # whole-row increments (last_product_viewed None)
+    assert np.array_equal(dense_co, g["co_counts"]) and np.array_equal(dense_p, g["pulls_a"])
+    assert np.array_equal(dense_c, g["clicks_a"]) and st.last_view == int(g["bandit_lpv"])
+    assert ra.sum() > 0                                    # the golden exercises the None-row quirk
+    oc, bc = st.organic_count_policy(), st.bandit_count_policy()
+    assert np.array_equal(oc["table"].cpu().numpy(), g["co_counts"].argmax(axis=1))
+    assert np.array_equal(bc["table"].cpu().numpy(), g["ctr"].argmax(axis=1))
+    assert np.array_equal(bc["ps_table"].cpu().numpy(), g["ctr"].max(axis=1))
+    cap0 = st.bandit.capacity
+    # many more users: the tables grow (device re-insertion) and rows fill up completely (every cell touched)
+    log2 = generate_logs_device(de, 3000, "uniform", None, None, 44, 0, 1, prev_last_view=st.last_view)
+    st.train(log2)
+    assert st.bandit.capacity > cap0
+    dn = CountStats(P, sparse=False)
+    dn.train(log); dn.last_view = int(g["bandit_lpv"]); dn.train(log2)
+    for a, b in ((st.organic_count_policy(), dn.organic_count_policy()), (st.bandit_count_policy(), dn.bandit_count_policy())):
+        assert np.array_equal(a["table"].cpu().numpy(), b["table"].cpu().numpy())
+        assert np.array_equal(a["ps_table"].cpu().numpy(), b["ps_table"].cpu().numpy())
+    assert st.last_view == dn.last_view
+    de.close()
+
+
+def test_sparse_bandit_count_at_catalogue_scale(oracle):
+    """BASELINE configs[3] catalogue size (P = 100 000; dense statistics would be 3 x 80 GB): BanditCount and OrganicCount
+    trained on the device == the oracle's dict-of-keys restatement of the reference's train calls on the same log;
+    test_agent runs end to end with the package-level agent."""
+    import recogym_b200 as rg
+    from oracle import train_oracle as T
+    from recogym_b200.logs import generate_logs_device
+    P, K = 100000, 4
+    oe, de = both_envs(P, K, 31)
+    n, n_org = 400, 5
+    ro = oracle.rollout(oe, 0, n, n_organic_users=n_org, log=True, threads=16)["log"]
+    bc = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": P}))
+    oc = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
+    assert bc.pulls_a is None and oc.co_counts is None          # nothing dense was allocated
+    log = generate_logs_device(de, n, "uniform", None, None, 0, n_org, 2)
+    for k in "utzvac":
+        assert np.array_equal(log.to_host()[k].astype(np.int64), ro[k].astype(np.int64)), k
+    bc.device_train(log); oc.device_train(log)
+    co, cells, rp, rc, lpv = _sparse_oracle_cells(T, P, ro, n_org)
+    assert bc._stats.bandit.cells() == cells and {k: v[0] for k, v in oc._stats.co.cells().items()} == co
+    assert bc.device_last_view() == lpv
+    tb, psb = T.sparse_bandit_count_table(P, {k: v[0] for k, v in cells.items()}, {k: v[1] for k, v in cells.items()}, rp, rc)
+    pol = bc.device_policy()
+    assert np.array_equal(pol["table"].cpu().numpy(), tb) and np.array_equal(pol["ps_table"].cpu().numpy(), psb)
+    assert np.array_equal(oc.device_policy()["table"].cpu().numpy(), T.sparse_organic_count_table(P, co))
+    # host synchronisation: the facade-side agent acts like the table
+    bc.sync_host(); oc.sync_host()
+    t2, ps2 = bc._sp.bandit_table()
+    assert np.array_equal(t2, tb) and np.array_equal(ps2, psb) and np.array_equal(oc._sp.organic_table(), T.sparse_organic_count_table(P, co))
+    # and back to the device (facade-trained statistics continue on the GPU)
+    log2 = generate_logs_device(de, 100, "uniform", None, None, n + n_org, 0, 2, prev_last_view=bc.device_last_view())
+    bc.device_train(log2)
+    both = {k: np.concatenate([ro[k], log2.to_host()[k]]) for k in "utzvac"}
+    _, cells2, rp2, rc2, _ = _sparse_oracle_cells(T, P, both, n_org)
+    assert bc._stats.bandit.cells() == cells2
+    de.close()
+    env = rg.make("reco-gym-v1")
+    env.init_gym({**rg.env_1_args, "random_seed": 31, "num_products": P, "K": K})
+    q = rg.test_agent(env, rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": P})),
+                      300, 2000, 10)
+    assert 0.0 < q[1] < q[0] < q[2] < 0.1

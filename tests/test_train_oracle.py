@@ -144,3 +144,27 @@ def test_host_ips_snips_estimators_match_reference():
     m = g["ipslog_u"][g["ipslog_z"] == 1]
     nrow = int(((m < 5)).sum())                                  # users 0..4: the last user of the sub-log is left out
     assert np.array_equal(r2, g["ips_rewards"][:nrow]) and np.array_equal(q2, g["ips_p_ratio"][:nrow])
+
+
+def test_sparse_count_statistics_equal_dense(oracle):
+    from oracle import train_oracle as T
+    """oracle/train_oracle.py's dict-of-keys statistics (the checker of the device hash-table statistics used at
+    P = 100 000, where P x P does not exist) == the dense restatement that is pinned to the reference's agents:
+    acting tables, 'ps' values and the carried last view, for all three training loops, including rows in which every
+    cell was touched and the whole-row increments made while last_product_viewed is None."""
+    import recogym_b200 as rg
+    from recogym_b200.envs.static_params import draw_static_params
+    for P, K, seed, n, no in ((12, 3, 5, 300, 4), (60, 8, 7, 300, 0), (7, 2, 1, 500, 3), (200, 4, 9, 80, 2)):
+        cfg = rg.Configuration({**rg.env_1_args, "num_products": P, "K": K, "random_seed": seed})
+        sp = draw_static_params(cfg)
+        oe = oracle.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                              1, 0.1, seed)
+        log = oracle.rollout(oe, 0, n, n_organic_users=no, log=True)["log"]
+        for mode in (0, 1, 2):
+            co, pu, cl, lpv = T.count_stats(P, log, no, mode=mode)
+            sco, spu, scl, rp, rc, slpv = T.sparse_count_stats(P, log, no, mode=mode)
+            assert slpv == lpv
+            assert np.array_equal(T.sparse_organic_count_table(P, sco), T.organic_count_table(co))
+            tb, psb = T.sparse_bandit_count_table(P, spu, scl, rp, rc)
+            tb_d, ps_d = T.bandit_count_table(pu, cl)
+            assert np.array_equal(tb, tb_d) and np.array_equal(psb, ps_d)
