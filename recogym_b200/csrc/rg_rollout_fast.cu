@@ -26,6 +26,7 @@
 //           (longest-first schedule for large launches); omega updates are batched over the CTA.
 //
 // All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
+#include <cstdio>
 #include <cstdlib>
 
 #include "rg_device.cuh"
@@ -67,7 +68,7 @@ struct Params {
     const int32_t *perm;    // longest-first schedule: ticket q -> user index perm[q] (nullptr: identity)
     int nstage, rec_sub, nrec, nrec_pad, kp, ncs;
     int tc;                 // 1: tensor-core pass 1 (RG_MATH_TENSOR)
-    int async2;             // tc: tier 2/3 re-sampling runs on warps 5-7 underneath the next round's pass 1
+    int nhalf;              // partial sums per record tile and user: 2 in tensor mode (one per column half), else 1
     double *om_scratch;     // tc (or spill >= 2): the binary64 omega rows live in global memory, [grid][TU][kp]
     double *csum_scratch;   // spill >= 1: partial sums of the re-sampling sweeps in global memory, [grid][ncs * FB * 2]
     int spill;              // CUDA-core form, large P x K: 0 all in shared memory, 1 csum global, 2 csum + omega global
@@ -85,9 +86,9 @@ __host__ inline void make_layout(Params &p) {
     tc::kt_slabs(K, &KC, &KCs, &nslab);
     const int tc_tile_bytes = 2 * KCs * tc::CHUNK_BYTES_B;  // one K slab of a B tile (hi + lo): the ring unit
     const int tc_a_bytes = 2 * KC * tc::CHUNK_BYTES;       // the 128-user A tile (hi + lo)
-    L.mbar = o; o += 8 * (2 * kMaxStages + 2 * NBUF + 1);  // ring full / ring free, NBUF TMEM-full, NBUF TMEM-empty, TMEM address
+    L.mbar = o; o += 8 * (kMaxStages + 2 * NBUF + 1);  // ring full, NBUF TMEM-full, NBUF TMEM-empty, TMEM address
     L.om64 = o; if (!p.tc && p.spill < 2) o += 8 * TU * p.kp;
-    L.csum = o; if ((!p.tc || p.async2) && p.spill < 1) o += 8 * p.ncs * FB * 2;
+    L.csum = o; if (!p.tc && p.spill < 1) o += 8 * p.ncs * FB * 2;
     L.fb_u = o; o += 8 * FB;
     L.fb_lse = o; o += 8 * FB;
     L.fb_om = o; o += 8 * FB * p.kp;
@@ -137,12 +138,12 @@ __host__ inline void make_layout(Params &p) {
         // the partial sums of the re-sampling sweeps live in the same bytes
         int ring = p.nstage * tc_tile_bytes;
         const int om32_bytes = align_up(4 * K1 * TU, 16);
-        const int alias = om32_bytes + 5 * 8 * TU + (p.async2 ? 0 : 8 * p.ncs * FB * 2);
+        const int alias = om32_bytes + 5 * 8 * TU + 8 * p.ncs * FB * 2;
         if (alias > ring) ring = align_up(alias, 128);
         L.om32 = o;
         L.lse = o + om32_bytes;
         L.pz = L.lse + 8 * TU; L.pu = L.pz + 8 * TU; L.ptau = L.pu + 8 * TU; L.pcum = L.ptau + 8 * TU;
-        if (!p.async2) L.csum = L.pcum + 8 * TU;
+        L.csum = L.pcum + 8 * TU;
         o += ring;
         L.atile = o; o += tc_a_bytes;
     }
@@ -172,7 +173,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Waiting threads are SUSPENDED by the hardware up to this many ns per try_wait instead of re-issuing the probe: the
 // issuer / loader warps share their scheduler with an epilogue warp, and their polling cost that warp ~10 % of its issue
 // slots (r02 profile: epilogue warp 0 took 2200 cycles per tile where warp 3 took 2050, and the slowest warp paces the tile).
-constexpr unsigned kSuspendHint = 1000000u;
+#ifndef RG_SUSPEND_NS
+#define RG_SUSPEND_NS 1000000
+#endif
+constexpr unsigned kSuspendHint = RG_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -215,6 +219,10 @@ __device__ __forceinline__ void umma_commit_s(uint32_t bar_saddr, uint32_t issue
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_saddr), "r"(issue)
         : "memory");
 }
+// Barrier of the NT compute threads (named barrier 1).  The tensor-mode kernel carries a ninth warp -- the MMA issuer --
+// that never takes part in it; barrier 2 (NT + 32 threads) releases that warp into a round's pass 1.
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void issuer_sync() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -418,7 +426,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
     const int K = env.K, P = env.P, Ppad = env.Ppad;
     const int lane = tid & 31, warp = tid >> 5, nwarps = gn >> 5;
     auto gsync = [&]() {
-        if (bar_id == 0) __syncthreads();
+        if (bar_id == 0) cta_sync();
         else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gn) : "memory");
     };
     double *esum = csum + (size_t)FB * ncs;
@@ -668,9 +676,10 @@ __global__ void lpt_scatter_kernel(const unsigned char *__restrict__ est, long l
 }
 
 template <bool TC>
-__global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
-    // TC pass 1: warps 0-3 run the epilogue (thread = TMEM lane = user), warp 4 is the TMA producer / MMA issuer,
-    // warps 5-7 idle (288 threads would cap the kernel at 96 registers)
+__device__ __forceinline__ void rollout_cta_body(const Params &p) {
+    // NT compute threads (8 warps).  TC: a ninth warp is the MMA issuer of pass 1; warps 0-7 run the epilogue (thread =
+    // TMEM lane = user; warps w and w+4 share a lane quarter and take one column half of every accumulator tile each, so
+    // that every scheduler has two warps feeding the MUFU pipe), warp 0 also refills the B ring.
     constexpr int NTH = NT, NWARP = NTH / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const EnvDev &env = p.env;
@@ -732,9 +741,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     float *tilesum = (float *)(smem + L.tilesum);
     float *gtile = (float *)(smem + L.gtile);
     float *a_tile = (float *)(smem + L.atile);
-    uint64_t *sfree = mbar + kMaxStages;                   // TC: the UMMAs that read this ring stage have completed
-    uint64_t *dfull = mbar + 2 * kMaxStages;               // TC: accumulator tile ready, one per TMEM buffer
-    uint64_t *dempty = dfull + NBUF;                       // TC: accumulator tile drained by the 4 epilogue warps
+    uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
+    uint64_t *dempty = dfull + NBUF;                       // TC: accumulator tile drained by the 4 epilogue warps that read it
     uint32_t *tmem_slot = (uint32_t *)(dempty + NBUF);
     const int KC = env.KC, KCs = env.KCs, nslab = env.nslab;
     const unsigned tc_tile_bytes = 2u * (unsigned)KCs * tc::CHUNK_BYTES_B;   // one K slab of a B tile
@@ -744,12 +752,64 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     const int ntile = TC ? nsub * (128 / tc::TILE_N) : nsub;  // product tiles per round
     const int nunit = TC ? ntile * nslab : nsub;               // ring units streamed per round (TC: K slabs of tiles)
 
+    if constexpr (TC) {
+        if (warp == NWARP) {
+            // ---- MMA issuer (ninth warp; converged, warp-uniform values, one elected lane issues).  Per ring unit (K
+            // slab of a product tile): B slab landed -> accumulator buffer drained (first slab of a tile) -> three-term
+            // MMA -> commit "accumulator ready" after the last slab.  Every scalar instruction of this loop is on the
+            // critical path of pass 1: ring stage, accumulator buffer and their phase bits are carried incrementally,
+            // descriptors are additions to a precomputed low word, the MMA sequence is unrolled for the slab size.
+            issuer_sync();   // set-up done
+            tc::tc_fence_after();
+            const uint32_t tmem_u = *(volatile uint32_t *)tmem_slot;
+            const uint32_t mbar_s = smem_u32(mbar), dfull_s = smem_u32(dfull), dempty_s = smem_u32(dempty);
+            const uint32_t a_lo0 = tc::umma_desc_lo(tc::smem_addr(a_tile), tc::CHUNK_BYTES);
+            const uint32_t b_lo0 = tc::umma_desc_lo(tc::smem_addr(gtile), tc::CHUNK_BYTES_B);
+            const uint32_t a_term16 = (uint32_t)KC * tc::CHUNK_BYTES / 16u, a_slab16 = (uint32_t)KCs * tc::CHUNK_BYTES / 16u;
+            const uint32_t b_stage16 = tile_bytes / 16u;
+            const uint32_t el = tc::elect_one();
+            unsigned st = 0u, stph = 0u, buf = 0u, use = 0u;   // carried across rounds (nunit units per round)
+            RG_PROF_ONLY(unsigned long long pf[4] = {0ull, 0ull, 0ull, 0ull}; int round_no = 0;)
+            for (;;) {
+                RG_PROF_ONLY(++round_no; const bool tr_on = blockIdx.x == 0 && round_no == 30;)
+                issuer_sync();   // a round's A tile is complete, or the launch is over
+                if (*(volatile int *)&misc[9]) break;
+                tc::tc_fence_after();
+                int sl = 0;
+                for (int uu = 0; uu < nunit; ++uu) {
+                    RG_PROF_ONLY(const long long pa = clock64();)
+                    mbar_wait_s(mbar_s + st * 8u, stph);
+                    RG_PROF_ONLY(const long long pb = clock64();)
+                    if (sl == 0 && use > 0) mbar_wait_s(dempty_s + buf * 8u, (use - 1u) & 1u);
+                    RG_PROF_ONLY(const long long pc = clock64();)
+                    tc::tc_fence_after();
+                    const uint32_t td = tmem_u + buf * (uint32_t)tc::TILE_N;
+                    const uint32_t a_lo = a_lo0 + (uint32_t)sl * a_slab16, b_lo = b_lo0 + st * b_stage16;
+                    const uint32_t accf = sl > 0 ? 1u : 0u;
+                    switch (KCs) {
+                        case 2: tc::issue_slab_mmas_lean<2>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        case 4: tc::issue_slab_mmas_lean<4>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        case 6: tc::issue_slab_mmas_lean<6>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        default: tc::issue_slab_mmas_lean<8>(td, a_lo, a_term16, b_lo, accf, el); break;
+                    }
+                    if (sl == nslab - 1) umma_commit_s(dfull_s + buf * 8u, el);   // the accumulator tile is complete
+                    RG_PROF_ONLY(const long long pd = clock64(); pf[0] += pd - pc; pf[1] += pc - pb; pf[2] += pb - pa; pf[3] += 1ull;
+                                 if (tr_on && uu < 1000 && lane == 0) { g_trace[uu * 8 + 0] = pb; g_trace[uu * 8 + 1] = pc; g_trace[uu * 8 + 2] = pd; })
+                    if (++st == (unsigned)nstage) { st = 0u; stph ^= 1u; }
+                    if (++sl == nslab) { sl = 0; if (++buf == NBUF) { buf = 0u; ++use; } }
+                }
+            }
+            RG_PROF_ONLY(if (lane == 0) { atomicAdd(&g_prof[16], pf[2]); atomicAdd(&g_prof[17], pf[1]); atomicAdd(&g_prof[18], pf[0]); atomicAdd(&g_prof[19], pf[3]); })
+            return;
+        }
+    }
     // ---- set-up: barriers, first claims, first tile loads
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&mbar[s], 1); if (TC) mbar_init(&sfree[s], 1); }
-        if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], 4); }
+        for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+        if (TC) for (int b = 0; b < NBUF; ++b) { mbar_init(&dfull[b], 1); mbar_init(&dempty[b], NWARP / 2); }
         fence_barrier_init();
         misc[1] = 0;
+        misc[9] = 0;   // TC: 1 = the launch is over (read by the issuer warp after barrier 2)
     }
     if (TC && warp == 0) tc::tmem_alloc(tmem_slot, 256);  // NBUF accumulator tiles of TILE_N columns
     unsigned long long tot_users = 0, tot_events = 0, tot_org = 0, tot_ban = 0, tot_clk = 0, tot_ph = 0;
@@ -757,6 +817,14 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     unsigned long long ph_a = 0, ph_b = 0, ph_c = 0, ph_c2 = 0, ph_d = 0, ph_o = 0;
     unsigned ambig64 = 0;
 
+    // RG_PROF: sub-phase cycle counters of thread 0 (g_prof[48..]); a shared-memory read orders the clock read behind the
+    // release of the preceding barrier (a bare clock read after bar.sync captures the barrier's ISSUE time)
+    RG_PROF_ONLY(unsigned long long pf2[12]; for (int i = 0; i < 12; ++i) pf2[i] = 0ull; long long pm_last = clock64();)
+#ifdef RG_PROF
+#define RG_MARK(idx) do { if (tid == 0) { (void)*(volatile int *)misc; const long long pm_now = clock64(); pf2[idx] += (unsigned long long)(pm_now - pm_last); pm_last = pm_now; } } while (0)
+#else
+#define RG_MARK(idx) do { } while (0)
+#endif
     auto claim = [&](int slot) -> bool {  // next user id from the global queue -> reset()
         const unsigned long long q = atomicAdd(p.queue, 1ull);
         if (q >= (unsigned long long)p.n_total) {
@@ -789,7 +857,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
             if (lane == 0) misc[3] = base;
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(8);   // omega: list of pending slots
         const int npend = misc[3], npairs = (K + 1) / 2;
         for (int task = tid; task < npend * npairs; task += NTH) {
             const int slot = pend_list[task / npairs], j = task - (task / npairs) * npairs;
@@ -804,15 +873,15 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 om[2 * j + 1] = (init ? 0.0 : om[2 * j + 1]) + scale * z1;
             }
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(9);   // omega: normals + updates
         if (tid < TU) s_pend[tid] = 0;
     };
     if (tid < TU) { s_pend[tid] = 0; s_wait[tid] = 0; claim(tid); }
     if (tid == 0) { misc[6] = 0; misc[4] = 0; }
-    const bool ASYNC = TC && p.async2 != 0;
-    __syncthreads();
+    cta_sync();
     omega_phase();
-    __syncthreads();
+    cta_sync();
 
     unsigned seq_use = 0;   // sequence number of the next ring unit to consume (same in every thread)
     auto issue_load = [&](unsigned seq) {  // thread 0 only: unit (seq % nunit) -> ring stage (seq % nstage)
@@ -835,7 +904,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     uint32_t tmem_base = 0;
     if (TC) {
         tc::tc_fence_before();
-        __syncthreads();
+        issuer_sync();     // barriers initialised, TMEM allocated: the issuer warp may read the TMEM address
         tc::tc_fence_after();
         tmem_base = *tmem_slot;
     }
@@ -859,12 +928,19 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
             if (lane == 0) misc[0] = base;
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(0);   // A: compaction (+ whatever was left of the previous round's last barrier)
         const int nlive = misc[0];
         RG_PROF_ONLY(if (tid == 0) { pf[12] += (unsigned long long)nlive; pf[13] += 1ull; })
         const int nq = misc[6];  // draws waiting for a re-sampling sweep (tier 2) ...
         const int nq3 = misc[4]; // ... and for a tier-3 sweep
-        if (nlive == 0 && nq == 0 && nq3 == 0) break;
+        if (nlive == 0 && nq == 0 && nq3 == 0) {
+            if (TC) {   // release the issuer warp into its exit
+                if (tid == 0) misc[9] = 1;
+                issuer_sync();
+            }
+            break;
+        }
 
         // fp32 operand tile [K+1][TU] (row K = 1 multiplies the mu row of the Gamma tile), per-user shift and
         // error bound.  Dead positions get zeros.  (TC: the fp32 tile is only needed by pass 2 and shares its
@@ -909,8 +985,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             s_shift[tid] = sh;
             s_eps[tid] = ep;
         }
-        __syncthreads();
+        cta_sync();
 
+        RG_MARK(1);   // A: logit bounds, shifts
         { const long long tk1 = clock64(); ph_a += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- B: pass 1, dense contraction + exponentials + per-record-tile partial sums
         if constexpr (TC) {
@@ -945,211 +1022,95 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             }
             tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core
             tc::tc_fence_before();
-            __syncthreads();
+            issuer_sync();            // the A tile is complete: the issuer warp starts this round's MMAs
             tc::tc_fence_after();
-
-            const uint32_t a_saddr = tc::smem_addr(a_tile);
-            const uint32_t ring_saddr = tc::smem_addr(gtile);
             RG_PROF_ONLY(const long long pq0 = clock64(); if (tid == 0) pf[10] += (unsigned long long)(pq0 - tk0);)
-            if (warp == 4) {
-                // ---- producer / MMA issuer (one thread): B tile landed -> accumulator buffer drained -> three-term
-                // MMA -> commit (accumulator ready).  The ring stage of tile gs-1 is refilled as soon as its MMA
-                // has completed, i.e. independently of the epilogue.
-                {   // the whole warp runs the loop (converged, warp-uniform values); one elected lane issues
-                    // Every scalar instruction of this loop is on the critical path of pass 1 (r02 profile: 650 cycles of
-                    // index arithmetic + 1170 of descriptor building per tile against 576 of tensor time): ring stage,
-                    // accumulator buffer and their phase bits are carried incrementally, descriptors are additions to
-                    // a precomputed low word, the MMA sequence is unrolled at compile time for the slab size.
-                    unsigned st = seq_use % (unsigned)nstage, stph = (seq_use / (unsigned)nstage) & 1u;
-                    const unsigned tile_use = seq_use / (unsigned)nslab;   // accumulator tiles consumed so far
-                    unsigned buf = tile_use % NBUF, use = tile_use / NBUF;
-                    int sl = 0;
-                    const uint32_t mbar_s = smem_u32(mbar), sfree_s = smem_u32(sfree), dfull_s = smem_u32(dfull),
-                                   dempty_s = smem_u32(dempty);
-                    const uint32_t a_lo0 = tc::umma_desc_lo(a_saddr, tc::CHUNK_BYTES);
-                    const uint32_t b_lo0 = tc::umma_desc_lo(ring_saddr, tc::CHUNK_BYTES_B);
-                    const uint32_t a_term16 = (uint32_t)KC * tc::CHUNK_BYTES / 16u, a_slab16 = (uint32_t)KCs * tc::CHUNK_BYTES / 16u;
-                    const uint32_t b_stage16 = tile_bytes / 16u;
-                    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-                    const uint32_t el = tc::elect_one();
-                    for (int uu = 0; uu < nunit; ++uu) {   // ring units: K slab sl of a product tile
-                        RG_PROF_ONLY(const long long pa = clock64();)
-                        mbar_wait_s(mbar_s + st * 8u, stph);
-                        RG_PROF_ONLY(const long long pb = clock64();)
-                        if (sl == 0 && use > 0) mbar_wait_s(dempty_s + buf * 8u, (use - 1u) & 1u);
-                        RG_PROF_ONLY(const long long pc = clock64();)
-                        tc::tc_fence_after();
-                        const uint32_t td = tmem_u + buf * (uint32_t)tc::TILE_N;
-                        const uint32_t a_lo = a_lo0 + (uint32_t)sl * a_slab16, b_lo = b_lo0 + st * b_stage16;
-                        const uint32_t accf = sl > 0 ? 1u : 0u;
-                        switch (KCs) {
-                            case 2: tc::issue_slab_mmas_lean<2>(td, a_lo, a_term16, b_lo, accf, el); break;
-                            case 4: tc::issue_slab_mmas_lean<4>(td, a_lo, a_term16, b_lo, accf, el); break;
-                            case 6: tc::issue_slab_mmas_lean<6>(td, a_lo, a_term16, b_lo, accf, el); break;
-                            default: tc::issue_slab_mmas_lean<8>(td, a_lo, a_term16, b_lo, accf, el); break;
-                        }
-                        umma_commit_s(sfree_s + st * 8u, el);                        // this ring stage may be refilled ...
-                        if (sl == nslab - 1) umma_commit_s(dfull_s + buf * 8u, el);  // ... and the accumulator tile is complete
-                        RG_PROF_ONLY(const long long pd = clock64(); pf[0] += pb - pa; pf[1] += pc - pb; pf[2] += pd - pc; pf[3] += 1ull;
-                                     if (tr_on && uu < 1000 && lane == 0) { g_trace[uu * 8 + 0] = pb; g_trace[uu * 8 + 1] = pc; g_trace[uu * 8 + 2] = pd; })
-                        if (ASYNC && lane == 0 && uu > 0 && uu - 1 + nstage < nunit) {   // (ASYNC: no free warp for the loader)
-                            const unsigned gp = seq_use + (unsigned)uu - 1u;
-                            mbar_wait(&sfree[gp % (unsigned)nstage], (gp / (unsigned)nstage) & 1u);
-                            issue_load(gp + (unsigned)nstage);
-                        }
-                        if (ASYNC) __syncwarp();
-                        if (++st == (unsigned)nstage) { st = 0u; stph ^= 1u; }
-                        if (++sl == nslab) { sl = 0; if (++buf == NBUF) { buf = 0u; ++use; } }
-                    }
-                }
-                __syncwarp();
-            } else if (warp == 5 && !ASYNC) {
-                // ---- loader (one thread): refills a ring stage the moment the UMMAs that read it have completed.
-                // Decoupled from the MMA issuer: that thread is blocked on "B tile landed" most of the time, and a
-                // refill issued from there would start a full TMA latency late.  sfree[stage] flips once per use of
-                // the stage and the next use needs this thread's load, so a phase can never be missed.
-                if (lane == 0) {
-                    // seq_use is a multiple of nunit, so ring unit uu + nstage of this round goes into the stage unit uu used
-                    unsigned st = seq_use % (unsigned)nstage, stph = (seq_use / (unsigned)nstage) & 1u;
-                    const uint32_t mbar_s = smem_u32(mbar), sfree_s = smem_u32(sfree);
-                    const unsigned char *src = (const unsigned char *)env.GTC + (size_t)nstage * tile_bytes;
-                    for (int uu = 0; uu + nstage < nunit; ++uu) {
-                        RG_PROF_ONLY(const long long pa = clock64();)
-                        mbar_wait_s(sfree_s + st * 8u, stph);
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s + st * 8u), "r"(tile_bytes) : "memory");
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                         ring_saddr + st * tile_bytes), "l"(src), "r"(tile_bytes), "r"(mbar_s + st * 8u) : "memory");
-                        src += tile_bytes;
-                        RG_PROF_ONLY(const long long pb = clock64(); pf[4] += pb - pa; pf[5] += 1ull;
-                                     if (tr_on && uu < 1000) g_trace[uu * 8 + 6] = pb;)
-                        if (++st == (unsigned)nstage) { st = 0u; stph ^= 1u; }
-                    }
-                }
-                __syncwarp();
-            } else if (warp >= 5) {
-                // ---- re-sampling warps: the draws queued in the previous round, tier 2 then tier 3, on the
-                // (otherwise idle) FP64 pipe while warps 0-4 stream the contraction of this round
-                if (ASYNC) {
-                    const int gtid = tid - 5 * 32, gn = 3 * 32;
-                    const int *qs = rq_slot;
-                    const double *qu = rq_u, *ql = rq_lse;
-                    for (int b0 = 0; b0 < nq; b0 += FB) {
-                        int nb = min(FB, nq - b0);
-                        if (gtid < nb) {
-                            fb_slot[gtid] = qs[b0 + gtid];
-                            fb_u[gtid] = qu[b0 + gtid];
-                            fb_lse[gtid] = ql[b0 + gtid];
-                            fb_unres[gtid] = 0;
-                        }
-                        asm volatile("bar.sync 1, 96;" ::: "memory");
-                        block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
-                                                 fb_om, gtid, gn, 1, ambig64);
-                        if (gtid == 0) {  // compact the draws tier 2 left open (serial: at most FB entries)
-                            int n3 = 0;
-                            for (int f = 0; f < nb; ++f)
-                                if (fb_unres[f]) { fb_slot[n3] = fb_slot[f]; fb_u[n3] = fb_u[f]; ++n3; }
-                            misc[8] = n3;
-                            n_fallback += (unsigned long long)nb;
-                            n_tier3 += (unsigned long long)n3;
-                        }
-                        asm volatile("bar.sync 1, 96;" ::: "memory");
-                        const int n3 = misc[8];
-                        if (n3 > 0)
-                            block_sample_views<false>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, n3, s_view,
-                                                      fb_unres, fb_om, gtid, gn, 1, ambig64);
-                        asm volatile("bar.sync 1, 96;" ::: "memory");
-                    }
-                    for (int e = gtid; e < nq; e += gn) s_wait[qs[e]] = 0;  // their views are in s_view: advance in D
-                }
-            } else if (warp < 4) {
-                // ---- epilogue warps: thread = TMEM lane = user 32*warp+lane, all TILE_N columns of every tile
-                const int q = warp;
+            {
+                // ---- epilogue, all 8 warps: thread = TMEM lane = user 32 q + lane.  The two warps of a lane quarter (w and
+                // w + 4, same scheduler) take ALTERNATE accumulator tiles -- group g = w / 4 reads the tiles tt = g, g + 2, ...,
+                // i.e. always the same TMEM buffer -- so that their hand-shakes and loads never coincide and the scheduler
+                // always has one warp in its run of exponentials (two warps per scheduler saturate the MUFU pipe, one does
+                // not: scripts/micro/epilogue_mma.cu).  Per logit: one ex2 and one add.
+                const int q = warp & 3, grp = warp >> 2;
                 const int pos = q * 32 + lane;
                 const bool act = pos < nlive;
-                float part = 0.f;
-                int rec = 0, in_rec = 0;
+                const bool warp_act = q * 32 < nlive;   // a warp without live users only keeps the hand-shakes going
                 const int tiles_per_rec = p.rec_sub * (128 / tc::TILE_N);
                 const unsigned tile_use = seq_use / (unsigned)nslab;
-                const uint32_t dfull_s = smem_u32(dfull);
+                const uint32_t dfull_s = smem_u32(dfull), dempty_s = smem_u32(dempty);
                 const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-                // Software pipeline: the tcgen05.ld of the next 32 columns (of this tile, or of the next tile when its
-                // accumulator is already complete) is in flight while the 32 exponentials of the current ones issue; one
-                // warp per scheduler then keeps the MUFU pipe busy without bubbles.  Dead rows (pos >= nlive) carry zero
-                // operands: their logits are finite, their masses are computed and never used (no branch in the loop).
-                uint32_t va[32], vb[32];
-                bool have_first = false;   // chunk 0 of the coming tile is already in flight (in va)
-                constexpr int NCH = tc::TILE_N / 32;
-                static_assert(NCH % 2 == 0, "the register double buffer alternates per 32-column chunk");
-                for (int tt = 0; tt < ntile; ++tt) {
-                    const unsigned gs = tile_use + (unsigned)tt;
-                    const unsigned buf = gs % NBUF;
-                    const uint32_t taddr = lane_taddr + buf * (uint32_t)tc::TILE_N;
-                    RG_PROF_ONLY(const long long pa = clock64();)
-                    if (!have_first) {
+                constexpr int NCH = tc::TILE_N / 32;     // 32-column chunks per tile
+                static_assert(NBUF == 2, "one accumulator buffer per epilogue warp group");
+                const int ring_tiles = nstage / nslab;   // product tiles the B ring holds (nstage is a multiple of nslab)
+                float *gs_row = gsum_cta + pos;
+                float *ts_row = tilesum + (size_t)pos * p.nrec_pad + grp;
+                int tt = grp;
+                for (int rec = 0; rec < p.nrec; ++rec) {
+                    const int rec_end = min((rec + 1) * tiles_per_rec, ntile);
+                    float part = 0.f;
+                    for (; tt < rec_end; tt += 2) {
+                        const unsigned gs = tile_use + (unsigned)tt;
+                        const unsigned buf = gs % NBUF;
+                        const uint32_t taddr = lane_taddr + buf * (uint32_t)tc::TILE_N;
+                        RG_PROF_ONLY(const long long pa = clock64();)
                         mbar_wait_s(dfull_s + buf * 8u, (gs / NBUF) & 1u);
                         tc::tc_fence_after();
-                        tc::tmem_ld32_issue(taddr, va);
-                    }
-                    RG_PROF_ONLY(const long long pb = clock64(); long long pld = 0;)
-                    have_first = false;
-                    float *gs_out = gsum_cta + (size_t)tt * NCH * TU + pos;
+                        RG_PROF_ONLY(const long long pb = clock64(); long long pld = 0;)
+                        // Accumulator tile tt is complete, i.e. every UMMA that read its ring stages has completed: refill
+                        // them with the tile that comes ring_tiles later (no "stage free" barrier is needed).
+                        if (q == 0 && lane == 0 && tt + ring_tiles < ntile) {
+                            for (int sl = 0; sl < nslab; ++sl) issue_load(seq_use + (unsigned)((tt + ring_tiles) * nslab + sl));
+                        }
+                        float *gs_out = gs_row + (size_t)tt * (NCH * TU);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        uint32_t(&cur)[32] = (c & 1) ? vb : va;
-                        uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-                        RG_PROF_ONLY(const long long pl0 = clock64();)
-                        tc::tmem_ld32_wait(cur);
-                        RG_PROF_ONLY(pld += clock64() - pl0;)
-                        if (c + 1 < NCH) {
-                            tc::tmem_ld32_issue(taddr + (uint32_t)(32 * (c + 1)), nxt);
-                        } else {
-                            // every read of this accumulator has completed: hand it back before the math, and start on
-                            // the next tile if its accumulator is ready
-                            tc::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&dempty[buf]);
-                            if (tt + 1 < ntile) {
-                                const unsigned gn = gs + 1u, bn = gn % NBUF;
-                                int ready = 0;
-                                if (lane == 0) ready = mbar_test_s(dfull_s + bn * 8u, (gn / NBUF) & 1u) ? 1 : 0;
-                                ready = __shfl_sync(0xffffffffu, ready, 0);
-                                if (ready) {
-                                    tc::tc_fence_after();
-                                    tc::tmem_ld32_issue(lane_taddr + bn * (uint32_t)tc::TILE_N, nxt);
-                                    have_first = true;
+                        for (int c = 0; c < NCH; ++c) {
+                            float v[32];
+                            RG_PROF_ONLY(const long long pl0 = clock64();)
+#ifdef RG_X_NOLD
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = -3.f - 0.01f * (float)(lane + i + tt);
+#else
+                            if (warp_act) tc::tmem_ld32(taddr + (uint32_t)(32 * c), v);
+#endif
+                            RG_PROF_ONLY(pld += clock64() - pl0;)
+                            if (c == NCH - 1) {   // last read of this tile: hand the accumulator back before the math
+                                tc::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dempty_s + buf * 8u) : "memory");
+                            }
+                            if (warp_act) {
+                                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+#ifdef RG_X_NOMUFU
+                                    s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
+#else
+                                    s0 += ex2_approx(v[i]); s1 += ex2_approx(v[i + 1]);
+                                    s2 += ex2_approx(v[i + 2]); s3 += ex2_approx(v[i + 3]);
+#endif
                                 }
+                                // the masses of this 32-product group: kept (coalesced over the 32 users of the warp) so that
+                                // pass 2b only has to recompute ONE group of 32 products instead of the whole record tile
+                                const float cs = (s0 + s1) + (s2 + s3);
+#ifndef RG_X_NOSTG
+                                if (act) gs_out[c * TU] = cs;
+#endif
+                                part += cs;
                             }
                         }
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            s0 += ex2_approx(__uint_as_float(cur[i])); s1 += ex2_approx(__uint_as_float(cur[i + 1]));
-                            s2 += ex2_approx(__uint_as_float(cur[i + 2])); s3 += ex2_approx(__uint_as_float(cur[i + 3]));
-                        }
-                        // the masses of this 32-product group: kept (coalesced over the 32 users of the warp) so that
-                        // pass 2b only has to recompute ONE group of 32 products instead of the whole record tile
-                        const float cs = (s0 + s1) + (s2 + s3);
-                        if (act) gs_out[(size_t)c * TU] = cs;
-                        part += cs;
+                        RG_PROF_ONLY(if (lane == 0) { const long long pe = clock64(); pf[6] += pb - pa; pf[7] += pld; pf[8] += pe - pb; pf[9] += 1ull;
+                                         if (tr_on && tt < 1000 && (warp == 0 || warp == 4)) { g_trace[tt * 8 + 3] = pb; g_trace[tt * 8 + 4] = pe; g_trace[tt * 8 + 5] = warp; } })
                     }
-                    if (++in_rec == tiles_per_rec || tt == ntile - 1) {
-                        if (act) tilesum[(size_t)pos * p.nrec_pad + rec] = part;
-                        part = 0.f;
-                        in_rec = 0;
-                        ++rec;
-                    }
-                    RG_PROF_ONLY(if (lane == 0) { const long long pe = clock64(); pf[6] += pb - pa; pf[7] += pld; pf[8] += pe - pb; pf[9] += 1ull;
-                                     if (tr_on && tt < 1000 && (q == 0 || q == 3)) { g_trace[tt * 8 + (q == 0 ? 3 : 5)] = pb; g_trace[tt * 8 + (q == 0 ? 4 : 7)] = pe; } })
+                    if (act) ts_row[2 * rec] = part;   // this group's share of the record tile (0 if it owns none of its tiles)
                 }
             }
             RG_PROF_ONLY(const long long pq1 = clock64(); if (tid == 0) pf[11] += (unsigned long long)(pq1 - pq0);)
             tc::tc_fence_before();
-            __syncthreads();
+            cta_sync();
             tc::tc_fence_after();
-            if (ASYNC && tid == 0) misc[6] = 0;  // the queue has been consumed; pass 2b refills it (after the next barrier)
             seq_use += (unsigned)nunit;
             build_om32();     // pass 2 operand, in the (now idle) ring bytes
-            __syncthreads();
+            cta_sync();
             RG_PROF_ONLY(if (tid == 0) pf[14] += (unsigned long long)(clock64() - pq1);)
         } else {
             const bool warp_active = warp * 16 < nlive;
@@ -1202,12 +1163,13 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     ++rec;
                     sub_in_rec = 0;
                 }
-                __syncthreads();  // everyone is done with this ring stage
+                cta_sync();  // everyone is done with this ring stage
                 if (tid == 0) issue_load(seq + (unsigned)nstage - 1u);
             }
             seq_use += (unsigned)nsub;
         }
 
+        RG_MARK(2);   // B: pass 1 (A tile, tiles, omega tile of pass 2)
         { const long long tk1 = clock64(); ph_b += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- C: pass 2a, one thread per live user: view uniform, total mass, tau = u*Z, the record tile that
         // contains tau and the mass before it (sequential binary64 sums of the fp32 tile sums)
@@ -1216,19 +1178,22 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
             const double u = uniform53(w.x, w.y);
             const float *ts = tilesum + (size_t)i * p.nrec_pad;
+            // TC: a record tile's mass is kept as two fp32 partial sums (one per column half / epilogue warp)
+            auto rec_mass = [&](int r) -> double { return TC ? (double)ts[2 * r] + (double)ts[2 * r + 1] : (double)ts[r]; };
             double Z = 0.0;
-            for (int r = 0; r < p.nrec; ++r) Z += (double)ts[r];
+            for (int r = 0; r < p.nrec; ++r) Z += rec_mass(r);
             const double tau = u * Z;
             double cum = 0.0;
             int rsel = -1;
             for (int r = 0; r < p.nrec; ++r) {
-                const double nx = cum + (double)ts[r];
+                const double nx = cum + rec_mass(r);
                 if (nx > tau) { rsel = r; break; }
                 cum = nx;
             }
             s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel; s_u[i] = u;
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(3);   // C: pass 2a
 
         // ---- C: pass 2b (tensor mode), one warp per UI live users at a time: locate the crossing 32-product group with
         // the pass-1 group sums the epilogue kept, recompute only that group (one product per lane) for the index and its
@@ -1326,7 +1291,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         // Filter (see the CUDA-core form below for the derivation): the tolerance is
                         // d [ (1-u) S + u (Z - S) + 2u m(T) ] with T the crossing record tile
                         const double dlt = (double)s_eps[i], uu = s_u[i];
-                        const double tmass = (double)tilesum[(size_t)i * p.nrec_pad + s_rsel[i]];
+                        const float *tsr = tilesum + (size_t)i * p.nrec_pad + 2 * s_rsel[i];
+                        const double tmass = (double)tsr[0] + (double)tsr[1];
                         const double tl = dlt * ((1.0 - uu) * lo + uu * fmax(Z - lo, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
                         const double tu = dlt * ((1.0 - uu) * up + uu * fmax(Z - up, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
                         amb = (tau - lo < tl && fnd > 0) || (up - tau < tu && fnd < P - 1);
@@ -1336,7 +1302,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         const double lse = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
                         const int e = atomicAdd(&misc[6], 1);
                         rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
-                        s_wait[slot] = ASYNC ? 2 : 1;
+                        s_wait[slot] = 1;
                     }
                 }
                 __syncwarp();
@@ -1487,24 +1453,25 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     // queued for a re-sampling sweep; the slot sits out until its draw has been resolved
                     const int e = atomicAdd(&misc[6], 1);
                     rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
-                    s_wait[slot] = ASYNC ? 2 : 1;
+                    s_wait[slot] = 1;
                 }
             }
         }
-        __syncthreads();
+        cta_sync();
 
+        RG_MARK(4);   // C: pass 2b
         { const long long tk1 = clock64(); ph_c += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- C2: re-sampling of the draws the fp32 filter could not certify: tier 2 (binary64 logits, fp32 ex2,
         // a-posteriori bound), tier 3 (all binary64) for what tier 2 leaves open.  One sweep streams the whole binary64
         // Gamma (L2 -> SM) whatever the number of users in it, so uncertified draws WAIT in a queue (their slots sit the
         // rounds out) until FB of them share a sweep; in the tail of the launch (few live slots) they are resolved at once.
-        if (!ASYNC) {
+        {
             const bool tail = nlive < 16;
             for (int tier = 2; tier <= 3; ++tier) {
                 int *qs = tier == 2 ? rq_slot : q3_slot;
                 double *qu = tier == 2 ? rq_u : q3_u;
                 for (;;) {
-                    __syncthreads();
+                    cta_sync();
                     const int n = tier == 2 ? misc[6] : misc[4];
                     if (n == 0 || (n < FB && !tail)) break;
                     const int nb = min(FB, n);
@@ -1514,7 +1481,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                         fb_lse[tid] = tier == 2 ? rq_lse[tid] : 0.0;
                         fb_unres[tid] = 0;
                     }
-                    __syncthreads();
+                    cta_sync();
                     if (tier == 2)
                         block_sample_views<true>(env, om64, KP, csum, p.ncs, fb_slot, fb_u, fb_lse, nb, s_view, fb_unres,
                                                  fb_om, tid, NTH, 0, ambig64);
@@ -1540,7 +1507,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     }
                 }
             }
-            __syncthreads();
+            cta_sync();
         }
 
         if (TC && tid == 0) {
@@ -1549,6 +1516,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
             for (int s2 = 0; s2 < tc_prologue; ++s2) issue_load(seq_use + (unsigned)s2);
         }
 
+        RG_MARK(5);   // C2: re-sampling
         { const long long tk1 = clock64(); ph_c2 += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         // ---- D: advance the users.  D1 (one thread per slot) finishes the organic event: bookkeeping of the
         // view, transition.  D2 (one warp per user) runs the bandit events: the draws of an event depend only
@@ -1632,7 +1600,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 s_state[slot] = st;  // ORGANIC, or BANDIT: the run is played by D2
             }
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(6);   // D1: view bookkeeping, transition
         if (!serial_bandit) {
             if (warp == 0) {  // list of the slots that enter a bandit run (amb_list is free at this point)
                 int base = 0;
@@ -1645,7 +1614,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 }
                 if (lane == 0) misc[5] = base;
             }
-            __syncthreads();
+            cta_sync();
             const int nban = misc[5];
             for (int b = warp; b < nban; b += NWARP) {
                 const int slot = amb_list[b];
@@ -1663,9 +1632,35 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                     const double uc = uniform53(wb.x, wb.y);
                     // ff() never exceeds sig(5*0.5-6) = 0.02931, so the click threshold (1-ctr)/((1-ctr)+ctr) is
                     // above 0.9706: below that the click is 0 whatever omega is (97% of the bandit events)
+                    // The few candidate clicks are evaluated ONE AT A TIME BY THE WHOLE WARP, in event order, and only up to
+                    // the event whose transition ends the run: lane k fetches beta[a][k] and omega[k] (two coalesced loads
+                    // instead of a chain of 2K dependent L2 round trips in one lane), the dot product is then accumulated in
+                    // the oracle's order (sequential fma over k, ctr_of_action) from shuffled operands.
                     int c = 0;
-                    if (uc >= 0.9706) c = click_from_uniform(ctr_of_action(env, om, a), uc);
                     const int nst = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
+                    const unsigned mleave = __ballot_sync(0xffffffffu, nst != RG_BANDIT);
+                    const int nev_t = mleave ? __ffs(mleave) : 32;   // events up to the first transition out of the bandit state
+                    unsigned mcand = __ballot_sync(0xffffffffu, uc >= 0.9706 && lane < nev_t);
+                    while (mcand) {   // warp-uniform
+                        const int j = __ffs(mcand) - 1;
+                        mcand &= mcand - 1u;
+                        const int aj = __shfl_sync(0xffffffffu, a, j);
+                        const double *row = env.beta + (size_t)aj * K;
+                        double acc = 0.0;
+                        for (int k0 = 0; k0 < K; k0 += 32) {
+                            const int k = k0 + lane;
+                            const double bk = k < K ? __ldg(row + k) : 0.0;
+                            const double wk = k < K ? om[k] : 0.0;
+                            const int kn = min(32, K - k0);
+                            for (int kk = 0; kk < kn; ++kk)
+                                acc = fma(__shfl_sync(0xffffffffu, bk, kk), __shfl_sync(0xffffffffu, wk, kk), acc);
+                        }
+                        const int cj = click_from_uniform(ff64(acc + __ldg(env.mu_b + aj)), __shfl_sync(0xffffffffu, uc, j));
+                        if (cj) {     // the run ends with this click: later candidates never happen
+                            if (lane == j) c = 1;
+                            break;
+                        }
+                    }
                     const unsigned m = __ballot_sync(0xffffffffu, nst != RG_BANDIT || c != 0);
                     const int nev = m ? __ffs(m) : 32;  // events of this turn that really happen
                     const uint64_t rec = ((uint64_t)(uint32_t)a << 2) | ((uint64_t)c << 1) | 1u;
@@ -1703,10 +1698,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
                 __syncwarp();
             }
         }
-        __syncthreads();
+        cta_sync();
+        RG_MARK(7);   // D2: bandit runs
         { const long long tk1 = clock64(); ph_d += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
         omega_phase();
-        __syncthreads();
+        cta_sync();
         { const long long tk1 = clock64(); ph_o += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
     }
 
@@ -1717,7 +1713,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
     }
     if (TC) {
         tc::tc_fence_before();
-        __syncthreads();
+        cta_sync();
         if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
     }
 
@@ -1732,7 +1728,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
     }
 
-    RG_PROF_ONLY(if (lane == 0) { for (int i = 0; i < 16; ++i) if (pf[i]) atomicAdd(&g_prof[(warp < 4 ? 0 : warp == 4 ? 16 : 32) + i], pf[i]); })
+    RG_PROF_ONLY(if (lane == 0) { for (int i = 0; i < 16; ++i) if (pf[i]) atomicAdd(&g_prof[i], pf[i]); })
+    RG_PROF_ONLY(if (tid == 0) { for (int i = 0; i < 12; ++i) if (pf2[i]) atomicAdd(&g_prof[48 + i], pf2[i]); })
     // ---- totals: warp reduction, one atomic per counter per warp
     if (p.out.totals) {
         if (tid == 0) {   // SM cycles thread 0 of this CTA spent in each phase (diagnostic, summed over the CTAs)
@@ -1750,6 +1747,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_cta_kernel(const Params p) {
         }
     }
 }
+
+// CUDA-core form: 256 threads, two CTAs per SM at 128 registers.  Tensor form: 288 threads (the ninth warp is the MMA
+// issuer), two CTAs per SM at 96 registers (the register file is per scheduler: 5 warps x 32 x 96 regs fit its 16 K, 5 x 112 do not).
+__global__ void __launch_bounds__(NT, 2) rollout_cta_kernel_cc(const Params p) { rollout_cta_body<false>(p); }
+__global__ void __launch_bounds__(NT + 32, 2) rollout_cta_kernel_tc(const Params p) { rollout_cta_body<true>(p); }
 
 }  // namespace fast
 
@@ -1778,7 +1780,7 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     p.n_total = n_total;
     p.out = out;
     p.tc = tensor ? 1 : 0;
-    p.async2 = tensor ? 1 : 0;
+    p.nhalf = tensor ? 2 : 1;
     p.om_scratch = nullptr;
     p.csum_scratch = nullptr;
     p.spill = 0;
@@ -1789,14 +1791,15 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     const int nsub = e.dev.nsub;
     // record tiles: at most 64 partial sums per user, at least 2 sub-tiles each
     int rec_sub = 2;
-    static const int rec_max = [] { const char *v = getenv("RG_REC_MAX"); const int x = v ? atoi(v) : 0; return x > 0 ? x : 64; }();
+    static const int rec_max_env = [] { const char *v = getenv("RG_REC_MAX"); const int x = v ? atoi(v) : 0; return x > 0 ? x : 0; }();
+    const int rec_max = rec_max_env ? rec_max_env : (tensor ? 20 : 64);   // tensor mode keeps two partial sums per record (same bytes as 40 records)
     while ((nsub + rec_sub - 1) / rec_sub > rec_max) ++rec_sub;
     if (rec_sub > nsub) rec_sub = nsub;
     p.rec_sub = rec_sub;
     p.nrec = (nsub + rec_sub - 1) / rec_sub;
-    p.nrec_pad = p.nrec | 1;
+    p.nrec_pad = (p.nrec * p.nhalf) | 1;
     // ring depth: as deep as shared memory allows (2 CTAs/SM when possible)
-    const int hi_stage = tensor ? kMaxStages : 3, lo_stage = tensor ? NBUF : 2;
+    const int hi_stage = tensor ? kMaxStages : 3, lo_stage = tensor ? e.dev.nslab : 2;
     const int two_ctas = 113 * 1024;  // (228 KB - 1 KB reserved per CTA) / 2
     int best_stage = 0;
     // (CUDA-core form) when P x K is too large for one CTA's shared memory, the partial sums of the re-sampling sweeps,
@@ -1806,16 +1809,13 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     for (int pass = force_one ? 1 : 0; pass < 2 && !best_stage; ++pass) {
         p.spill = spill;
         const int limit = pass == 0 ? two_ctas : 227 * 1024;
-        // asynchronous re-sampling (warps 5-7 underneath pass 1) is correct but measured SLOWER at C3 (3.2e8 vs
-        // 4.1e8 steps/s: three warps take longer over the sweep than pass 1 lasts); opt-in via RG_ASYNC_RESAMPLE=1
-        static const bool want_async = [] { const char *v = getenv("RG_ASYNC_RESAMPLE"); return v && v[0] == '1'; }();
-        for (int a2 = (tensor && want_async) ? 1 : 0; a2 >= 0 && !best_stage; --a2) {
-            p.async2 = a2;
-            for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
-                p.nstage = nstage;
-                make_layout(p);
-                if (p.L.total <= limit) best_stage = nstage;
-            }
+        // (asynchronous re-sampling on idle warps underneath pass 1 was measured SLOWER at C3 -- 3.2e8 vs 4.1e8 steps/s: three
+        // warps take longer over the sweep than pass 1 lasts -- and has been removed)
+        for (int nstage = hi_stage; nstage >= lo_stage && !best_stage; --nstage) {
+            if (tensor && nstage % e.dev.nslab != 0) continue;   // the B ring holds whole product tiles (all K slabs)
+            p.nstage = nstage;
+            make_layout(p);
+            if (p.L.total <= limit) best_stage = nstage;
         }
     }
     if (!best_stage && tensor) {
@@ -1832,19 +1832,26 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
     // launch never needs a memset (and profiler kernel replays see a clean queue).  30 pairs in rotation
     // keep launches on different streams apart.
     p.queue = e.diag + 4 + 2 * (launch_seq++ % 30u);
-    cudaError_t ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
-                            : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+    cudaError_t ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
+                            : cudaFuncSetAttribute(rollout_cta_kernel_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
     if (ce != cudaSuccess) return ce;
     int ctas_per_sm = p.L.total <= two_ctas ? 2 : 1;
     if (force_one && ctas_per_sm == 2) {   // deepest ring that fits, padded so that only one CTA is resident per SM
         ctas_per_sm = 1;
         p.L.total = two_ctas + 1024;
-        ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
-                    : cudaFuncSetAttribute(rollout_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
+        ce = tensor ? cudaFuncSetAttribute(rollout_cta_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total)
+                    : cudaFuncSetAttribute(rollout_cta_kernel_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, p.L.total);
         if (ce != cudaSuccess) return ce;
     }
     long long blocks = (n_total + TU - 1) / TU;
     const long long max_blocks = (long long)e.num_sms * ctas_per_sm;
+    static const bool dbg_launch = [] { const char *v = getenv("RG_DEBUG_LAUNCH"); return v && v[0] == '1'; }();
+    if (dbg_launch) {
+        static thread_local int printed = 0;
+        if (printed++ < 4)
+            fprintf(stderr, "[rg] rollout_cta %s: P=%d K=%d nstage=%d nslab=%d rec_sub=%d nrec=%d smem=%d B ctas/SM=%d\n",
+                    tensor ? "tensor" : "cuda-core", e.dev.P, e.dev.K, p.nstage, e.dev.nslab, p.rec_sub, p.nrec, p.L.total, ctas_per_sm);
+    }
     if (blocks > max_blocks) blocks = max_blocks;
     if (p.spill >= 1) {
         const size_t need_c = sizeof(double) * (size_t)max_blocks * (size_t)p.ncs * FB * 2;
@@ -1901,9 +1908,9 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.gsum_bytes = need_g;
         }
         p.gsum = e.d_gsum;
-        rollout_cta_kernel<true><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+        rollout_cta_kernel_tc<<<(unsigned)blocks, NT + 32, (size_t)p.L.total, stream>>>(p);
     } else {
-        rollout_cta_kernel<false><<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
+        rollout_cta_kernel_cc<<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     }
     ce = cudaGetLastError();
     if (lpt_arena) cudaFreeAsync(lpt_arena, stream);

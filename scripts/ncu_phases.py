@@ -3,11 +3,14 @@
 import re, sys, collections, subprocess
 rep = sys.argv[1]
 txt = subprocess.run([sys.executable, 'scripts/ncu_lines.py', rep, '600'], capture_output=True, text=True).stdout
-src = subprocess.run(['git', 'show', (sys.argv[2] if len(sys.argv) > 2 else 'HEAD') + ':recogym_b200/csrc/rg_rollout_fast.cu'],
-                     capture_output=True, text=True).stdout.split('\n')
+if len(sys.argv) > 2 and sys.argv[2] == 'WORK':
+    src = open('recogym_b200/csrc/rg_rollout_fast.cu').read().split('\n')
+else:
+    src = subprocess.run(['git', 'show', (sys.argv[2] if len(sys.argv) > 2 else 'HEAD') + ':recogym_b200/csrc/rg_rollout_fast.cu'],
+                         capture_output=True, text=True).stdout.split('\n')
 def find(s):
     return next(i + 1 for i, l in enumerate(src) if s in l)
-marks = [('resample(tier2/3)', find('template <int NB, int PP, bool T2>')), ('setup', find('rollout_cta_kernel(const Params p)')),
+marks = [('resample(tier2/3)', find('template <int NB, int PP, bool T2>')), ('setup', find('rollout_cta_body(const Params &p)')),
          ('A:compact/shift', find('---- A: compact the live slots')), ('B:pass1', find('---- B: pass 1')),
          ('C:pass2a', find('---- C: pass 2a')), ('C:pass2b', find('---- C: pass 2b')),
          ('C2:resample-call', find('---- C2: re-sampling')), ('D:advance', find('---- D: advance the users')),

@@ -66,6 +66,10 @@ def main():
                                              "tile_total_after_dfull": ep[8] / ntile_e, "tiles_x_warps": ep[9]}
         out["pass1_thread0_per_round"] = {"a_tile_build_and_sync": ep[10] / max(ep[13], 1.0), "tile_loop": ep[11] / max(ep[13], 1.0),
                                           "tail_sync_and_omega_tile": ep[14] / max(ep[13], 1.0)}
+        sub = p[48:58]
+        names = ("A_compact", "A_bounds", "B_pass1", "C_pass2a", "C_pass2b", "C2_resample", "D1_view", "D2_bandit_runs",
+                 "O_list", "O_normals")
+        out["thread0_cycles_per_round"] = {n: round(float(v) / max(ep[13], 1.0), 1) for n, v in zip(names, sub)}
         out["rounds"] = ep[13]
         out["mean_live_per_round"] = ep[12] / max(ep[13], 1.0)
         t = np.array(list(trace), dtype=np.int64).reshape(-1, 8)
