@@ -209,6 +209,12 @@ int rg_sparse_count_policy_device(int kind, int32_t P, const rg_sparse_counts *c
  * Needs the columns z, u, a, c, ps, lv. */
 int rg_ips_device(const rg_log_columns *cols_device, int64_t rows, int64_t u_end, const int32_t *target_table,
                   double *out4_device, void *stream);
+/* evaluate_recall_at_k (evaluate_agent.py:852-908) of a deterministic table policy: over the bandit rows of the users
+ * < u_end that were not clicked and are directly followed by an organic row of the same user, out2_device = {hits, rows}
+ * with hit = [next view in topk_table[target[lv]][0..k)].  topk_table[g] = the k indices numpy.argpartition(one-hot(g), -k)
+ * [-k:] returns (the reference's "top k" of a one-hot 'ps-a'), tabulated by the caller.  Needs the columns z, u, v, c, lv. */
+int rg_recall_device(const rg_log_columns *cols_device, int64_t rows, int64_t u_end, const int32_t *target_table,
+                     const int32_t *topk_table, int32_t k, int64_t *out2_device, void *stream);
 
 /* Batched gym protocol.  State of N concurrent users is a caller-owned SoA on the device:
  *   user_id[N] int64, state[N] int32 (RG_*), t[N] int32 (current_time), last_view[N] int32,

@@ -108,6 +108,26 @@ def ips_table_policy(log, ps, target_table):
     return np.array(ee), np.array(rewards), np.array(ratio)
 
 
+def recall_at_k_table_policy(log, target_table, k=5):
+    """evaluate_recall_at_k (evaluate_agent.py:852-893) for pi = one-hot at target_table[last view], row by row: an
+    un-clicked bandit row of a user < max(u) that is directly followed by an organic row of the same user is a hit when
+    the next view is in numpy.argpartition(one_hot, -k)[-k:].  -> list of 0/1."""
+    u, z, v, c = (np.asarray(log[k_]) for k_ in ("u", "z", "v", "c"))
+    lv = acting_last_view(log)
+    umax = int(u.max())
+    P = len(target_table)
+    hits = []
+    for r in range(len(u) - 1):
+        if z[r] != 1 or u[r] >= umax:
+            continue
+        if u[r + 1] != u[r] or z[r + 1] != 0 or c[r] > 0:
+            continue
+        prob = np.zeros(P)
+        prob[int(target_table[lv[r]])] = 1.0
+        hits.append(1 if int(v[r + 1]) in set(np.argpartition(prob, -k)[-k:]) else 0)
+    return hits
+
+
 def ips_summary(ee, rewards, ratio):
     """verify_agents_IPS / verify_agents_SNIPS (evaluate_agent.py:813-835): mean and standard error."""
     se = np.std(ee) / np.sqrt(len(ee))

@@ -11,7 +11,7 @@ from .constants import AgentStats, AgentInit, EvolutionCase, TrainingApproach, R
 from .bench_agents import test_agent
 from .evaluate_agent import (evaluate_agent, build_agent_init, build_agents, verify_agents, gather_agent_stats,
                              gather_exploration_stats, verify_agents_IPS, verify_agents_SNIPS, evaluate_IPS,
-                             evaluate_SNIPS, to_categorical)
+                             evaluate_SNIPS, evaluate_recall_at_k, verify_agents_recall_at_k, to_categorical)
 from .competition import competition_score
 from . import agents
 from ._lib import MATH_EXACT, MATH_FAST, MATH_TENSOR, RecoGymB200Error

@@ -59,6 +59,7 @@ _lib = None
 EXPORTS = (
     "rg_env_create", "rg_env_set_seed", "rg_env_destroy", "rg_rollout_device", "rg_rollout_host",
     "rg_generate_logs_device", "rg_count_stats_device", "rg_count_policy_device", "rg_ips_device",
+    "rg_recall_device",
     "rg_batch_reset_device", "rg_batch_step_device", "rg_batch_continue_device",
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
     "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
@@ -108,6 +109,8 @@ def lib():
     L.rg_sparse_count_policy_device.argtypes = [C.c_int, i32, C.POINTER(SparseCounts), vp, vp, vp]
     L.rg_ips_device.restype = C.c_int
     L.rg_ips_device.argtypes = [C.POINTER(LogColumns), i64, i64, vp, vp, vp]
+    L.rg_recall_device.restype = C.c_int
+    L.rg_recall_device.argtypes = [C.POINTER(LogColumns), i64, i64, vp, vp, i32, vp, vp]
     L.rg_batch_reset_device.restype = C.c_int
     L.rg_batch_reset_device.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_int, vp]
     L.rg_batch_step_device.restype = C.c_int

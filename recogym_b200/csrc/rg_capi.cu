@@ -527,6 +527,17 @@ int rg_ips_device(const rg_log_columns *cols, int64_t rows, int64_t u_end, const
     return RG_OK;
 }
 
+int rg_recall_device(const rg_log_columns *cols, int64_t rows, int64_t u_end, const int32_t *target_table,
+                     const int32_t *topk_table, int32_t k, int64_t *out2_device, void *stream_) {
+    if (!cols || rows < 0 || !target_table || !topk_table || !out2_device || k < 1) return fail(RG_EINVAL, "bad argument");
+    if (rows > cols->capacity) return fail(RG_EINVAL, "rows exceed the column capacity");
+    if (!cols->z || !cols->u || !cols->v || !cols->c || !cols->lv) return fail(RG_EINVAL, "recall@k needs the columns z, u, v, c, lv");
+    cudaError_t ce = rg::launch_recall(*cols, rows, u_end, target_table, topk_table, k, (unsigned long long *)out2_device,
+                                       current_num_sms(), (cudaStream_t)stream_);
+    if (ce != cudaSuccess) return fail(RG_ECUDA, "recall failed: %s", cudaGetErrorString(ce));
+    return RG_OK;
+}
+
 static int batch_common(rg_env *env, int mode, int64_t N, const int64_t *user_id, const int32_t *action,
                         int32_t *state, int32_t *t, int32_t *last_view, double *omega, int32_t *reward,
                         int32_t *sess_v, int32_t *sess_len, int32_t sess_cap, int32_t *n_unfinished, int math_mode,

@@ -65,5 +65,7 @@ cudaError_t launch_sparse_policy(int kind, int P, const rg_sparse_counts &s, int
                                  unsigned long long *scratch, int num_sms, cudaStream_t stream);
 cudaError_t launch_ips(const rg_log_columns &c, long long rows, long long u_end, const int32_t *target, double *part,
                        int nblocks, double *out, cudaStream_t stream);
+cudaError_t launch_recall(const rg_log_columns &c, long long rows, long long u_end, const int32_t *target,
+                          const int32_t *topk, int k, unsigned long long *out2, int num_sms, cudaStream_t stream);
 cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);
 }  // namespace rg

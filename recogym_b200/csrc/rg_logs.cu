@@ -172,6 +172,9 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const float fnan = __int_as_float(0x7fc00000);
     const double dnan = __longlong_as_double(0x7ff8000000000000ll);
+    // The log did not fit (the caller reads the row count and regenerates into larger columns): order_scatter placed only
+    // the first `capacity` records, the rest of `ordered` is uninitialised -- nothing here may be derived from it.
+    if (row_offset[n_total] > capacity) return;
     for (long long i = warp; i < n_total; i += nwarps) {
         const long long r0 = row_offset[i], r1 = min(row_offset[i + 1], capacity);
         int carry_lv = -1;                               // last view before this chunk
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
                     double ps = dnan;
                     if (!org) {
                         if (policy_kind == RG_POLICY_UNIFORM) ps = 1.0 / (double)P;   // abstract.py:219
-                        else if (policy_kind == RG_POLICY_TABLE) ps = ps_table ? ps_table[lv] : 1.0;
+                        else if (policy_kind == RG_POLICY_TABLE) ps = ps_table ? (lv >= 0 && lv < P ? ps_table[lv] : dnan) : 1.0;
                     }
                     col.ps[r] = ps;
                 }
@@ -251,6 +254,10 @@ __global__ void carry_kernel(const int4 *__restrict__ ordered, const long long *
                              int prev_last_view, long long capacity, int train_mode, int32_t *__restrict__ carry_out) {
     const int lane = threadIdx.x & 31;
     int x = prev_last_view;
+    if (row_offset[n_total] > capacity) {   // incomplete log (see columns_kernel): the caller regenerates it
+        if (lane == 0) carry_out[0] = prev_last_view;
+        return;
+    }
     for (long long j = n_total - 1; j >= n_organic_users; --j) {
         const int t = trained_last_view(ordered, row_offset, last_view, j, capacity, train_mode, lane);
         if (t != -2) { x = t; break; }
@@ -530,6 +537,35 @@ __global__ void ips_final_kernel(const double *__restrict__ part, int nblocks, d
     }
 }
 
+// recall@k of a deterministic table policy (evaluate_agent.py:852-908): for every bandit row of the users < u_end that was
+// not clicked and is directly followed by an organic row of the same user, is the product viewed next among the top k of
+// the policy's action probabilities?  pi(. | lv) is one-hot at g = target[lv]; its "top k" is whatever numpy.argpartition
+// returns for that vector (k - 1 zero-probability products beside g), tabulated per action by the caller: topk[g][0..k).
+// Integer counters: out2 = {hits, eligible rows}.
+__global__ void __launch_bounds__(256) recall_kernel(const int8_t *__restrict__ z, const int32_t *__restrict__ u,
+                                                     const int32_t *__restrict__ v, const float *__restrict__ c,
+                                                     const int32_t *__restrict__ lv, long long rows, long long u_end,
+                                                     const int32_t *__restrict__ target, const int32_t *__restrict__ topk,
+                                                     int k, unsigned long long *__restrict__ out2) {
+    unsigned long long hits = 0ull, n = 0ull;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r + 1 < rows; r += (long long)gridDim.x * blockDim.x) {
+        if (z[r] != 1 || (long long)u[r] >= u_end) continue;
+        if (u[r + 1] != u[r] || z[r + 1] != 0 || c[r] != 0.f) continue;
+        const int32_t *tk = topk + (size_t)target[lv[r]] * k;
+        const int32_t next = v[r + 1];
+        int hit = 0;
+        for (int j = 0; j < k; ++j) hit |= (tk[j] == next) ? 1 : 0;
+        hits += (unsigned long long)hit;
+        n += 1ull;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        hits += __shfl_xor_sync(0xffffffffu, hits, d);
+        n += __shfl_xor_sync(0xffffffffu, n, d);
+    }
+    if ((threadIdx.x & 31) == 0 && n) { atomicAdd(out2, hits); atomicAdd(out2 + 1, n); }
+}
+
 }  // namespace logs
 
 using namespace logs;
@@ -621,6 +657,16 @@ cudaError_t launch_ips(const rg_log_columns &c, long long rows, long long u_end,
                        int nblocks, double *out, cudaStream_t stream) {
     ips_partial_kernel<<<nblocks, 256, 0, stream>>>(c.z, c.u, c.a, c.c, c.ps, c.lv, rows, u_end, target, part);
     ips_final_kernel<<<1, 32, 0, stream>>>(part, nblocks, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_recall(const rg_log_columns &c, long long rows, long long u_end, const int32_t *target,
+                          const int32_t *topk, int k, unsigned long long *out2, int num_sms, cudaStream_t stream) {
+    cudaError_t ce = cudaMemsetAsync(out2, 0, 16, stream);
+    if (ce != cudaSuccess || rows < 2) return ce;
+    long long blocks = (rows + 255) / 256;
+    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+    recall_kernel<<<(unsigned)blocks, 256, 0, stream>>>(c.z, c.u, c.v, c.c, c.lv, rows, u_end, target, topk, k, out2);
     return cudaGetLastError();
 }
 

@@ -153,6 +153,8 @@ def _policy_struct(keep, policy, table, P, host):
     elif policy == "table":
         pol.kind = L.POLICY_TABLE
         if host:
+            if hasattr(table, "is_cuda"):     # a table trained on the device (CountStats): the host path takes a host copy
+                table = table.detach().cpu().numpy()
             t = np.ascontiguousarray(table, np.int32)
             assert t.shape == (P,)
             pol.table = t.ctypes.data

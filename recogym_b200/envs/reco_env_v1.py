@@ -88,6 +88,7 @@ class RecoEnv1:
         self._batch = None
         self._device = 0
         self._epoch_seed = None
+        self._user_key_offset = 0   # RNG key of the facade's current user = its label + this (generate_logs(user_begin=))
 
     # ---------------------------------------------------------------------------------- set-up
     def reset_random_seed(self, epoch=0):
@@ -191,10 +192,11 @@ class RecoEnv1:
         self.current_time = self.time_generator.new_time()
         self.current_user_id = user_id
         self.organic_views = np.zeros(self.config.num_products)
+        key = int(user_id) + int(getattr(self, "_user_key_offset", 0))
         if self._batch is None:
-            self._batch = BatchState(self.device_env, [int(user_id)], sess_cap=64)
+            self._batch = BatchState(self.device_env, [key], sess_cap=64)
         else:
-            self._batch.user_id.fill_(int(user_id))
+            self._batch.user_id.fill_(key)
         self._pending_reset = True
 
     def _collect_sessions(self, h, t_before):
@@ -254,8 +256,9 @@ class RecoEnv1:
                 action = self.agent.act(observation, reward, done)
             else:
                 P = self.config.num_products
-                a = L.lib().rg_spec_policy_uniform_action(self._epoch_seed, int(self.current_user_id),
-                                                          int(self.current_time), P)
+                a = L.lib().rg_spec_policy_uniform_action(
+                    self._epoch_seed, int(self.current_user_id) + int(getattr(self, "_user_key_offset", 0)),
+                    int(self.current_time), P)
                 action = {
                     "t": observation.context().time(),
                     "u": observation.context().user(),
@@ -269,9 +272,13 @@ class RecoEnv1:
         observation, reward, done, info = self.step(action["a"] if action is not None else None)
         return action, observation, reward, done, info
 
-    def generate_logs(self, num_offline_users, agent=None, num_organic_offline_users=0, fused=None):
+    def generate_logs(self, num_offline_users, agent=None, num_organic_offline_users=0, fused=None, user_begin=0):
         """abstract.py:241-327: DataFrame[t,u,z,v,a,c,ps,ps-a] of a rollout.  u/v/a are Int32 (the reference's
         UInt16 overflows at 65 535 users / int16 at 32 767 products).
+
+        user_begin: the reference env draws from ONE sequential stream, so every call sees fresh users; here a user is
+        the counter-RNG key `user_begin + u` (u = the 0-based label in the log), and a call is reproducible: the default
+        replays users 0..N-1.  Drivers that train and then evaluate pass the first unused key (test_agent, verify_agents).
 
         fused=None (default): when the acting policy runs on the device (no agent = the default uniform logging
         policy, or an agent with `device_policy()`), all users are simulated by ONE fused CUDA rollout whose
@@ -286,7 +293,8 @@ class RecoEnv1:
         if fused:
             if pol is None:
                 raise ValueError("fused generate_logs needs a device policy (no agent, or agent.device_policy())")
-            return self._generate_logs_fused(num_offline_users, pol, num_organic_offline_users)
+            return self._generate_logs_fused(num_offline_users, pol, num_organic_offline_users, user_begin)
+        self._user_key_offset = int(user_begin)
         if agent:
             old_agent = self.agent
             self.agent = agent
@@ -330,13 +338,15 @@ class RecoEnv1:
         data["c"] = np.array(data["c"], dtype=np.float32)
         if agent:
             self.agent = old_agent
+        self._user_key_offset = 0
         return pd.DataFrame().from_dict(data)
 
-    def _generate_logs_fused(self, num_offline_users, pol, num_organic_offline_users):
+    def _generate_logs_fused(self, num_offline_users, pol, num_organic_offline_users, user_begin=0):
         import pandas as pd
         from .device_env import rollout_log
-        r = rollout_log(self.device_env, num_offline_users, pol["policy"], pol.get("table"), 0,
+        r = rollout_log(self.device_env, num_offline_users, pol["policy"], pol.get("table"), int(user_begin),
                         num_organic_offline_users)
+        r["u"] = r["u"] - int(user_begin)          # labels are 0-based per call, as in the reference
         organic = r["z"] == 0
         P = self.config.num_products
         if pol["policy"] == "uniform":
@@ -356,6 +366,8 @@ class RecoEnv1:
                 # the acting last view of a bandit row is the most recent organic view of the same user
                 lv = pd.Series(np.where(organic, r["v"], np.nan)).groupby(r["u"]).ffill().to_numpy()
                 bidx = np.flatnonzero(~organic)
+                if hasattr(ps_table, "is_cuda"):   # trained on the device
+                    ps_table = ps_table.detach().cpu().numpy()
                 ps[bidx] = np.asarray(ps_table)[lv[bidx].astype(np.int64)]
         nan = np.float32("nan")
         df = pd.DataFrame({

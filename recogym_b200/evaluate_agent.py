@@ -21,20 +21,24 @@ def build_agent_init(agent_key, ctor, def_args):
     return {agent_key: {AgentInit.CTOR: ctor, AgentInit.DEF_ARGS: def_args}}
 
 
-def verify_agents(env, number_of_users, agents, allow_probe=False):
+def verify_agents(env, number_of_users, agents, allow_probe=False, user_begin=0):
     """A/B test: every agent is rolled out on a fresh copy of the env (same seed, same users) and
     scored by the Beta posterior of its click rate over bandit rows, phantom rows included
-    (evaluate_agent.py:732-750).  Compilable agents use one fused CUDA rollout each."""
+    (evaluate_agent.py:732-750).  Compilable agents use one fused CUDA rollout each.
+
+    user_begin: first counter-RNG key of the A/B users.  The reference copies the env in its CURRENT state, i.e. after
+    whatever users the agents were trained on; pass the number of users already consumed to keep the A/B users disjoint
+    from the training users (a rollout here is a pure function of (seed, user key))."""
     import pandas as pd
     stat = {"Agent": [], "0.025": [], "0.500": [], "0.975": []}
     for agent_id, agent in agents.items():
         e = deepcopy(env)
         pol = device_policy(agent, e.config.num_products, allow_probe=allow_probe)
         if pol is not None:
-            r = e.generate_logs_counters(number_of_users, pol["policy"], pol.get("table"))
+            r = e.generate_logs_counters(number_of_users, pol["policy"], pol.get("table"), user_begin=user_begin)
             successes, failures = r["successes"], r["failures"]
         else:
-            data = e.generate_logs(number_of_users, agent)
+            data = e.generate_logs(number_of_users, agent, user_begin=user_begin)
             bandits = data[data["z"] == "bandit"]
             successes = bandits[bandits["c"] == 1].shape[0]
             failures = bandits[bandits["c"] == 0].shape[0]
@@ -330,6 +334,60 @@ def evaluate_SNIPS(agent, reco_log):
     """-> (rewards, p_ratio) (evaluate_agent.py:784-811)."""
     c, pi, ps = _replay_policy_probabilities(agent, reco_log)
     return list(c), list(pi / ps)
+
+
+def evaluate_recall_at_k(agent, reco_log, k=5):
+    """Hit list of recall@k (evaluate_agent.py:852-893): for every un-clicked bandit row of the users 0 .. max(u)-1 that
+    is directly followed by an organic row of the same user, 1 if the product viewed next is among the top k of the
+    agent's action probabilities ('ps-a'; numpy.argpartition decides ties, as in the reference), else 0.  Table agents
+    are evaluated in one vectorised pass, any other agent is replayed row by row through its own act()."""
+    import numpy as np
+    import pandas as pd
+    from .envs.context import DefaultContext
+    from .envs.observation import Observation
+    from .envs.session import OrganicSessions
+    from .logs import one_hot_top_k_table
+    u = reco_log["u"].to_numpy(dtype="int64")
+    z = (reco_log["z"].to_numpy() == "bandit")
+    pol = agent.device_policy() if hasattr(agent, "device_policy") else None
+    if pol is not None and pol.get("policy") == "table":
+        table = np.asarray(pol["table"].cpu().numpy() if hasattr(pol["table"], "cpu") else pol["table"])
+        v = reco_log["v"].to_numpy(dtype="float64", na_value=np.nan)
+        c = reco_log["c"].to_numpy(dtype="float64")
+        lv = pd.Series(np.where(z, np.nan, v)).groupby(u).ffill().to_numpy()
+        nxt = np.arange(len(u)) + 1
+        ok = z & (u < int(u.max()))
+        ok[-1] = False
+        rows = np.flatnonzero(ok)
+        rows = rows[(u[rows + 1] == u[rows]) & ~z[rows + 1] & ~(c[rows] > 0)]
+        topk = one_hot_top_k_table(len(table), k, table)
+        g = table[lv[rows].astype(np.int64)]
+        return [int(x) for x in (topk[g] == v[rows + 1].astype(np.int64)[:, None]).any(axis=1)]
+    hits = []
+    for user in range(int(u.max())):
+        rows = reco_log[reco_log["u"] == user]
+        zz, vv, cc, tt = list(rows["z"]), np.array(rows["v"]), np.array(rows["c"]), np.array(rows["t"])
+        session = OrganicSessions()
+        agent.reset()
+        for j in range(len(zz)):
+            if zz[j] == "organic":
+                session.next(DefaultContext(tt[j], user), int(vv[j]))
+                continue
+            prob = agent.act(Observation(DefaultContext(tt[j], user), session), 0, False)["ps-a"]
+            if j + 1 < len(zz) and zz[j + 1] == "organic" and not cc[j]:
+                hits.append(1 if int(vv[j + 1]) in set(np.argpartition(prob, -k)[-k:]) else 0)
+            session = OrganicSessions()
+    return hits
+
+
+def verify_agents_recall_at_k(reco_log, agents, k=5):
+    """evaluate_agent.py:896-908: mean +- 2 standard errors of the recall@k hits per agent."""
+    import numpy as np
+    rows = []
+    for agent_id, agent in agents.items():
+        hits = np.asarray(evaluate_recall_at_k(agent, reco_log, k=k))
+        rows.append((agent_id, np.mean(hits), np.std(hits) / np.sqrt(len(hits))))
+    return _estimator_frame(rows)
 
 
 def _estimator_frame(rows):

@@ -348,6 +348,47 @@ def _reinsert(old, new, stream):
         raise RuntimeError("sparse count statistics: growth lost cells")
 
 
+def one_hot_top_k_table(P, k, actions=None):
+    """topk[g] = the k indices the reference's recall@k takes as the "top k" of a one-hot 'ps-a' at g:
+    numpy.argpartition(one_hot(g), -k)[-k:] (evaluate_agent.py:884) -- g itself plus k - 1 zero-probability products that
+    only numpy's partition algorithm determines, so the table is built WITH numpy, one call per distinct action.
+    Rows of actions that never occur stay -1.  int32 [P][k]."""
+    k = int(min(k, P))
+    acts = range(P) if actions is None else sorted(set(int(a) for a in np.asarray(actions).ravel()))
+    out = np.full((P, k), -1, np.int32)
+    prob = np.zeros(P)
+    for g in acts:
+        prob[g] = 1.0
+        out[g] = np.argpartition(prob, -k)[-k:]
+        prob[g] = 0.0
+    return out
+
+
+def recall_table_policy(log, target_table, k=5, u_end=None):
+    """evaluate_recall_at_k / verify_agents_recall_at_k (evaluate_agent.py:852-908) of the deterministic policy
+    a = target_table[last view] on a DeviceLog: one segmented pass over the log columns.  Returns dict(hits, n, mean, se)
+    with se = std(hits) / sqrt(n) as in the reference; the last user of the log is left out, as there."""
+    torch = _torch()
+    dev = log.env.torch_device
+    host_table = target_table.detach().cpu().numpy() if hasattr(target_table, "is_cuda") else np.asarray(target_table)
+    if not (hasattr(target_table, "is_cuda") and target_table.is_cuda):
+        target_table = torch.as_tensor(np.ascontiguousarray(target_table, np.int32), device=dev)
+    P = int(host_table.shape[0])
+    topk = one_hot_top_k_table(P, k, host_table)
+    topk_d = torch.as_tensor(topk, device=dev)
+    if u_end is None:
+        u_end = log.user_begin + log.n_users_total - 1
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    cols = log.struct()
+    L.check(L.lib().rg_recall_device(C.byref(cols), int(log.rows), int(u_end), C.c_void_p(target_table.data_ptr()),
+                                     C.c_void_p(topk_d.data_ptr()), int(topk.shape[1]), C.c_void_p(out.data_ptr()),
+                                     log.env._stream()))
+    hits, n = (int(x) for x in out.cpu().numpy())
+    mean = hits / n if n else float("nan")
+    se = (mean * (1.0 - mean)) ** 0.5 / n ** 0.5 if n else float("nan")
+    return {"hits": hits, "n": n, "mean": mean, "se": se}
+
+
 def ips_table_policy(log, target_table, u_end=None):
     """evaluate_IPS / evaluate_SNIPS of the deterministic policy a = target_table[last view] on a DeviceLog
     (evaluate_agent.py:753-835).  Returns dict(ips_mean, ips_se, snips_mean, snips_se, n) with the reference's

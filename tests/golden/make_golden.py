@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as H  # noqa: E402
 
-OUT = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("RG_GOLDEN_OUT", os.path.dirname(os.path.abspath(__file__)))
 
 
 def save(name, **kw):
@@ -202,6 +202,17 @@ def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
     # per-row terms c * pi(a) / ps are exactly evaluate_SNIPS's rewards * p_ratio, evaluate_agent.py:777,808-809)
     rewards, p_ratio = evaluate_SNIPS(oc, df3)
     snips = verify_agents_SNIPS(df3, {"oc": oc})
+    # recall@k of both trained agents on the same log (evaluate_agent.py:852-908); BanditCount needs 'ps-a'
+    from recogym.evaluate_agent import evaluate_recall_at_k, verify_agents_recall_at_k
+    bc_all = BanditCount(ref.Configuration({**bandit_count_args, "num_products": P, "with_ps_all": True}))
+    bc_all.pulls_a, bc_all.clicks_a, bc_all.ctr = bc.pulls_a.copy(), bc.clicks_a.copy(), bc.ctr.copy()
+    bc_all.last_product_viewed = bc.last_product_viewed
+    recall = {}
+    for kk in (1, 5):
+        recall["recall_hits_oc_k%d" % kk] = np.asarray(evaluate_recall_at_k(oc, df3, k=kk), np.int64)
+        recall["recall_hits_bc_k%d" % kk] = np.asarray(evaluate_recall_at_k(deepcopy(bc_all), df3, k=kk), np.int64)
+    rk = verify_agents_recall_at_k(df3, {"oc": oc, "bc": deepcopy(bc_all)}, k=5)
+    recall["recall_frame_k5"] = np.array([[rk["0.025"][i], rk["0.500"][i], rk["0.975"][i]] for i in range(2)], np.float64)
     B = H.logs_to_arrays(df3)
     save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_organic,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
@@ -210,7 +221,7 @@ def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
          co_counts=oc.co_counts, pulls_a=bc.pulls_a, clicks_a=bc.clicks_a, ctr=bc.ctr,
          bandit_lpv=int(bc.last_product_viewed),
          ips_rewards=np.asarray(rewards, np.float64), ips_p_ratio=np.asarray(p_ratio, np.float64),
-         snips=np.array([snips["0.025"][0], snips["0.500"][0], snips["0.975"][0]], np.float64))
+         snips=np.array([snips["0.025"][0], snips["0.500"][0], snips["0.975"][0]], np.float64), **recall)
     print(name, "rows", len(df), "co sum", oc.co_counts.sum(), "pulls", bc.pulls_a.sum(), "snips", snips.values.tolist())
 
 

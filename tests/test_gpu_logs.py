@@ -102,6 +102,20 @@ def test_count_stats_tables_and_ips_equal_reference(oracle):
     assert r["n"] == len(ee) and r["sum_ee"] == ee.sum() and r["sum_ratio"] == g["ips_p_ratio"].sum()
     assert abs(r["ips_mean"] - ee.mean()) < 1e-15 and abs(r["snips_mean"] - g["snips"][1]) < 1e-15
     assert abs(r["ips_se"] - ee.std() / np.sqrt(len(ee))) < 1e-12
+    # recall@k of both reference-trained count agents on the same log (evaluate_agent.py:852-908): the device pass ==
+    # the reference's own hit lists, and a larger log == the oracle's row-by-row restatement
+    from recogym_b200.logs import recall_table_policy
+    for tag, table in (("oc", g["co_counts"].argmax(axis=1)), ("bc", g["ctr"].argmax(axis=1))):
+        for k in (1, 5):
+            rk = recall_table_policy(ilog, table.astype(np.int32), k)
+            hits = g["recall_hits_%s_k%d" % (tag, k)]
+            assert rk["n"] == len(hits) and rk["hits"] == int(hits.sum()), (tag, k, rk)
+            assert abs(rk["mean"] - hits.mean()) < 1e-15 and abs(rk["se"] - hits.std() / np.sqrt(len(hits))) < 1e-12
+    big = generate_logs_device(de, 700, "uniform", None, None, 1000, 0, 2)
+    tab = np.random.RandomState(3).randint(0, P, P).astype(np.int32)
+    want = T.recall_at_k_table_policy(big.to_host(), tab, 3)
+    rk = recall_table_policy(big, tab, 3)
+    assert rk["n"] == len(want) and rk["hits"] == int(np.sum(want))
     de.close()
 
 

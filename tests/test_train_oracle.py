@@ -146,6 +146,57 @@ def test_host_ips_snips_estimators_match_reference():
     assert np.array_equal(r2, g["ips_rewards"][:nrow]) and np.array_equal(q2, g["ips_p_ratio"][:nrow])
 
 
+def _golden_frame(g, prefix="ipslog_"):
+    import pandas as pd
+    P = g["Gamma"].shape[0]
+    z = g[prefix + "z"]
+    df = pd.DataFrame({
+        "t": g[prefix + "t"].astype(np.float32), "u": pd.array(g[prefix + "u"], dtype=pd.Int32Dtype()),
+        "z": np.where(z == 0, "organic", "bandit"),
+        "v": pd.array(np.where(z == 0, g[prefix + "v"], 0), dtype=pd.Int32Dtype()),
+        "a": pd.array(np.where(z == 1, g[prefix + "a"], 0), dtype=pd.Int32Dtype()),
+        "c": np.where(z == 1, g[prefix + "c"], np.nan).astype(np.float32), "ps": np.where(z == 1, 1.0 / P, np.nan)})
+    df.loc[z == 1, "v"] = pd.NA
+    df.loc[z == 0, "a"] = pd.NA
+    return df
+
+
+def test_recall_at_k_matches_reference():
+    """evaluate_recall_at_k / verify_agents_recall_at_k (evaluate_agent.py:852-908): the oracle's row-by-row restatement,
+    the package's vectorised table path and its row-by-row replay == the reference's own hit lists for its trained
+    OrganicCount and BanditCount (k = 1 and 5), and the summary frame."""
+    import recogym_b200 as rg
+    from oracle import train_oracle as T
+    g = load_golden(CASE)
+    P = g["Gamma"].shape[0]
+    log = golden_log(g, "ipslog_")
+    df = _golden_frame(g)
+    oc = rg.agents.OrganicCount(rg.Configuration({**rg.agents.organic_count_args, "num_products": P}))
+    oc.co_counts = g["co_counts"].copy()
+    bc = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": P}))
+    bc.pulls_a, bc.clicks_a, bc.ctr = g["pulls_a"].copy(), g["clicks_a"].copy(), g["ctr"].copy()
+    bc.last_product_viewed = int(g["bandit_lpv"])
+    t_oc = T.organic_count_table(g["co_counts"])
+    t_bc, _ = T.bandit_count_table(g["pulls_a"], g["clicks_a"])
+    for k in (1, 5):
+        assert np.array_equal(T.recall_at_k_table_policy(log, t_oc, k), g["recall_hits_oc_k%d" % k]), k
+        assert np.array_equal(T.recall_at_k_table_policy(log, t_bc, k), g["recall_hits_bc_k%d" % k]), k
+        assert np.array_equal(rg.evaluate_recall_at_k(oc, df, k=k), g["recall_hits_oc_k%d" % k]), k
+        assert np.array_equal(rg.evaluate_recall_at_k(bc, df, k=k), g["recall_hits_bc_k%d" % k]), k
+    out = rg.verify_agents_recall_at_k(df, {"oc": oc, "bc": bc}, k=5)
+    assert list(out.columns) == ["Agent", "0.025", "0.500", "0.975"] and list(out["Agent"]) == ["oc", "bc"]
+    got = np.array([[out["0.025"][i], out["0.500"][i], out["0.975"][i]] for i in range(2)])
+    assert np.allclose(got, g["recall_frame_k5"], rtol=0, atol=1e-15)
+
+    class Replay(rg.agents.OrganicCount):                        # no table -> the reference's row-by-row replay
+        def device_policy(self):
+            return None
+    rp = Replay(rg.Configuration({**rg.agents.organic_count_args, "num_products": P, "with_ps_all": True}))
+    rp.co_counts = g["co_counts"].copy()
+    sub = rg.evaluate_recall_at_k(rp, df[df["u"] < 8], k=5)      # users 0..6 (the last user of the sub-log is left out)
+    assert len(sub) > 10 and np.array_equal(sub, g["recall_hits_oc_k5"][:len(sub)])
+
+
 def test_sparse_count_statistics_equal_dense(oracle):
     from oracle import train_oracle as T
     """oracle/train_oracle.py's dict-of-keys statistics (the checker of the device hash-table statistics used at
