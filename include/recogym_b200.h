@@ -47,6 +47,11 @@ extern "C" {
                                (cumsum, /= cdf[-1], searchsorted right) on the policy stream's second uniform.
                                The per-user view counts (ViewsFeaturesProvider, agents/abstract.py:318-409) live in
                                a device scratch owned by rg_env. */
+#define RG_POLICY_EPS_TABLE 3  /* EpsilonGreedy around a table agent (agents/epsilon_greedy.py:21-71, epsilon_pure_new,
+                                  not epsilon_select_worse): policy stream words 0,1 = the uniform of the coin
+                                  choice([True, False], p = [eps, 1 - eps]); exploit -> table[last view]; explore ->
+                                  words 2,3 = the uniform of choice(P, p = ones with a 0 at the greedy action / sum).
+                                  An action differs from table[last view] exactly when it was an exploring one. */
 
 /* math modes of the organic-view sampler */
 #define RG_MATH_EXACT 0 /* every view sampled in binary64 (reference arithmetic) */
@@ -70,6 +75,14 @@ typedef struct rg_env_desc {
     int32_t change_omega_for_bandits;/* reco_env_v1.py:95,106 */
     int32_t reserved;
     uint64_t seed;                   /* config.random_seed + epoch (abstract.py:59-62) */
+    int32_t time_generator;          /* 0 = DefaultTimeGenerator (default_time_generator.py:4-16: the clock is the event
+                                        index); 1 = NormalTimeGenerator (normal_time_generator.py:7-31: the clock advances
+                                        by |N(mu, sigma)| per event, the omega drift is scaled by that step,
+                                        reco_env_v1.py:89-99; the step of event index i is drawn from Philox slot 2 at
+                                        (user, i)) */
+    int32_t reserved2;
+    double normal_time_mu;           /* config.normal_time_mu (default 0) */
+    double normal_time_sigma;        /* config.normal_time_sigma (default 1) */
 } rg_env_desc;
 
 typedef struct rg_env rg_env; /* opaque: owns the device copies of the static parameters */
@@ -84,8 +97,9 @@ int rg_env_destroy(rg_env *env);
 typedef struct rg_policy {
     int32_t kind;          /* RG_POLICY_* */
     int32_t reserved;
-    const int32_t *table;  /* [P] (RG_POLICY_TABLE); host pointer for rg_rollout_host,
+    const int32_t *table;  /* [P] (RG_POLICY_TABLE, RG_POLICY_EPS_TABLE); host pointer for rg_rollout_host,
                               device pointer for rg_rollout_device */
+    double epsilon;        /* RG_POLICY_EPS_TABLE: exploration probability in (0, 1); needs P >= 2 */
 } rg_policy;
 
 /* Outputs of a rollout; every pointer is nullable.  Per-user arrays are indexed by
@@ -248,6 +262,8 @@ double rg_spec_ff(double x);            /* reco_env_v1.py:38-41 */
 double rg_spec_event_uniform(uint64_t seed, uint64_t user, uint32_t t, int which);
 void rg_spec_normals(uint64_t seed, uint64_t user, uint32_t t, int K, double *z);
 int32_t rg_spec_policy_uniform_action(uint64_t seed, uint64_t user, uint32_t t, int32_t P);
+/* NormalTimeGenerator.new_time() (normal_time_generator.py:25-28): |mu + sigma z| of this user's `call`-th call */
+double rg_spec_time_step(uint64_t seed, uint64_t user, uint32_t call, double mu, double sigma);
 
 /* The same functions evaluated ON THE DEVICE (device buffers): kind 0 exp, 1 log, 2 norm_ppf, 3 ff map
  * in[n] -> out[n]; kinds 4 (first normal pair), 5 (event uniforms), 6 (uniform action for P=1000003, word 3)

@@ -176,6 +176,11 @@ class PhiloxAgentRNG:
         self.env = env
         self.seed = int(seed)
 
+    def __deepcopy__(self, memo):
+        # evaluate_agent deep-copies the agent at every step boundary (evaluate_agent.py:59,84,139-142): the copy must keep
+        # reading the (user, time) of the ONE env that is being stepped, not of a copy of it
+        return PhiloxAgentRNG(self.env, self.seed)
+
     def choice(self, a, p=None):
         from oracle import oracle as O
         u, t = self.env.rng._ut() if isinstance(self.env.rng, PhiloxUserRNG) else (int(self.env.current_user_id),

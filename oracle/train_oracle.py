@@ -90,6 +90,84 @@ def acting_last_view(log):
     return lv
 
 
+def evolution(rollout, P, kind, n_init, n_step, n_steps, approach="all", epsilon=0.0, window=0):
+    """evaluate_agent (evaluate_agent.py:51-146) for a count agent (kind "organic" | "bandit"), bare or under
+    EpsilonGreedy(epsilon), restated call by call on the oracle's logs.  rollout(user_begin, n, policy, table, epsilon)
+    -> ordered log dict (u, z, v, a, c; the phantom row after `done` included).  approach: "all" | "last" | "swall"
+    (samples % window == 0) | "expl" (not greedy) | "swexpl".  -> dict(success, failure, success_greedy, failure_greedy,
+    actions [P][n_steps + 1])."""
+    new = lambda: {"co": np.zeros((P, P)), "pulls": np.zeros((P, P)), "clicks": np.zeros((P, P)), "lpv": None}
+    copy = lambda s: {"co": s["co"].copy(), "pulls": s["pulls"].copy(), "clicks": s["clicks"].copy(), "lpv": s["lpv"]}
+
+    def train(st, session, action, reward):       # OrganicCount.train / BanditCount.train on one call
+        if session:
+            b = np.bincount(session, minlength=P).astype(np.float64).reshape(P, 1)
+            st["co"] = st["co"] + np.matmul(b, b.T)
+        ix = st["lpv"]
+        if session:
+            st["lpv"] = session[-1]
+        st["pulls"][ix, action] += 1               # ix None -> numpy's [np.newaxis, action]: the whole row `action`
+        st["clicks"][ix, action] += reward
+
+    def table_of(st):
+        return organic_count_table(st["co"]) if kind == "organic" else bandit_count_table(st["pulls"], st["clicks"])[0]
+
+    agent = new()
+    initial = copy(agent)
+    if n_init > 0:
+        log = rollout(0, n_init, "uniform", None, 0.0)
+        for _, session, action, reward in iter_train_calls(log, 0, 0, mode=2):
+            train(agent, session, action, reward)
+    uid = n_init
+    training = copy(agent)
+    samples = 0
+    out = {k: [] for k in ("success", "failure", "success_greedy", "failure_greedy")}
+    actions = [[0] for _ in range(P)]
+    for _ in range(n_steps):
+        table = np.asarray(table_of(agent), np.int32)
+        log = rollout(uid, n_step, "eps_table" if epsilon > 0.0 else "table", table, epsilon)
+        u, z, v, a, c = (np.asarray(log[k]) for k in ("u", "z", "v", "a", "c"))
+        s = f = sg = fg = 0
+        i, n = 0, len(u)
+        while i < n:
+            j = i
+            while j < n and u[j] == u[i]:
+                j += 1
+            session, last_view = [], None
+            for r in range(i, j):
+                if z[r] == 0:
+                    session.append(int(v[r])); last_view = int(v[r])
+                    continue
+                if r == j - 1:                       # the phantom row after done: `while not done` never reaches it
+                    break
+                samples += 1
+                greedy = int(a[r]) == int(table[last_view])
+                upd = {"all": True, "last": True, "swall": window and samples % window == 0, "expl": not greedy,
+                       "swexpl": (not greedy) and window and samples % window == 0}[approach]
+                if upd:
+                    train(training, session, int(a[r]), int(max(c[r], 0)))
+                if c[r] == 1:
+                    s += 1; sg += int(greedy and epsilon_wrapped(epsilon)); actions[int(a[r])][-1] += 1
+                else:
+                    f += 1; fg += int(greedy and epsilon_wrapped(epsilon))
+                session = []
+            i = j
+        uid += n_step
+        agent = training
+        for p in range(P):
+            actions[p].append(0)
+        training = copy(initial if approach == "last" else agent)
+        out["success"].append(s); out["failure"].append(f); out["success_greedy"].append(sg); out["failure_greedy"].append(fg)
+    out["actions"] = np.array(actions, np.int64)
+    return out
+
+
+def epsilon_wrapped(epsilon):
+    """'greedy' exists in the action dict only under EpsilonGreedy (evaluate_agent.py:122-129); the goldens with
+    epsilon > 0 are the wrapped ones."""
+    return epsilon > 0.0
+
+
 def ips_table_policy(log, ps, target_table):
     """evaluate_IPS + evaluate_SNIPS (evaluate_agent.py:753-811) for pi(a) = [a == target_table[last view]]:
     -> ee list (IPS), rewards list, p_ratio list, over the bandit rows of users 0..max(u)-1."""

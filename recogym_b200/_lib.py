@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(_HERE, "librecogym_b200
 
 RG_OK, RG_EINVAL, RG_ECUDA, RG_ENOMEM, RG_ENODEVICE = 0, -1, -2, -3, -4
 ORGANIC, BANDIT, STOP = 0, 1, 2
-POLICY_UNIFORM, POLICY_TABLE, POLICY_USER_VIEWS = 0, 1, 2
+POLICY_UNIFORM, POLICY_TABLE, POLICY_USER_VIEWS, POLICY_EPS_TABLE = 0, 1, 2, 3
 MATH_EXACT, MATH_FAST, MATH_TENSOR = 0, 1, 2
 TRAIN_TEST_AGENT, TRAIN_EVOLUTION_STEP, TRAIN_EVOLUTION_INIT = 0, 1, 2
 
@@ -31,11 +31,13 @@ class EnvDesc(C.Structure):
         ("sigma_omega_initial", C.c_double), ("sigma_omega", C.c_double),
         ("change_omega_for_bandits", C.c_int32), ("reserved", C.c_int32),
         ("seed", C.c_uint64),
+        ("time_generator", C.c_int32), ("reserved2", C.c_int32),
+        ("normal_time_mu", C.c_double), ("normal_time_sigma", C.c_double),
     ]
 
 
 class Policy(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("table", C.c_void_p)]
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("table", C.c_void_p), ("epsilon", C.c_double)]
 
 
 class RolloutOut(C.Structure):
@@ -62,7 +64,7 @@ EXPORTS = (
     "rg_recall_device",
     "rg_batch_reset_device", "rg_batch_step_device", "rg_batch_continue_device",
     "rg_spec_philox", "rg_spec_exp", "rg_spec_log", "rg_spec_norm_ppf", "rg_spec_ff",
-    "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action",
+    "rg_spec_event_uniform", "rg_spec_normals", "rg_spec_policy_uniform_action", "rg_spec_time_step",
     "rg_spec_eval_device", "rg_tc_logits_device", "rg_device_count", "rg_version", "rg_last_error",
     "rg_debug_force_tier4", "rg_sparse_count_stats_device", "rg_sparse_count_policy_device",
     "rg_sparse_rehash_device",
@@ -128,6 +130,8 @@ def lib():
     L.rg_spec_normals.argtypes = [u64, u64, u32, C.c_int, vp]
     L.rg_spec_policy_uniform_action.restype = i32
     L.rg_spec_policy_uniform_action.argtypes = [u64, u64, u32, i32]
+    L.rg_spec_time_step.restype = dbl
+    L.rg_spec_time_step.argtypes = [u64, u64, u32, dbl, dbl]
     L.rg_spec_eval_device.restype = C.c_int
     L.rg_spec_eval_device.argtypes = [C.c_int, i64, vp, vp, vp]
     L.rg_debug_force_tier4.restype = C.c_int

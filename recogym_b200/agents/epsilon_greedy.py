@@ -48,9 +48,20 @@ class EpsilonGreedy(Agent):
         self.agent.reset()
 
     def device_policy(self):
-        """epsilon == 0 never explores: the wrapped agent's device policy is the policy."""
-        if float(self.config.epsilon) == 0.0 and hasattr(self.agent, "device_policy"):
-            pol = self.agent.device_policy()
-            if pol is not None and not self.config.with_ps_all:
-                return pol
+        """Around an agent that compiles to a last-view table: epsilon == 0 never explores (the wrapped agent's policy is
+        the policy); 0 < epsilon < 1 with the default selection (epsilon_pure_new, not epsilon_select_worse) is the device
+        policy RG_POLICY_EPS_TABLE -- the coin and the exploring choice are drawn from the env's policy stream (counter
+        RNG keyed by user and event time) instead of this object's RandomState, as RandomAgent's device form does."""
+        cfg = self.config
+        if not hasattr(self.agent, "device_policy") or cfg.with_ps_all:
+            return None
+        pol = self.agent.device_policy()
+        if pol is None:
+            return None
+        eps = float(cfg.epsilon)
+        if eps == 0.0:
+            return pol
+        if pol.get("policy") == "table" and 0.0 < eps < 1.0 and cfg.epsilon_pure_new and not cfg.epsilon_select_worse \
+                and int(cfg.num_products) >= 2:
+            return {**pol, "policy": "eps_table", "epsilon": eps}
         return None

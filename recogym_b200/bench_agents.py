@@ -42,7 +42,7 @@ def _collect_stats(args):
         log = generate_logs_device(train_env.device_env, args["num_offline_users"], log_pol["policy"],
                                    log_pol.get("table"), log_pol.get("ps_table"), train_begin,
                                    args["num_organic_offline_users"], L.MATH_TENSOR, prev_last_view=prev,
-                                   train_mode=L.TRAIN_TEST_AGENT)
+                                   train_mode=L.TRAIN_TEST_AGENT, epsilon=log_pol.get("epsilon", 0.0))
         new_agent.device_train(log)
         uid += args["num_organic_offline_users"] + args["num_offline_users"]
         args = {**args, "num_organic_offline_users": 0, "num_offline_users": 0}
@@ -74,7 +74,7 @@ def _collect_stats(args):
     pol = device_policy(new_agent, eval_env.config.num_products, allow_probe=args.get("allow_probe", False))
     if pol is not None:
         r = eval_env.generate_logs_counters(args["num_online_users"], pol["policy"], pol.get("table"),
-                                            user_begin=eval_begin)
+                                            user_begin=eval_begin, epsilon=pol.get("epsilon", 0.0))
         successes, failures = r["successes"], r["failures"]
     else:
         data = eval_env.generate_logs(args["num_online_users"], agent=new_agent, user_begin=eval_begin)

@@ -40,7 +40,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_env(rg_env_impl &e) {
     cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
-    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_csum_scratch); cudaFree(e.d_gsum); cudaFree(e.d_views); cudaFree(e.diag); cudaFree(e.d_t4); cudaFree(e.d_host_arena);
+    cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_csum_scratch); cudaFree(e.d_gsum); cudaFree(e.d_views); cudaFree(e.diag); cudaFree(e.d_t4); cudaFree(e.d_host_arena); cudaFree(e.d_hole_cdf);
 }
 
 int g_force_t4 = 0;   // rg_debug_force_tier4
@@ -63,9 +63,15 @@ int check_rollout_args(const rg_env *env, const rg_policy *policy, int64_t n_org
                        const rg_rollout_out *out, int math_mode) {
     if (!env || !policy || !out) return fail(RG_EINVAL, "null argument");
     if (n_organic_users < 0 || n_users < 0) return fail(RG_EINVAL, "negative user count");
-    if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE && policy->kind != RG_POLICY_USER_VIEWS)
+    if (policy->kind != RG_POLICY_UNIFORM && policy->kind != RG_POLICY_TABLE && policy->kind != RG_POLICY_USER_VIEWS &&
+        policy->kind != RG_POLICY_EPS_TABLE)
         return fail(RG_EINVAL, "unknown policy kind %d", policy->kind);
-    if (policy->kind == RG_POLICY_TABLE && !policy->table) return fail(RG_EINVAL, "table policy without table");
+    if ((policy->kind == RG_POLICY_TABLE || policy->kind == RG_POLICY_EPS_TABLE) && !policy->table)
+        return fail(RG_EINVAL, "table policy without table");
+    if (policy->kind == RG_POLICY_EPS_TABLE) {
+        if (!(policy->epsilon > 0.0 && policy->epsilon < 1.0)) return fail(RG_EINVAL, "epsilon must lie in (0, 1), got %g", policy->epsilon);
+        if (env->impl.dev.P < 2) return fail(RG_EINVAL, "an exploring policy needs at least two products");
+    }
     if (math_mode != RG_MATH_EXACT && math_mode != RG_MATH_FAST && math_mode != RG_MATH_TENSOR)
         return fail(RG_EINVAL, "unknown math mode %d", math_mode);
     return RG_OK;
@@ -237,6 +243,9 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     v.KCs = KCs;
     v.nslab = nslab;
     v.change_omega_for_bandits = d->change_omega_for_bandits ? 1 : 0;
+    v.time_mode = d->time_generator == 1 ? 1 : 0;
+    v.time_mu = d->normal_time_mu;
+    v.time_sigma = d->normal_time_sigma;
     v.seed = d->seed;
     v.t4_buf = e.d_t4;
     v.t4_lock = (int *)(e.d_t4 + (size_t)rg::kT4Slots * Ppad);
@@ -271,8 +280,24 @@ int rg_rollout_device(rg_env *env, const rg_policy *policy, int64_t user_begin, 
     if (rc != RG_OK) return rc;
     RG_CUDA(cudaSetDevice(env->impl.device));
     env->impl.dev.force_t4 = g_force_t4;
-    rg::PolicyDev pol{policy->kind, policy->table, nullptr, 0, nullptr};
+    rg::PolicyDev pol{policy->kind, policy->table, nullptr, 0, nullptr, 0.0, nullptr};
     const rg::RolloutOutDev od = to_dev(*out);
+    if (policy->kind == RG_POLICY_EPS_TABLE) {
+        // numpy: choice([True, False], p = [eps, 1 - eps]) -> cdf = [eps, eps + (1 - eps)] / cdf[-1]; explore iff u < cdf[0]
+        const double c0 = policy->epsilon, c1 = c0 + (1.0 - policy->epsilon);
+        pol.eps_c0 = c0 / c1;
+        rg_env_impl &e = env->impl;
+        if (!e.d_hole_cdf) {      // S[m] = sequential binary64 sum of m copies of 1 / (P - 1): numpy's cumsum, once per env
+            const int P = e.dev.P;
+            std::vector<double> S((size_t)P, 0.0);
+            const double c = 1.0 / (double)(P - 1);
+            double acc = 0.0;
+            for (int m = 1; m < P; ++m) { acc = acc + c; S[(size_t)m] = acc; }
+            RG_CUDA(cudaMalloc((void **)&e.d_hole_cdf, sizeof(double) * (size_t)P));
+            RG_CUDA(cudaMemcpy(e.d_hole_cdf, S.data(), sizeof(double) * (size_t)P, cudaMemcpyHostToDevice));
+        }
+        pol.hole_cdf = e.d_hole_cdf;
+    }
     if (policy->kind == RG_POLICY_USER_VIEWS) {
         // one sorted (product, views) list per resident user: 2 CTAs x 128 slots per SM in the CTA-batched kernel,
         // 64 warps per SM in the warp-per-user kernel.  A user with more than 1024 distinct views would need an
@@ -325,7 +350,8 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
                              16 * (size_t)(out->log_capacity > 0 ? out->log_capacity : 0), false);
     const size_t o_lc = add(out->log && out->log_count ? out->log_count : nullptr, 8, true);
     const size_t o_tab = total;
-    if (policy->kind == RG_POLICY_TABLE) total += ((size_t)4 * P + 255) & ~(size_t)255;
+    const bool has_table = policy->kind == RG_POLICY_TABLE || policy->kind == RG_POLICY_EPS_TABLE;
+    if (has_table) total += ((size_t)4 * P + 255) & ~(size_t)255;
     // The staging arena belongs to the env and only ever grows: no cudaMalloc / cudaFree (an implicit device
     // synchronisation each) on the call path.  Only the ACCUMULATED outputs need zeroing -- every per-user entry and
     // every log row below *log_count is written by the kernel.
@@ -345,7 +371,7 @@ int rg_rollout_host(rg_env *env, const rg_policy *policy, int64_t user_begin, in
     for (const Seg &s : segs)
         if (s.accumulate && ce == cudaSuccess) ce = cudaMemsetAsync(arena + s.off, 0, s.bytes, 0);
     rg_policy pd = *policy;
-    if (ce == cudaSuccess && policy->kind == RG_POLICY_TABLE) {
+    if (ce == cudaSuccess && has_table) {
         ce = cudaMemcpyAsync(arena + o_tab, policy->table, (size_t)4 * P, cudaMemcpyHostToDevice, 0);
         pd.table = (const int32_t *)(arena + o_tab);
     }
@@ -442,7 +468,9 @@ int rg_generate_logs_device(rg_env *env, const rg_policy *policy, const double *
                               (int4 *)(arena + o_ord), cap, env->impl.num_sms, stream);
     if (ce == cudaSuccess)
         ce = rg::launch_columns((const int4 *)(arena + o_ord), ro, n, n_organic_users, user_begin, lv, prev_last_view,
-                                policy->kind, env->impl.dev.P, ps_table_device, *cols, train_mode, carry_device,
+                                policy->kind, env->impl.dev.P, ps_table_device, policy->table, policy->epsilon,
+                                env->impl.dev.time_mode, env->impl.dev.seed, env->impl.dev.time_mu, env->impl.dev.time_sigma, *cols,
+                                train_mode, carry_device,
                                 env->impl.num_sms, stream);
     cudaFreeAsync(arena, stream);
     if (ce != cudaSuccess) return fail(RG_ECUDA, "generate_logs failed: %s", cudaGetErrorString(ce));
@@ -610,6 +638,9 @@ void rg_spec_normals(uint64_t seed, uint64_t user, uint32_t t, int K, double *z)
         z[2 * j] = rg::normal_from_words(w.x, w.y);
         if (2 * j + 1 < K) z[2 * j + 1] = rg::normal_from_words(w.z, w.w);
     }
+}
+double rg_spec_time_step(uint64_t seed, uint64_t user, uint32_t call, double mu, double sigma) {
+    return rg::time_step(seed, user, call, mu, sigma);
 }
 int32_t rg_spec_policy_uniform_action(uint64_t seed, uint64_t user, uint32_t t, int32_t P) {
     return rg::uniform_action(rg::draw(seed, user, t, rg::SLOT_POLICY).x, P);

@@ -27,6 +27,8 @@ struct EnvDev {
     const float *GTC;          // [tiles][nslab][2][KCs][TILE_N/8][8][4] tf32 hi/lo UMMA tiles in K slabs (rg_tensor.cuh)
     int KC, KCs, nslab;        // 16-byte K chunks per operand row: padded total, per slab, slabs (KC = KCs * nslab)
     int change_omega_for_bandits;
+    int time_mode;             // 0 default clock, 1 NormalTimeGenerator (include/recogym_b200.h rg_env_desc.time_generator)
+    double time_mu, time_sigma;
     uint64_t seed;
     // tier 4 (oracle-order re-draw of the draws no binary64 summation order can separate, warp_sample_view_oracle_order)
     double *t4_buf;            // [kT4Slots][Ppad] scratch of masses, one slot per concurrent re-draw
@@ -43,7 +45,27 @@ struct PolicyDev {
     int2 *views;           // [lists][view_cap]
     int view_cap;
     unsigned long long *view_overflow;  // counts users whose distinct views exceeded view_cap (results invalid)
+    // RG_POLICY_EPS_TABLE: coin threshold eps / (eps + (1 - eps)) and the hole-CDF table of the exploring draw
+    double eps_c0;
+    const double *hole_cdf;             // [P]: S[m] = sequential sum of m copies of 1 / (P - 1) (oracle.hole_cdf_table)
 };
+
+// EpsilonGreedy.act around a table agent (agents/epsilon_greedy.py:30-68; oracle/rg_oracle.c eps_table_act): the coin on
+// the first uniform of the policy stream, the exploring action by numpy's choice(P, p) on the second one, with
+// p = ones(P), p[greedy] = 0, p /= sum.  The cdf of that p is cdf[j] = S[j + 1] for j < greedy and S[j] for j >= greedy
+// (adding the hole's exact 0 changes nothing), so the inverse cdf is a binary search in ONE table per P.
+__device__ __forceinline__ int eps_table_action(const PolicyDev &pol, int P, int last_view, const u32x4 &w) {
+    const int g = __ldg(pol.table + last_view);
+    if (pol.eps_c0 <= uniform53(w.x, w.y)) return g;          // searchsorted(right) == 1 -> False -> exploit
+    const double u = uniform53(w.z, w.w), last = __ldg(pol.hole_cdf + P - 1);
+    int lo = 0, hi = P;                                        // smallest j with cdf[j] / last > u
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double cdf = __ldg(pol.hole_cdf + (mid < g ? mid + 1 : mid));
+        if (cdf / last <= u) lo = mid + 1; else hi = mid;
+    }
+    return lo < P ? lo : P - 1;
+}
 
 // ViewsFeaturesProvider.observe (agents/abstract.py:340-351): views[0, v] += 1 on the sparse sorted list.
 __device__ __forceinline__ void views_insert(int2 *list, int &d, int cap, int v, unsigned long long *overflow) {

@@ -25,6 +25,7 @@ struct rg_env_impl {
     unsigned long long *diag = nullptr;  // [4] device diagnostics (f64-ambiguous samples, ...)
     char *d_host_arena = nullptr;        // rg_rollout_host: device staging of the table and the outputs, grown on demand
     size_t host_arena_bytes = 0;
+    double *d_hole_cdf = nullptr;        // RG_POLICY_EPS_TABLE: [P] table of the exploring draw's cdf (built on first use)
     double *d_t4 = nullptr;              // tier 4 (oracle-order re-draw): [kT4Slots][Ppad] masses + kT4Slots int locks
 };
 
@@ -52,8 +53,9 @@ cudaError_t launch_order(const int4 *log, const unsigned long long *log_count, l
                          cudaStream_t stream);
 cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, long long n_total,
                            long long n_organic_users, long long user_begin, const int32_t *last_view, int prev_last_view,
-                           int policy_kind, int P, const double *ps_table, const rg_log_columns &c, int train_mode,
-                           int32_t *carry_out, int num_sms, cudaStream_t stream);
+                           int policy_kind, int P, const double *ps_table, const int32_t *table, double epsilon,
+                           int time_mode, uint64_t seed, double time_mu, double time_sigma,
+                           const rg_log_columns &c, int train_mode, int32_t *carry_out, int num_sms, cudaStream_t stream);
 cudaError_t launch_count_stats(const rg_log_columns &c, long long rows, int P, int train_mode, int64_t *co,
                                int64_t *pulls, int64_t *clicks, int num_sms, cudaStream_t stream);
 cudaError_t launch_row_argmax(int kind, int P, const int64_t *A, const int64_t *B, int32_t *table, double *ps,

@@ -39,7 +39,7 @@ __device__ __forceinline__ int organic_event(const EnvDev &env, const WarpCtx &w
     state = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
     t += 1;
     if (env.change_omega_for_bandits || state == RG_ORGANIC)
-        warp_omega_update(wc.omega, env.K, env.sigma * 1.0, false, env.seed, user, t, lane);
+        warp_omega_update(wc.omega, env.K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t, lane);
     return v;
 }
 
@@ -51,7 +51,7 @@ __device__ __forceinline__ int bandit_event(const EnvDev &env, const WarpCtx &wc
     state = next_state(env, RG_BANDIT, uniform53(w.z, w.w));
     t += 1;
     if (env.change_omega_for_bandits || state == RG_ORGANIC)
-        warp_omega_update(wc.omega, env.K, env.sigma * 1.0, false, env.seed, user, t, lane);
+        warp_omega_update(wc.omega, env.K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t, lane);
     if (click) state = RG_ORGANIC;  // abstract.py:180-181: a click overrides any transition, incl. stop
     return click;
 }
@@ -60,6 +60,7 @@ __device__ __forceinline__ int policy_action(const EnvDev &env, const PolicyDev 
                                              int last_view, const int2 *vlist, int nd, int nviews) {
     if (pol.kind == RG_POLICY_TABLE) return __ldg(pol.table + last_view);
     const u32x4 w = draw(env.seed, user, t, SLOT_POLICY);
+    if (pol.kind == RG_POLICY_EPS_TABLE) return eps_table_action(pol, env.P, last_view, w);
     if (pol.kind == RG_POLICY_USER_VIEWS) return views_action(vlist, nd, nviews, uniform53(w.z, w.w));
     return uniform_action(w.x, env.P);
 }

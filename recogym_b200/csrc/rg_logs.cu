@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
                                                       long long n_organic_users, long long user_begin,
                                                       const int32_t *__restrict__ last_view, int prev_last_view,
                                                       int policy_kind, int P, const double *__restrict__ ps_table,
+                                                      const int32_t *__restrict__ table, double epsilon,
+                                                      int time_mode, uint64_t seed, double time_mu, double time_sigma,
                                                       long long capacity, int train_mode, Columns col) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -189,11 +191,26 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
         }
         const long long last_real = warp_find_last(ordered, r0, r1, lane, [](const int4 &q) { return (q.w & 1) && !(q.w & 4); });
         int run = 0;                                     // organic rows immediately before this chunk (open session)
+        double clock = 0.0;                              // NormalTimeGenerator: the clock after the rows before this chunk
         for (long long b = r0; b < r1; b += 32) {
             const long long r = b + lane;
             const bool ok = r < r1;
             int4 rec = make_int4(0, 0, 0, 1);
             if (ok) rec = ordered[r];
+            // The row's clock value.  Default clock: the event index.  NormalTimeGenerator (normal_time_generator.py:25-28,
+            // abstract.py:100, reco_env_v1.py:91): the clock of event index t is the SEQUENTIAL binary64 sum of the steps
+            // of the calls 0 .. t-1 -- every lane draws its row's step, the warp then accumulates them one after the
+            // other, each lane keeping the value at its own row.
+            float tval = (float)rec.y;
+            if (time_mode == 1) {
+                const double st = (ok && rec.y > 0) ? time_step(seed, (uint64_t)(user_begin + i), (uint32_t)rec.y - 1u, time_mu, time_sigma) : 0.0;
+                double mine = clock;
+                for (int k = 0; k < 32; ++k) {
+                    clock += __shfl_sync(0xffffffffu, st, k);
+                    if (lane == k) mine = clock;
+                }
+                tval = (float)mine;
+            }
             const bool org = ok && !(rec.w & 1);
             const bool ban = ok && (rec.w & 1);
             const unsigned om = __ballot_sync(0xffffffffu, org);
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
             // distance to the session start: organic rows since the last bandit row
             const int since = bmlt ? lane - (31 - __clz(bmlt)) - 1 : lane + run;
             if (ok) {
-                if (col.t) col.t[r] = (float)rec.y;
+                if (col.t) col.t[r] = tval;
                 if (col.u) col.u[r] = (int32_t)(user_begin + i);
                 if (col.z) col.z[r] = org ? 0 : 1;
                 if (col.v) col.v[r] = org ? rec.z : -1;
@@ -230,6 +247,12 @@ __global__ void __launch_bounds__(256) columns_kernel(const int4 *__restrict__ o
                     if (!org) {
                         if (policy_kind == RG_POLICY_UNIFORM) ps = 1.0 / (double)P;   // abstract.py:219
                         else if (policy_kind == RG_POLICY_TABLE) ps = ps_table ? (lv >= 0 && lv < P ? ps_table[lv] : dnan) : 1.0;
+                        else if (policy_kind == RG_POLICY_EPS_TABLE && lv >= 0 && lv < P) {
+                            // epsilon_greedy.py:44-68: exploit -> (1 - eps) * the wrapped agent's ps; explore -> eps * p[a],
+                            // p = ones with a hole / sum = 1 / (P - 1).  An action is greedy iff it is table[lv].
+                            const double ps_greedy = ps_table ? ps_table[lv] : 1.0;
+                            ps = rec.z == table[lv] ? (1.0 - epsilon) * ps_greedy : epsilon * (1.0 / (double)(P - 1));
+                        }
                     }
                     col.ps[r] = ps;
                 }
@@ -590,7 +613,9 @@ cudaError_t launch_order(const int4 *log, const unsigned long long *log_count, l
 
 cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, long long n_total,
                            long long n_organic_users, long long user_begin, const int32_t *last_view, int prev_last_view,
-                           int policy_kind, int P, const double *ps_table, const rg_log_columns &c, int train_mode,
+                           int policy_kind, int P, const double *ps_table, const int32_t *table, double epsilon,
+                           int time_mode, uint64_t seed, double time_mu, double time_sigma,
+                           const rg_log_columns &c, int train_mode,
                            int32_t *carry_out, int num_sms, cudaStream_t stream) {
     if (n_total <= 0) {
         if (carry_out) return cudaMemcpyAsync(carry_out, &prev_last_view, 4, cudaMemcpyHostToDevice, stream);
@@ -600,7 +625,8 @@ cudaError_t launch_columns(const int4 *ordered, const long long *row_offset, lon
     long long blocks = (n_total + 7) / 8;
     if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
     columns_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ordered, row_offset, n_total, n_organic_users, user_begin,
-                                                         last_view, prev_last_view, policy_kind, P, ps_table, c.capacity,
+                                                         last_view, prev_last_view, policy_kind, P, ps_table, table, epsilon,
+                                                         time_mode, seed, time_mu, time_sigma, c.capacity,
                                                          train_mode, col);
     if (carry_out)
         carry_kernel<<<1, 32, 0, stream>>>(ordered, row_offset, last_view, n_total, n_organic_users, prev_last_view,

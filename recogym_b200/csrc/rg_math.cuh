@@ -19,6 +19,7 @@ namespace rg {
 constexpr uint32_t SLOT_EVENT = 0u;     // words 0,1: view/click uniform; words 2,3: transition uniform
 constexpr uint32_t SLOT_POLICY = 1u;    // word 0: uniform logging-policy action; RG_POLICY_USER_VIEWS: words 0,1 =
                                         // the explore coin's uniform, words 2,3 = the action's uniform
+constexpr uint32_t SLOT_TIME = 2u;      // NormalTimeGenerator: words 0,1 -> the normal behind the clock step of event index t
 constexpr uint32_t SLOT_NORMAL = 0x100u; // + j : normals 2j, 2j+1 of omega init (t=0) / drift into t
 
 struct u32x4 { uint32_t x, y, z, w; };
@@ -124,29 +125,31 @@ RG_HD double log64(double x) {
     return fma(de, kLn2Hi, fma(de, kLn2Lo, lm));
 }
 
-// Standard normal quantile, Wichura's AS241 (PPND16), rational evaluation with fma.
-RG_HD double norm_ppf(double p) {
-    const double q = p - 0.5;
-    if (fabs(q) <= 0.425) {
-        const double r = 0.180625 - q * q;
-        double n = 2509.0809287301226727;
-        n = fma(n, r, 33430.575583588128105);
-        n = fma(n, r, 67265.770927008700853);
-        n = fma(n, r, 45921.953931549871457);
-        n = fma(n, r, 13731.693765509461125);
-        n = fma(n, r, 1971.5909503065514427);
-        n = fma(n, r, 133.14166789178437745);
-        n = fma(n, r, 3.387132872796366608);
-        double d = 5226.495278852545925;
-        d = fma(d, r, 28729.085735721942674);
-        d = fma(d, r, 39307.89580009271061);
-        d = fma(d, r, 21213.794301586595867);
-        d = fma(d, r, 5394.1960214247511077);
-        d = fma(d, r, 687.1870074920579083);
-        d = fma(d, r, 42.313330701600911252);
-        d = fma(d, r, 1.0);
-        return q * n / d;
-    }
+// Standard normal quantile, Wichura's AS241 (PPND16), rational evaluation with fma.  Split into its central branch
+// (|p - 1/2| <= 0.425, 85 % of the draws) and its tail branches so that a warp can evaluate the two separately (the rollout
+// gathers the tail cases of a warp onto a few lanes instead of running both branches under divergence); norm_ppf is the
+// composition, operation for operation.
+RG_HD double norm_ppf_central(double q) {
+    const double r = 0.180625 - q * q;
+    double n = 2509.0809287301226727;
+    n = fma(n, r, 33430.575583588128105);
+    n = fma(n, r, 67265.770927008700853);
+    n = fma(n, r, 45921.953931549871457);
+    n = fma(n, r, 13731.693765509461125);
+    n = fma(n, r, 1971.5909503065514427);
+    n = fma(n, r, 133.14166789178437745);
+    n = fma(n, r, 3.387132872796366608);
+    double d = 5226.495278852545925;
+    d = fma(d, r, 28729.085735721942674);
+    d = fma(d, r, 39307.89580009271061);
+    d = fma(d, r, 21213.794301586595867);
+    d = fma(d, r, 5394.1960214247511077);
+    d = fma(d, r, 687.1870074920579083);
+    d = fma(d, r, 42.313330701600911252);
+    d = fma(d, r, 1.0);
+    return q * n / d;
+}
+RG_HD double norm_ppf_tail(double p, double q) {
     double r = (q < 0.0) ? p : 1.0 - p;
     r = sqrt(-log64(r));
     double val;
@@ -191,11 +194,30 @@ RG_HD double norm_ppf(double p) {
     }
     return (q < 0.0) ? -val : val;
 }
+RG_HD double norm_ppf(double p) {
+    const double q = p - 0.5;
+    if (fabs(q) <= 0.425) return norm_ppf_central(q);
+    return norm_ppf_tail(p, q);
+}
 
 // standard normal from two words: 52-bit m, p = (2m+1)/2^53 lies strictly inside (0,1).
-RG_HD double normal_from_words(uint32_t a, uint32_t b) {
+RG_HD double normal_p_from_words(uint32_t a, uint32_t b) {   // the probability whose quantile is the normal
     const uint64_t m = ((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6);
-    return norm_ppf((double)(2 * m + 1) * (1.0 / 9007199254740992.0));
+    return (double)(2 * m + 1) * (1.0 / 9007199254740992.0);
+}
+RG_HD double normal_from_words(uint32_t a, uint32_t b) { return norm_ppf(normal_p_from_words(a, b)); }
+
+// NormalTimeGenerator.new_time() (normal_time_generator.py:25-28): the clock step taken by the `call`-th call of this user,
+// |mu + sigma * z|; call i moves the clock from event index i to i + 1.
+RG_HD double time_step(uint64_t seed, uint64_t user, uint32_t call, double mu, double sigma) {
+    const u32x4 w = draw(seed, user, call, SLOT_TIME);
+    return fabs(mu + sigma * normal_from_words(w.x, w.y));
+}
+// omega_k of RecoEnv1.update_state (reco_env_v1.py:89-93) for the update INTO event index t (t >= 1)
+RG_HD double omega_k_into(int time_mode, uint64_t seed, uint64_t user, uint32_t t, double mu, double sigma) {
+    if (time_mode == 0) return 1.0;
+    const double dt = time_step(seed, user, t - 1u, mu, sigma);
+    return dt == 0.0 ? 1.0 : dt;
 }
 
 RG_HD double sigmoid64(double x) { return 1.0 / (1.0 + exp64(-x)); }  // reco_env_v1.py:32-34

@@ -242,6 +242,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // issue slots per exponential; with two co-resident CTAs sharing the schedulers the kernel got 10 % slower, 4.6e8 vs
 // 5.1e8 user-steps/s at C3.)
 
+// (Measured and dropped in round 2, all parity-green on B200 at C3: issuing the Gamma loads of all five k steps of a sweep
+// step before its first DMMA, with the epilogue's mu values prefetched -- 43.0k vs 37.8k cycles per round: the sweep is bound
+// by the FP64 pipe, 6250 DMMA per sweep, not by its load latency; a dedicated tenth warp that ran the tier 2/3 sweeps
+// asynchronously, off the round's critical path, with a ring of queued draws -- one scheduler then carries all the FP64
+// work and starves its two epilogue warps: 5.2e8 vs 7.0e8 user-steps/s; gathering the tail branch of the normal quantile
+// onto a few lanes of each warp in the omega phase -- 22.6k vs 18.2k cycles per round.)
 // ---- scalar (one thread per user) pieces --------------------------------------------------------
 // omega init / drift by ONE thread: same operation sequence as warp_omega_update.
 __device__ __forceinline__ void thread_omega_update(double *omega, int K, double scale, bool init, uint64_t seed,
@@ -427,6 +433,7 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
     const int lane = tid & 31, warp = tid >> 5, nwarps = gn >> 5;
     auto gsync = [&]() {
         if (bar_id == 0) cta_sync();
+        else if (bar_id < 0) __syncwarp();                       // a single warp (the tensor-mode re-sampling warp)
         else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gn) : "memory");
     };
     double *esum = csum + (size_t)FB * ncs;
@@ -450,7 +457,11 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
         om_s[idx] = k < K ? om64[(size_t)slots[f < nb ? f : nb - 1] * KP + k] : 0.0;
     }
     gsync();
+#ifdef RG_T2_DFMA
+    if (false) {
+#else
     if (T2) {   // FP64 tensor path (any nb <= 8 in one pass)
+#endif
         if (K <= 20) batch_partial_sums_mma<5>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
         else if (K <= 32) batch_partial_sums_mma<8>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
         else if (K <= 64) batch_partial_sums_mma<16>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
@@ -617,7 +628,7 @@ __global__ void lpt_ctr_kernel(const EnvDev env, const PolicyDev pol, double *__
     __shared__ double sh[8];
     double s = 0.0;
     for (int v = threadIdx.x; v < env.P; v += blockDim.x) {
-        const int a = pol.kind == RG_POLICY_TABLE ? __ldg(pol.table + v) : v;
+        const int a = (pol.kind == RG_POLICY_TABLE || pol.kind == RG_POLICY_EPS_TABLE) ? __ldg(pol.table + v) : v;
         s += ff64(__ldg(env.mu_b + a));
     }
     s = warp_sum(s);
@@ -714,6 +725,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
     auto policy_act = [&](int slot, uint64_t user, uint32_t t, int last_view, int n_org) -> int {
         if (p.pol.kind == RG_POLICY_TABLE) return __ldg(p.pol.table + last_view);
         const u32x4 w = draw(p.env.seed, user, t, SLOT_POLICY);
+        if (p.pol.kind == RG_POLICY_EPS_TABLE) return eps_table_action(p.pol, p.env.P, last_view, w);
         if (p.pol.kind == RG_POLICY_USER_VIEWS)
             return views_action(vlists + (size_t)slot * p.pol.view_cap, s_nview[slot], n_org, uniform53(w.z, w.w));
         return uniform_action(w.x, p.env.P);
@@ -759,7 +771,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             // MMA -> commit "accumulator ready" after the last slab.  Every scalar instruction of this loop is on the
             // critical path of pass 1: ring stage, accumulator buffer and their phase bits are carried incrementally,
             // descriptors are additions to a precomputed low word, the MMA sequence is unrolled for the slab size.
-            issuer_sync();   // set-up done
+            issuer_sync();   // set-up done (barriers initialised, TMEM allocated)
             tc::tc_fence_after();
             const uint32_t tmem_u = *(volatile uint32_t *)tmem_slot;
             const uint32_t mbar_s = smem_u32(mbar), dfull_s = smem_u32(dfull), dempty_s = smem_u32(dempty);
@@ -864,7 +876,8 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             const int slot = pend_list[task / npairs], j = task - (task / npairs) * npairs;
             const bool init = s_pend[slot] == 2;
             double *om = om64 + (size_t)slot * KP;
-            const double scale = init ? env.sigma0 : env.sigma * 1.0;
+            const double scale = init ? env.sigma0
+                                      : env.sigma * omega_k_into(env.time_mode, env.seed, s_user[slot], s_t[slot], env.time_mu, env.time_sigma);
             const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_NORMAL + (uint32_t)j);
             const double z0 = normal_from_words(w.x, w.y);
             om[2 * j] = (init ? 0.0 : om[2 * j]) + scale * z0;
@@ -920,8 +933,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             int base = 0;
             for (int c = 0; c < TU / 32; ++c) {
                 const int slot = c * 32 + lane;
-                if (s_wait[slot] == 2) s_wait[slot] = 1;  // queued last round: re-sampled during this pass 1
-                const bool lv = s_live[slot] != 0 && s_wait[slot] == 0;
+                const bool lv = s_live[slot] != 0 && s_wait[slot] == 0;   // s_wait: the slot's draw is queued for a re-sampling sweep
                 const unsigned m = __ballot_sync(0xffffffffu, lv);
                 if (lv) pos2slot[base + __popc(m & ((1u << lane) - 1u))] = slot;
                 base += __popc(m);
@@ -1045,6 +1057,11 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                 float *gs_row = gsum_cta + pos;
                 float *ts_row = tilesum + (size_t)pos * p.nrec_pad + grp;
                 int tt = grp;
+#ifdef RG_X_DEPHASE
+                // experiment: start the second warp group late, so that the two groups' waits for their accumulators do
+                // not coincide (they are released into pass 1 by the same barrier and would otherwise stay in lockstep)
+                if (grp) { const long long d0 = clock64(); while (clock64() - d0 < (long long)(RG_X_DEPHASE)) { } }
+#endif
                 for (int rec = 0; rec < p.nrec; ++rec) {
                     const int rec_end = min((rec + 1) * tiles_per_rec, ntile);
                     float part = 0.f;
@@ -1171,143 +1188,155 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
 
         RG_MARK(2);   // B: pass 1 (A tile, tiles, omega tile of pass 2)
         { const long long tk1 = clock64(); ph_b += (unsigned long long)(tk1 - tk0); tk0 = tk1; }
-        // ---- C: pass 2a, one thread per live user: view uniform, total mass, tau = u*Z, the record tile that
-        // contains tau and the mass before it (sequential binary64 sums of the fp32 tile sums)
-        if (tid < nlive) {
+        if constexpr (TC) {
+            // ---- C: pass 2 (tensor mode).  Stage A, one thread per live user: view uniform, total mass, tau = u Z, the
+            // record tile that contains tau (sequential binary64 sums of the fp32 partial sums).  Stage B, EIGHT LANES per
+            // user (four users per warp at a time, 32 per CTA pass): the crossing 32-product GROUP inside the record from
+            // the pass-1 group sums the epilogue kept, then the group's 32 masses recomputed in natural product order --
+            // lane q owns products 4q .. 4q+3, one 16-byte load per k, so that the eight lanes of a user read one whole
+            // 128-byte row segment of the Gamma tile per k (fully coalesced: a thread-private layout costs 8x the L1
+            // wavefronts) -- fp32 FMA chains over k as in pass 1's error model -> index, CDF margins, filter.
+            if (tid < nlive) {
+                const int i = tid, slot = pos2slot[i];
+                const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
+                const double u = uniform53(w.x, w.y);
+                const float *ts = tilesum + (size_t)i * p.nrec_pad;
+                double Z = 0.0;
+                for (int r = 0; r < p.nrec; ++r) Z += (double)ts[2 * r] + (double)ts[2 * r + 1];
+                const double tau = u * Z;
+                double cum = 0.0;
+                int rsel = -1;
+                for (int r = 0; r < p.nrec; ++r) {
+                    const double nx = cum + ((double)ts[2 * r] + (double)ts[2 * r + 1]);
+                    if (nx > tau) { rsel = r; break; }
+                    cum = nx;
+                }
+                s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel; s_u[i] = u;
+            }
+            cta_sync();
+            RG_MARK(3);   // C: pass 2, stage A
+            const int sub = lane & 7, seg = lane & ~7;
+            for (int ib = 0; ib < nlive; ib += NTH / 8) {
+                const int i = ib + (tid >> 3);
+                if (i >= nlive) continue;                       // whole 8-lane segments drop out
+                const unsigned pm = 0xffu << seg;               // every collective below is over this user's eight lanes only
+                const int rsel = s_rsel[i];
+                const double tau = s_tau[i];
+                double cum = s_cum[i];
+                const int p0 = max(rsel, 0) * p.rec_sub * SUB;
+                const int ngr = rsel < 0 ? 0 : (min(p0 + p.rec_sub * SUB, nsub * SUB) - p0) / 32;
+                const float *gs = gsum_cta + (size_t)(p0 / 32) * TU + i;
+                // crossing group: 32 groups per step, lane q holds the groups q, q+8, q+16, q+24 of the step
+                int gsel = -1;
+                double gmass = 0.0;
+                for (int g0 = 0; g0 < ngr && gsel < 0; g0 += 32) {
+                    float x[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { const int g = g0 + 8 * b + sub; x[b] = g < ngr ? __ldcg(gs + (size_t)g * TU) : 0.f; }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (gsel >= 0 || g0 + 8 * b >= ngr) continue;          // uniform over the segment
+                        const double own = (double)x[b];
+                        double xs = own;
+#pragma unroll
+                        for (int d = 1; d < 8; d <<= 1) {
+                            const double y = __shfl_up_sync(pm, xs, d, 8);
+                            if (sub >= d) xs += y;
+                        }
+                        const unsigned m = (__ballot_sync(pm, cum + xs > tau && g0 + 8 * b + sub < ngr) >> seg) & 0xffu;
+                        if (m) {
+                            const int fl = __ffs(m) - 1;
+                            gsel = g0 + 8 * b + fl;
+                            cum += __shfl_sync(pm, xs - own, seg + fl);          // groups before the crossing one
+                            gmass = __shfl_sync(pm, own, seg + fl);
+                        } else {
+                            cum += __shfl_sync(pm, xs, seg + 7);
+                        }
+                    }
+                }
+                // recompute the group: one float4 of Gamma per k and lane, FFMA chains over k
+                const int pj0 = p0 + max(gsel, 0) * 32 + 4 * sub;
+                const float *gp = env.G32 + (size_t)(pj0 >> 7) * K1 * SUB + (pj0 & (SUB - 1));
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 7
+                for (int k = 0; k < K1; ++k) {
+                    const float wk = om32[k * TU + i];
+                    const float4 g = __ldg(reinterpret_cast<const float4 *>(gp + k * SUB));
+                    a0 = fmaf(wk, g.x, a0); a1 = fmaf(wk, g.y, a1); a2 = fmaf(wk, g.z, a2); a3 = fmaf(wk, g.w, a3);
+                }
+                const float shf = s_shift[i];
+                const double m0 = (double)ex2_approx(a0 - shf), m1 = (double)ex2_approx(a1 - shf);
+                const double m2 = (double)ex2_approx(a2 - shf), m3 = (double)ex2_approx(a3 - shf);
+                const double l0 = m0, l1 = l0 + m1, l2 = l1 + m2, l3 = l2 + m3;     // this lane's inclusive prefixes
+                double xs = l3;
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    const double y = __shfl_up_sync(pm, xs, d, 8);
+                    if (sub >= d) xs += y;
+                }
+                const double gtot = __shfl_sync(pm, xs, seg + 7);       // recomputed mass of the whole group
+                const double base = cum + (xs - l3);                    // mass before this lane's first product
+                int fnd = -1;
+                double lo = 0.0, up = 0.0;
+                if (base + l0 > tau && pj0 < P) { fnd = pj0; lo = base; up = base + l0; }
+                else if (base + l1 > tau && pj0 + 1 < P) { fnd = pj0 + 1; lo = base + l0; up = base + l1; }
+                else if (base + l2 > tau && pj0 + 2 < P) { fnd = pj0 + 2; lo = base + l1; up = base + l2; }
+                else if (base + l3 > tau && pj0 + 3 < P) { fnd = pj0 + 3; lo = base + l2; up = base + l3; }
+                const unsigned mf = (__ballot_sync(pm, fnd >= 0) >> seg) & 0xffu;
+                const int first = mf ? __ffs(mf) - 1 : 0;
+                if (sub == first) {      // the lane that holds the crossing (lane 0 of the segment if there is none)
+                    const int slot = pos2slot[i];
+                    bool amb = gsel < 0 || mf == 0u;   // (a recomputed group lighter than its pass-1 sum by a rounding: ambiguous)
+                    const double Z = s_Z[i], uu = s_u[i];
+                    if (!amb) {
+                        // Filter.  Every computed mass is within d (relative) of the exact one; the SAME pass-1 masses enter
+                        // the prefix sum S^ and the total Z^, so their errors largely cancel in S^ - u Z^:
+                        //   |(S^ - u Z^) - (S - u Z)| <= d [(1-u) S + u (Z - S)] + 2 u d m(G) + u g m(T)
+                        // G = the crossing group, whose products are counted with their pass-1 value in Z^ and with their
+                        // recomputed value in S^; T = the crossing record tile, whose earlier groups enter S^ as group sums
+                        // and Z^ through the fp32 chain of the record sum: g = (adds of that chain) 2^-24.
+                        const double dlt = (double)s_eps[i];
+                        const float *ts = tilesum + (size_t)i * p.nrec_pad + 2 * rsel;
+                        const double tmass = (double)ts[0] + (double)ts[1];
+                        const double gm = fmax(gmass, gtot);
+                        const double grec = (double)(p.rec_sub * 4 + 4) * 5.9604644775390625e-08 * tmass;
+                        const double tl = dlt * ((1.0 - uu) * lo + uu * fmax(Z - lo, 0.0) + 2.0 * uu * gm) + uu * grec + 1e-10 * Z;
+                        const double tu = dlt * ((1.0 - uu) * up + uu * fmax(Z - up, 0.0) + 2.0 * uu * gm) + uu * grec + 1e-10 * Z;
+                        amb = (tau - lo < tl && fnd > 0) || (up - tau < tu && fnd < P - 1);
+                    }
+                    s_view[slot] = fnd;
+                    if (amb) {   // queued for a re-sampling sweep; the slot sits out until its draw has been resolved
+                        const double lse = log64(Z) * 1.4426950408889634074 + (double)shf;
+                        const int e = atomicAdd(&misc[6], 1);
+                        rq_slot[e] = slot; rq_u[e] = uu; rq_lse[e] = lse;
+                        s_wait[slot] = 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- C: pass 2a (CUDA-core form), one thread per live user: view uniform, total mass, tau = u*Z, the record tile
+        // that contains tau and the mass before it (sequential binary64 sums of the fp32 tile sums)
+        if (!TC && tid < nlive) {
             const int i = tid, slot = pos2slot[i];
             const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_EVENT);
             const double u = uniform53(w.x, w.y);
             const float *ts = tilesum + (size_t)i * p.nrec_pad;
-            // TC: a record tile's mass is kept as two fp32 partial sums (one per column half / epilogue warp)
-            auto rec_mass = [&](int r) -> double { return TC ? (double)ts[2 * r] + (double)ts[2 * r + 1] : (double)ts[r]; };
             double Z = 0.0;
-            for (int r = 0; r < p.nrec; ++r) Z += rec_mass(r);
+            for (int r = 0; r < p.nrec; ++r) Z += (double)ts[r];
             const double tau = u * Z;
             double cum = 0.0;
             int rsel = -1;
             for (int r = 0; r < p.nrec; ++r) {
-                const double nx = cum + rec_mass(r);
+                const double nx = cum + (double)ts[r];
                 if (nx > tau) { rsel = r; break; }
                 cum = nx;
             }
             s_Z[i] = Z; s_tau[i] = tau; s_cum[i] = cum; s_rsel[i] = rsel; s_u[i] = u;
         }
-        cta_sync();
+        if (!TC) cta_sync();
         RG_MARK(3);   // C: pass 2a
 
-        // ---- C: pass 2b (tensor mode), one warp per UI live users at a time: locate the crossing 32-product group with
-        // the pass-1 group sums the epilogue kept, recompute only that group (one product per lane) for the index and its
-        // margins, filter.  Every step is a latency chain (L2 loads, shuffles, binary64 adds): UI users are interleaved.
-        if constexpr (TC) {
-            constexpr int UI = 4;
-            for (int ib = warp * UI; ib < nlive; ib += NWARP * UI) {
-                int ii[UI], rs[UI], p0[UI], ngr[UI], gsel[UI], found[UI];
-                double cum[UI], lower[UI], upper[UI];
-#pragma unroll
-                for (int u = 0; u < UI; ++u) {
-                    ii[u] = min(ib + u, nlive - 1);          // surplus lanes of the last group repeat the last user
-                    rs[u] = s_rsel[ii[u]];
-                    cum[u] = s_cum[ii[u]];
-                    p0[u] = max(rs[u], 0) * p.rec_sub * SUB;
-                    ngr[u] = (min(p0[u] + p.rec_sub * SUB, nsub * SUB) - p0[u]) / 32;
-                    gsel[u] = -1; found[u] = -1; lower[u] = 0.0; upper[u] = 0.0;
-                }
-                // the 32-product groups of the record tile (these group sums are the very terms the record-tile sum
-                // was built from, up to the fp32 rounding of that chain, which the mass-error bound accounts for)
-                const int ngr_max = p.rec_sub * (SUB / 32);
-                for (int g0 = 0; g0 < ngr_max; g0 += 32) {
-                    double x[UI];
-#pragma unroll
-                    for (int u = 0; u < UI; ++u) {
-                        const int gi = g0 + lane;
-                        const bool need = rs[u] >= 0 && gsel[u] < 0 && gi < ngr[u];
-                        x[u] = need ? (double)__ldcg(gsum_cta + (size_t)(p0[u] / 32 + gi) * TU + ii[u]) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < UI; ++u) {
-                        if (rs[u] < 0 || gsel[u] >= 0 || g0 >= ngr[u]) continue;   // warp-uniform
-                        const double own = x[u];
-                        double xs = own;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const double y = __shfl_up_sync(0xffffffffu, xs, d);
-                            if (lane >= d) xs += y;
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, (cum[u] + xs > s_tau[ii[u]]) && (g0 + lane < ngr[u]));
-                        if (m) {
-                            const int fl = __ffs(m) - 1;
-                            gsel[u] = g0 + fl;
-                            cum[u] += __shfl_sync(0xffffffffu, xs - own, fl);   // groups before the crossing one
-                        } else {
-                            cum[u] += __shfl_sync(0xffffffffu, xs, 31);
-                        }
-                    }
-                }
-                // recompute the crossing group of each user: UI independent FFMA chains, UI loads in flight per k
-                float acc[UI];
-                const float *gp[UI];
-#pragma unroll
-                for (int u = 0; u < UI; ++u) {
-                    const int pj = p0[u] + max(gsel[u], 0) * 32 + lane;
-                    gp[u] = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & (SUB - 1));
-                    acc[u] = 0.f;
-                }
-#pragma unroll 7
-                for (int k = 0; k < K1; ++k) {   // 7 x UI L2 loads in flight
-#pragma unroll
-                    for (int u = 0; u < UI; ++u) acc[u] = fmaf(om32[k * TU + ii[u]], __ldg(gp[u] + k * SUB), acc[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < UI; ++u) {
-                    if (gsel[u] < 0) continue;                 // warp-uniform
-                    const double tau = s_tau[ii[u]];
-                    double x = (double)ex2_approx(acc[u] - s_shift[ii[u]]);
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double y = __shfl_up_sync(0xffffffffu, x, d);
-                        if (lane >= d) x += y;
-                    }
-                    const double pre = cum[u] + x;
-                    const int pj = p0[u] + gsel[u] * 32 + lane;
-                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
-                    if (m) {
-                        const int fl = __ffs(m) - 1;
-                        found[u] = p0[u] + gsel[u] * 32 + fl;
-                        upper[u] = __shfl_sync(0xffffffffu, pre, fl);
-                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
-                        lower[u] = fl > 0 ? below : cum[u];
-                    }   // else: the recomputed group is lighter than its pass-1 sum by a rounding: ambiguous
-                }
-                if (lane < UI && ib + lane < nlive) {   // lane u finishes user u: filter, view, re-sampling queue
-                    int fnd = found[0];
-                    double lo = lower[0], up = upper[0];
-#pragma unroll
-                    for (int u = 1; u < UI; ++u)
-                        if (lane == u) { fnd = found[u]; lo = lower[u]; up = upper[u]; }
-                    const int i = ib + lane, slot = pos2slot[i];
-                    const double Z = s_Z[i], tau = s_tau[i];
-                    bool amb = fnd < 0;
-                    if (!amb) {
-                        // Filter (see the CUDA-core form below for the derivation): the tolerance is
-                        // d [ (1-u) S + u (Z - S) + 2u m(T) ] with T the crossing record tile
-                        const double dlt = (double)s_eps[i], uu = s_u[i];
-                        const float *tsr = tilesum + (size_t)i * p.nrec_pad + 2 * s_rsel[i];
-                        const double tmass = (double)tsr[0] + (double)tsr[1];
-                        const double tl = dlt * ((1.0 - uu) * lo + uu * fmax(Z - lo, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
-                        const double tu = dlt * ((1.0 - uu) * up + uu * fmax(Z - up, 0.0) + 2.0 * uu * tmass) + 1e-10 * Z;
-                        amb = (tau - lo < tl && fnd > 0) || (up - tau < tu && fnd < P - 1);
-                    }
-                    s_view[slot] = fnd;
-                    if (amb) {
-                        const double lse = log64(Z) * 1.4426950408889634074 + (double)s_shift[i];
-                        const int e = atomicAdd(&misc[6], 1);
-                        rq_slot[e] = slot; rq_u[e] = s_u[i]; rq_lse[e] = lse;
-                        s_wait[slot] = 1;
-                    }
-                }
-                __syncwarp();
-            }
-        }
         // ---- C: pass 2b (CUDA-core form), one warp per live user: recompute the located record tile, index and margins
         for (int i = warp; i < (TC ? 0 : nlive); i += NWARP) {
             const int slot = pos2slot[i];
@@ -1323,55 +1352,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                 const float shf = s_shift[i];
                 const int p0 = rsel * p.rec_sub * SUB;
                 const int p1 = min(p0 + p.rec_sub * SUB, nsub * SUB);
-              if constexpr (TC) {
-                // the 32-product groups of the record tile: their pass-1 masses were kept by the epilogue; locate the
-                // crossing group with them, then recompute only that group (one product per lane) for the index and
-                // its margins.  (These group sums are the very terms the record-tile sum was built from, up to the
-                // fp32 rounding of that chain, which the mass-error bound accounts for; the filter below charges the
-                // whole record tile as "counted with two different values".)
-                const int ngr = (p1 - p0) / 32;
-                int gsel = -1;
-                for (int g0 = 0; g0 < ngr && gsel < 0; g0 += 32) {
-                    const int gi = g0 + lane;
-                    double x = gi < ngr ? (double)__ldcg(gsum_cta + (size_t)(p0 / 32 + gi) * TU + i) : 0.0;
-                    const double own = x;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double y = __shfl_up_sync(0xffffffffu, x, d);
-                        if (lane >= d) x += y;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, (cum + x > tau) && gi < ngr);
-                    if (m) {
-                        const int fl = __ffs(m) - 1;
-                        gsel = g0 + fl;
-                        cum += __shfl_sync(0xffffffffu, x - own, fl);   // mass of the groups before the crossing one
-                    } else {
-                        cum += __shfl_sync(0xffffffffu, x, 31);
-                    }
-                }
-                if (gsel >= 0) {
-                    const int pj = p0 + gsel * 32 + lane;
-                    const float *gp = env.G32 + (size_t)(pj >> 7) * K1 * SUB + (pj & (SUB - 1));
-                    float a0 = 0.f;
-#pragma unroll 7
-                    for (int k = 0; k < K1; ++k) a0 = fmaf(om32[k * TU + i], __ldg(gp + k * SUB), a0);
-                    double x = (double)ex2_approx(a0 - shf);
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double y = __shfl_up_sync(0xffffffffu, x, d);
-                        if (lane >= d) x += y;
-                    }
-                    const double pre = cum + x;
-                    const unsigned m = __ballot_sync(0xffffffffu, (pre > tau) && (pj < P));
-                    if (m) {
-                        const int fl = __ffs(m) - 1;
-                        found = p0 + gsel * 32 + fl;
-                        upper = __shfl_sync(0xffffffffu, pre, fl);
-                        const double below = __shfl_sync(0xffffffffu, pre, fl > 0 ? fl - 1 : 0);
-                        lower = fl > 0 ? below : cum;
-                    }   // else: the recomputed group is lighter than its pass-1 sum by a rounding: ambiguous
-                }
-              } else {
+              {
                 // two 128-product tiles per step: 8 masses per lane (8 independent FFMA chains keep 8 x K1 L2 loads
                 // in flight), the 8 group totals by butterfly sums, a scan only in the crossing group
                 bool done = false;
@@ -1572,7 +1553,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             t += 1;
             int pend = 0;
             if (st == RG_ORGANIC) pend = 1;
-            else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+            else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t);
             while (serial_bandit && st == RG_BANDIT && !organic_only) {  // abstract.py:174-181, one event per turn
                 const int a = policy_act(slot, user, t, last_view, n_org);
                 const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
@@ -1583,7 +1564,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                 if (p.out.log) log_write(p.out, log_reserve(p.out, 1), (long long)user - p.user_begin, t, a, 1 | (c << 1));
                 t += 1;
                 if (st == RG_ORGANIC) pend = 1;  // the loop ends here: deferred
-                else thread_omega_update(om, K, env.sigma * 1.0, false, env.seed, user, t);
+                else thread_omega_update(om, K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t);
                 if (c) st = RG_ORGANIC;
                 n_ban += 1;
                 n_clk += c;

@@ -22,7 +22,10 @@ class DeviceEnv:
     """Owns an `rg_env` handle (device copies of Gamma, mu, beta and the transition thresholds)."""
 
     def __init__(self, static_params, sigma_omega_initial, sigma_omega, seed, change_omega_for_bandits=False,
-                 device=0):
+                 device=0, normal_time=None):
+        """normal_time: None = DefaultTimeGenerator (the clock is the event index); (mu, sigma) = NormalTimeGenerator
+        (normal_time_generator.py:7-31): the clock advances by |N(mu, sigma)| per event (Philox slot 2 at (user, event
+        index)), the omega drift is scaled by that step (reco_env_v1.py:89-99)."""
         self.Gamma = np.ascontiguousarray(static_params["Gamma"], np.float64)
         self.P, self.K = self.Gamma.shape
         self.mu_organic = np.ascontiguousarray(np.ravel(static_params["mu_organic"]), np.float64)
@@ -43,6 +46,9 @@ class DeviceEnv:
         d.sigma_omega = float(sigma_omega)
         d.change_omega_for_bandits = int(bool(change_omega_for_bandits))
         d.seed = self.seed
+        self.normal_time = None if normal_time is None else (float(normal_time[0]), float(normal_time[1]))
+        if self.normal_time is not None:
+            d.time_generator, d.normal_time_mu, d.normal_time_sigma = 1, self.normal_time[0], self.normal_time[1]
         h = C.c_void_p()
         L.check(L.lib().rg_env_create(C.byref(d), self.device, C.byref(h)))
         self._h = h
@@ -64,7 +70,8 @@ class DeviceEnv:
         """Independent handle with the same parameters (deepcopy support of the facade)."""
         sp = {"Gamma": self.Gamma, "mu_organic": self.mu_organic, "beta": self.beta, "mu_bandit": self.mu_bandit,
               "state_transition": self.state_transition}
-        return DeviceEnv(sp, self._desc_args[0], self._desc_args[1], self.seed, self._desc_args[2], self.device)
+        return DeviceEnv(sp, self._desc_args[0], self._desc_args[1], self.seed, self._desc_args[2], self.device,
+                         self.normal_time)
 
     def set_seed(self, seed):
         """AbstractEnv.reset_random_seed(epoch): seed = random_seed + epoch (abstract.py:59-62)."""
@@ -80,8 +87,9 @@ class DeviceEnv:
 
     # -- fused rollout -------------------------------------------------------------------------
     def rollout_device(self, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
-                       math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False, totals=None):
+                       math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False, totals=None, epsilon=0.0):
         """generate_logs(n_users, agent, n_organic_users) reduced to counters, everything on device.
+        policy: "uniform" | "table" | "user_views" | "eps_table" (EpsilonGreedy(epsilon) around the table agent).
 
         Returns a dict of torch tensors (device): per-user n_events/n_organic/n_bandit/n_clicks/
         last_view/hash (if per_user), omega (if requested), view/action/click histograms (if hist)
@@ -107,16 +115,16 @@ class DeviceEnv:
                 setattr(out, name, res[name].data_ptr())
         res["totals"] = totals if totals is not None else torch.zeros(16, dtype=torch.int64, device=dev)
         out.totals = res["totals"].data_ptr()
-        if policy == "table" and not (hasattr(table, "is_cuda") and table.is_cuda):
+        if policy in ("table", "eps_table") and not (hasattr(table, "is_cuda") and table.is_cuda):
             table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
         keep = res["_keep"] = []  # keeps the table alive until the launch has been enqueued
-        pol = _policy_struct(keep, policy, table, self.P, host=False)
+        pol = _policy_struct(keep, policy, table, self.P, host=False, epsilon=epsilon)
         L.check(L.lib().rg_rollout_device(self._h, C.byref(pol), int(user_begin), int(n_organic_users),
                                           int(n_users), C.byref(out), int(math_mode), self._stream()))
         return res
 
     def rollout_host(self, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
-                     math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False):
+                     math_mode=L.MATH_FAST, per_user=True, omega=False, hist=False, epsilon=0.0):
         """Same through HOST (numpy) buffers: the C ABI performs the H2D/D2H copies. Synchronous."""
         n = int(n_users) + int(n_organic_users)
         res = {}
@@ -137,21 +145,22 @@ class DeviceEnv:
         res["totals"] = np.zeros(16, np.int64)
         out.totals = res["totals"].ctypes.data
         keep = []
-        pol = _policy_struct(keep, policy, table, self.P, host=True)
+        pol = _policy_struct(keep, policy, table, self.P, host=True, epsilon=epsilon)
         L.check(L.lib().rg_rollout_host(self._h, C.byref(pol), int(user_begin), int(n_organic_users), int(n_users),
                                         C.byref(out), int(math_mode)))
         del keep
         return res
 
 
-def _policy_struct(keep, policy, table, P, host):
+def _policy_struct(keep, policy, table, P, host, epsilon=0.0):
     pol = L.Policy()
+    pol.epsilon = float(epsilon)
     if policy == "uniform":
         pol.kind = L.POLICY_UNIFORM
     elif policy == "user_views":   # OrganicUserEventCounterAgent, default configuration (RG_POLICY_USER_VIEWS)
         pol.kind = L.POLICY_USER_VIEWS
-    elif policy == "table":
-        pol.kind = L.POLICY_TABLE
+    elif policy in ("table", "eps_table"):   # eps_table: EpsilonGreedy(epsilon) around the table agent (RG_POLICY_EPS_TABLE)
+        pol.kind = L.POLICY_TABLE if policy == "table" else L.POLICY_EPS_TABLE
         if host:
             if hasattr(table, "is_cuda"):     # a table trained on the device (CountStats): the host path takes a host copy
                 table = table.detach().cpu().numpy()
@@ -170,7 +179,7 @@ def _policy_struct(keep, policy, table, P, host):
 
 
 def rollout_log(env, n_users, policy="uniform", table=None, user_begin=0, n_organic_users=0,
-                math_mode=L.MATH_TENSOR, rows_per_user=110.0):
+                math_mode=L.MATH_TENSOR, rows_per_user=110.0, epsilon=0.0):
     """The rows of AbstractEnv.generate_logs (abstract.py:241-327) for users user_begin.., produced by ONE fused
     rollout (event-log output of the kernels) and sorted into the reference order on the host.
     Returns a dict of numpy arrays: u, t, z (0 organic / 1 bandit), v, a, c (-1 where the reference has NaN)."""
@@ -184,7 +193,7 @@ def rollout_log(env, n_users, policy="uniform", table=None, user_begin=0, n_orga
         out = L.RolloutOut()
         out.totals = totals.ctypes.data
         out.log, out.log_capacity, out.log_count = log.ctypes.data, cap, count.ctypes.data
-        pol = _policy_struct(keep, policy, table, env.P, host=True)
+        pol = _policy_struct(keep, policy, table, env.P, host=True, epsilon=epsilon)
         L.check(L.lib().rg_rollout_host(env._h, C.byref(pol), int(user_begin), int(n_organic_users), int(n_users),
                                         C.byref(out), int(math_mode)))
         rows = int(count[0])

@@ -32,8 +32,10 @@ class DefaultTimeGenerator(TimeGenerator):
 
 
 class NormalTimeGenerator(TimeGenerator):
-    """t += |N(mu, sigma)| (normal_time_generator.py:7-31).  Host-only value type: the device path
-    supports the default clock only, RecoEnv1.init_gym rejects this one."""
+    """t += |N(mu, sigma)| (normal_time_generator.py:7-31).  As the env's `time_generator` it selects the kernels'
+    normal clock (rg_env_desc.time_generator = 1): the steps are then drawn from the env's counter RNG (Philox slot 2
+    keyed by user and event index), not from this object's RandomState -- `new_time()` here only serves code that
+    uses the generator on its own."""
 
     def __init__(self, config):
         super().__init__(config)

@@ -21,7 +21,7 @@ from .. import _lib as L
 from .configuration import Configuration
 from .context import DefaultContext
 from .device_env import BatchState, DeviceEnv
-from .features.time import DefaultTimeGenerator
+from .features.time import DefaultTimeGenerator, NormalTimeGenerator
 from .observation import Observation
 from .session import OrganicSessions
 from .static_params import draw_static_params, make_beta
@@ -110,10 +110,10 @@ class RecoEnv1:
             self.time_generator = DefaultTimeGenerator(self.config)
         else:
             self.time_generator = self.config.time_generator
-            if not isinstance(self.time_generator, DefaultTimeGenerator):
+            if not isinstance(self.time_generator, (DefaultTimeGenerator, NormalTimeGenerator)):
                 raise NotImplementedError(
-                    "recogym_b200 implements the default event clock only (SURVEY.md 8f rank 4); got %r"
-                    % type(self.time_generator).__name__)
+                    "recogym_b200 implements DefaultTimeGenerator and NormalTimeGenerator (reference: "
+                    "recogym/envs/features/time/); got %r" % type(self.time_generator).__name__)
         self.device_env = None
         self.reset_random_seed()
         self.agent = args["agent"] if "agent" in args else None
@@ -145,8 +145,29 @@ class RecoEnv1:
         self.device_env = DeviceEnv(
             {"Gamma": self.Gamma, "mu_organic": self.mu_organic, "beta": self.beta, "mu_bandit": self.mu_bandit,
              "state_transition": self.state_transition},
-            c.sigma_omega_initial, c.sigma_omega, self._epoch_seed, c.change_omega_for_bandits, self._device)
+            c.sigma_omega_initial, c.sigma_omega, self._epoch_seed, c.change_omega_for_bandits, self._device,
+            self._normal_time())
         self._batch = None
+
+    def _normal_time(self):
+        """(mu, sigma) when the env's clock is a NormalTimeGenerator, else None (event index == clock)."""
+        tg = getattr(self, "time_generator", None)
+        if isinstance(tg, NormalTimeGenerator):
+            return float(tg.normal_time_mu), float(tg.normal_time_sigma)
+        return None
+
+    def _clock(self, event_index):
+        """current_time at the given event index of the facade's current user.  Default clock: the index itself.
+        NormalTimeGenerator: the sequential binary64 sum of the steps of the calls 0 .. index-1 (the kernels' Philox
+        slot 2 at (user key, call)), as normal_time_generator.py:25-28 accumulates them."""
+        nt = self._normal_time()
+        if nt is None:
+            return int(event_index)
+        cum = self._clock_cum
+        key = int(self.current_user_id) + int(getattr(self, "_user_key_offset", 0))
+        while len(cum) <= event_index:
+            cum.append(cum[-1] + L.lib().rg_spec_time_step(self._epoch_seed, key, len(cum) - 1, nt[0], nt[1]))
+        return cum[event_index]
 
     # ---------------------------------------------------------------------------- copy / pickle
     def __deepcopy__(self, memo):
@@ -189,8 +210,11 @@ class RecoEnv1:
         self.time_generator.reset()
         if self.agent:
             self.agent.reset()
-        self.current_time = self.time_generator.new_time()
+        self.time_generator.new_time()
         self.current_user_id = user_id
+        self._event_index = 0            # Markov events of this user so far == the RNG's event time
+        self._clock_cum = [0.0]
+        self.current_time = self._clock(0)
         self.organic_views = np.zeros(self.config.num_products)
         key = int(user_id) + int(getattr(self, "_user_key_offset", 0))
         if self._batch is None:
@@ -206,16 +230,20 @@ class RecoEnv1:
         while True:
             n = int(h["sess_len"][0])
             for v in h["sess_v"][0, :n]:
-                sessions.next(DefaultContext(t, self.current_user_id), int(v))
+                sessions.next(DefaultContext(self._clock(t), self.current_user_id), int(v))
                 t += 1
             if int(h["state"][0]) != organic:
                 break
             self._batch.continue_sessions(L.MATH_EXACT)
             h = self._batch.read()
         self.state = int(h["state"][0])
-        self.current_time = int(h["t"][0])
-        self.time_generator.current_time = self.current_time + 1
+        self._set_event_index(int(h["t"][0]))
         return sessions
+
+    def _set_event_index(self, idx):
+        self._event_index = idx
+        self.current_time = self._clock(idx)
+        self.time_generator.current_time = self._clock(idx + 1)   # the generator's own state after new_time()
 
     def step(self, action_id):
         """abstract.py:123-197: returns (Observation, reward, done, info)."""
@@ -231,7 +259,7 @@ class RecoEnv1:
         assert action_id is not None
         a = int(action_id)
         assert 0 <= a < self.config.num_products
-        t_before = self.current_time
+        t_before = self._event_index
         self._batch.step(np.array([a], np.int32), L.MATH_EXACT)
         h = self._batch.read()
         reward = int(h["reward"][0])
@@ -240,8 +268,7 @@ class RecoEnv1:
         else:
             sessions = self.empty_sessions
             self.state = int(h["state"][0])
-            self.current_time = int(h["t"][0])
-            self.time_generator.current_time = self.current_time + 1
+            self._set_event_index(int(h["t"][0]))
         return (Observation(DefaultContext(self.current_time, self.current_user_id), sessions), reward,
                 self.state == stop, info)
 
@@ -258,7 +285,7 @@ class RecoEnv1:
                 P = self.config.num_products
                 a = L.lib().rg_spec_policy_uniform_action(
                     self._epoch_seed, int(self.current_user_id) + int(getattr(self, "_user_key_offset", 0)),
-                    int(self.current_time), P)
+                    int(self._event_index), P)
                 action = {
                     "t": observation.context().time(),
                     "u": observation.context().user(),
@@ -345,7 +372,23 @@ class RecoEnv1:
         import pandas as pd
         from .device_env import rollout_log
         r = rollout_log(self.device_env, num_offline_users, pol["policy"], pol.get("table"), int(user_begin),
-                        num_organic_offline_users)
+                        num_organic_offline_users, epsilon=pol.get("epsilon", 0.0))
+        tcol = r["t"].astype(np.float32)
+        nt = self._normal_time()
+        if nt is not None:      # NormalTimeGenerator: the row's clock = sequential sum of its user's steps (host spec calls)
+            tcol = np.empty(len(r["t"]), np.float32)
+            f = L.lib().rg_spec_time_step
+            start = 0
+            while start < len(tcol):
+                key = int(r["u"][start])
+                end = start
+                while end < len(tcol) and r["u"][end] == key:
+                    end += 1
+                cum = [0.0]
+                for i in range(int(r["t"][start:end].max())):
+                    cum.append(cum[-1] + f(self._epoch_seed, key, i, nt[0], nt[1]))
+                tcol[start:end] = np.asarray(cum, np.float64)[r["t"][start:end]].astype(np.float32)
+                start = end
         r["u"] = r["u"] - int(user_begin)          # labels are 0-based per call, as in the reference
         organic = r["z"] == 0
         P = self.config.num_products
@@ -362,16 +405,23 @@ class RecoEnv1:
         else:
             ps_table = pol.get("ps_table")
             ps = np.where(organic, np.nan, 1.0)
-            if ps_table is not None:   # e.g. BanditCount reports its click-rate estimate as 'ps'
+            eps = float(pol.get("epsilon", 0.0)) if pol["policy"] == "eps_table" else 0.0
+            if ps_table is not None or eps > 0.0:   # e.g. BanditCount reports its click-rate estimate as 'ps'
                 # the acting last view of a bandit row is the most recent organic view of the same user
                 lv = pd.Series(np.where(organic, r["v"], np.nan)).groupby(r["u"]).ffill().to_numpy()
                 bidx = np.flatnonzero(~organic)
-                if hasattr(ps_table, "is_cuda"):   # trained on the device
-                    ps_table = ps_table.detach().cpu().numpy()
-                ps[bidx] = np.asarray(ps_table)[lv[bidx].astype(np.int64)]
+                lvb = lv[bidx].astype(np.int64)
+                if ps_table is not None:
+                    if hasattr(ps_table, "is_cuda"):   # trained on the device
+                        ps_table = ps_table.detach().cpu().numpy()
+                    ps[bidx] = np.asarray(ps_table)[lvb]
+                if eps > 0.0:   # epsilon_greedy.py:44-68: an action is greedy iff it is the wrapped agent's
+                    table = pol["table"].detach().cpu().numpy() if hasattr(pol["table"], "is_cuda") else np.asarray(pol["table"])
+                    greedy = r["a"][bidx] == table[lvb]
+                    ps[bidx] = np.where(greedy, (1.0 - eps) * ps[bidx], eps * (1.0 / float(P - 1)))
         nan = np.float32("nan")
         df = pd.DataFrame({
-            "t": r["t"].astype(np.float32),
+            "t": tcol,
             "u": pd.array(r["u"], dtype=pd.Int32Dtype()),
             "z": np.where(organic, "organic", "bandit"),
             "v": pd.array(np.where(organic, r["v"], 0), dtype=pd.Int32Dtype()),
@@ -391,12 +441,12 @@ class RecoEnv1:
 
     # --------------------------------------------------------------------- throughput entry point
     def generate_logs_counters(self, num_offline_users, policy="uniform", table=None, num_organic_offline_users=0,
-                               user_begin=0, math_mode=L.MATH_FAST, hist=False, per_user=False):
+                               user_begin=0, math_mode=L.MATH_FAST, hist=False, per_user=False, epsilon=0.0):
         """generate_logs() reduced to its counters, all users in ONE fused launch.  Returns a dict of
         host numpy arrays; successes/failures as test_agent counts them (phantom rows are failures,
         bench_agents.py:203-206)."""
         r = self.device_env.rollout_device(num_offline_users, policy, table, user_begin, num_organic_offline_users,
-                                           math_mode, per_user=per_user, hist=hist)
+                                           math_mode, per_user=per_user, hist=hist, epsilon=epsilon)
         out = {k: v.cpu().numpy() for k, v in r.items() if not k.startswith("_")}
         tot = out["totals"]
         out["successes"] = int(tot[4])

@@ -35,7 +35,8 @@ def verify_agents(env, number_of_users, agents, allow_probe=False, user_begin=0)
         e = deepcopy(env)
         pol = device_policy(agent, e.config.num_products, allow_probe=allow_probe)
         if pol is not None:
-            r = e.generate_logs_counters(number_of_users, pol["policy"], pol.get("table"), user_begin=user_begin)
+            r = e.generate_logs_counters(number_of_users, pol["policy"], pol.get("table"), user_begin=user_begin,
+                                         epsilon=pol.get("epsilon", 0.0))
             successes, failures = r["successes"], r["failures"]
         else:
             data = e.generate_logs(number_of_users, agent, user_begin=user_begin)
@@ -51,11 +52,15 @@ def verify_agents(env, number_of_users, agents, allow_probe=False, user_begin=0)
 
 def _device_evolution_agent(agent):
     """The count agent behind `agent` when the whole evolution loop can stay on the GPU: OrganicCount / BanditCount,
-    bare or wrapped in an EpsilonGreedy that never explores (epsilon == 0: every action is 'greedy')."""
+    bare or wrapped in an EpsilonGreedy with the default selection rule (epsilon = 0: every action is 'greedy';
+    0 < epsilon < 1: the device policy RG_POLICY_EPS_TABLE)."""
     from .agents import BanditCount, EpsilonGreedy, OrganicCount
     inner = agent
     if isinstance(agent, EpsilonGreedy):
-        if float(agent.config.epsilon) != 0.0 or agent.config.with_ps_all:
+        cfg = agent.config
+        eps = float(cfg.epsilon)
+        if cfg.with_ps_all or not (0.0 <= eps < 1.0) or (eps > 0.0 and (not cfg.epsilon_pure_new or cfg.epsilon_select_worse
+                                                                           or int(cfg.num_products) < 2)):
             return None
         inner = agent.agent
     if type(inner) in (OrganicCount, BanditCount) and not inner.config.with_ps_all:
@@ -64,24 +69,34 @@ def _device_evolution_agent(agent):
 
 
 def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps, training_approach,
-                           math_mode=None):
+                           math_mode=None, sliding_window_samples=10000):
     """evaluate_agent (evaluate_agent.py:51-146) with every phase on the GPU: the warm-up users are rolled out under
     the env's logging policy and the agent trains on their log (RG_TRAIN_EVOLUTION_INIT); each evolution step is ONE
-    fused rollout of the frozen acting table, whose ordered log feeds the training copy (RG_TRAIN_EVOLUTION_STEP) --
-    scatter-add kernels -- and the next acting table is a row arg-max kernel."""
+    fused rollout of the frozen acting policy -- the table, or EpsilonGreedy(epsilon) around it (RG_POLICY_EPS_TABLE) --
+    whose ordered log feeds the training copy (RG_TRAIN_EVOLUTION_STEP, all of its train calls or the ones the
+    TrainingApproach selects: logs.MaskedTrainingLog) through the scatter-add kernels; the next acting table is a row
+    arg-max kernel.  'greedy' of a logged action: it equals the acting table's (an exploring action never does)."""
+    import numpy as np
     import torch
     from . import _lib as L
-    from .logs import generate_logs_device
+    from .logs import MaskedTrainingLog, generate_logs_device
     mm = L.MATH_TENSOR if math_mode is None else math_mode
     de = env.device_env
     P = env.config.num_products
-    greedy = inner is not agent          # EpsilonGreedy(epsilon=0) marks every action greedy (epsilon_greedy.py:59-62)
+    wrapped = inner is not agent         # under EpsilonGreedy the action dict carries 'greedy' (epsilon_greedy.py:44-62)
+    eps = float(agent.config.epsilon) if wrapped else 0.0
+    explored_only = training_approach in (TrainingApproach.ALL_EXPLORATION_DATA,
+                                          TrainingApproach.SLIDING_WINDOW_EXPLORATION_DATA)
+    window = int(sliding_window_samples) if training_approach in (TrainingApproach.SLIDING_WINDOW_ALL_DATA,
+                                                                  TrainingApproach.SLIDING_WINDOW_EXPLORATION_DATA) else 0
+    samples = 0
     lpv = lambda a: a.device_last_view() if hasattr(a, "device_last_view") else -1
     initial_agent = deepcopy(inner)
     log_pol = device_policy(env.agent, P) if env.agent else {"policy": "uniform"}
     if num_initial_train_users > 0:
         log = generate_logs_device(de, num_initial_train_users, log_pol["policy"], log_pol.get("table"), None, 0, 0, mm,
-                                   prev_last_view=lpv(inner), train_mode=L.TRAIN_EVOLUTION_INIT)
+                                   prev_last_view=lpv(inner), train_mode=L.TRAIN_EVOLUTION_INIT,
+                                   epsilon=log_pol.get("epsilon", 0.0))
         inner.device_train(log)
     unique_user_id = num_initial_train_users
     rewards = {EvolutionCase.SUCCESS: [], EvolutionCase.SUCCESS_GREEDY: [], EvolutionCase.FAILURE: [],
@@ -91,25 +106,42 @@ def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_
     per_action = [[0] for _ in range(P)]
     for step in range(num_steps):
         pol = acting.device_policy()
-        log = generate_logs_device(de, num_step_users, pol["policy"], pol.get("table"), pol.get("ps_table"),
-                                   unique_user_id, 0, mm, prev_last_view=lpv(training),
-                                   train_mode=L.TRAIN_EVOLUTION_STEP)
+        if not (hasattr(pol["table"], "is_cuda") and pol["table"].is_cuda):
+            pol = {**pol, "table": torch.as_tensor(np.ascontiguousarray(pol["table"], np.int32), device=de.torch_device)}
+        log = generate_logs_device(de, num_step_users, "eps_table" if eps > 0.0 else pol["policy"], pol.get("table"),
+                                   pol.get("ps_table"), unique_user_id, 0, mm, prev_last_view=lpv(training),
+                                   train_mode=L.TRAIN_EVOLUTION_STEP, epsilon=eps)
         tot = log.totals.cpu().numpy()
         successes, failures = int(tot[4]), int(tot[3] - tot[4])        # real bandit events only: the loop stops at done
         n = log.rows
+        real = (log.z[:n] == 1) & ((log.flags[:n] & 1) == 0)
+        is_greedy = real & (log.a[:n] == pol["table"][log.lv[:n].clamp(min=0).long()]) if wrapped else None
         clicked = log.a[:n][log.c[:n] == 1].long()
         hist = torch.bincount(clicked, minlength=P).cpu().numpy()
-        training.device_train(log)
+        if explored_only and not wrapped:
+            raise KeyError("greedy")     # the reference reads action['greedy'], which only EpsilonGreedy provides
+        if explored_only or window:
+            view = MaskedTrainingLog(log, pol["table"], explored_only, window, samples, lpv(training))
+            samples = view.n_samples
+            training.device_train(view)
+        else:
+            samples += int(tot[3])
+            training.device_train(log)
         unique_user_id += num_step_users
         acting = training
         for a in range(P):
             per_action[a][-1] += int(hist[a])
             per_action[a].append(0)
         training = deepcopy(initial_agent if training_approach == TrainingApproach.LAST_STEP else acting)
+        if wrapped:
+            sg = int((is_greedy & (log.c[:n] == 1)).sum().item())
+            fg = int((is_greedy & (log.c[:n] != 1)).sum().item())
+        else:
+            sg = fg = 0
         rewards[EvolutionCase.SUCCESS].append(successes)
-        rewards[EvolutionCase.SUCCESS_GREEDY].append(successes if greedy else 0)
+        rewards[EvolutionCase.SUCCESS_GREEDY].append(sg)
         rewards[EvolutionCase.FAILURE].append(failures)
-        rewards[EvolutionCase.FAILURE_GREEDY].append(failures if greedy else 0)
+        rewards[EvolutionCase.FAILURE_GREEDY].append(fg)
     rewards[EvolutionCase.ACTIONS] = {a: per_action[a] for a in range(P)}
     return rewards
 
@@ -122,13 +154,15 @@ def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000,
     the gym facade with the Python agents, exactly as the reference does."""
     inner = _device_evolution_agent(agent)
     if device is None:
-        device = (inner is not None and training_approach in (TrainingApproach.ALL_DATA, TrainingApproach.LAST_STEP)
+        device = (inner is not None
+                  and (inner is not agent or training_approach in (TrainingApproach.ALL_DATA, TrainingApproach.LAST_STEP,
+                                                                   TrainingApproach.SLIDING_WINDOW_ALL_DATA))
                   and (not env.agent or device_policy(env.agent, env.config.num_products) is not None))
     if device:
         if inner is None:
             raise ValueError("the device evolution loop needs a count agent (OrganicCount / BanditCount)")
         return _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps,
-                                      training_approach)
+                                      training_approach, sliding_window_samples=sliding_window_samples)
     initial_agent = deepcopy(agent)
     unique_user_id = 0
     for u in range(num_initial_train_users):

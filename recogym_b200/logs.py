@@ -84,22 +84,85 @@ class DeviceLog:
         return df
 
 
+FLAG_PHANTOM = 1     # csrc/rg_logs.cu: the bandit row after `done`
+
+
+class MaskedTrainingLog:
+    """A DeviceLog seen through one of evaluate_agent's selective TrainingApproaches (evaluate_agent.py:105-119): only
+    the train calls of SOME bandit rows of an evolution step are made -- `not action['greedy']` (ALL_EXPLORATION_DATA),
+    `samples % window == 0` (SLIDING_WINDOW_ALL_DATA), or both.  A train call owns the organic session right before its
+    bandit row, so the rows to drop are marked in a COPY of the z column (value 2: neither organic nor bandit for the
+    scatter-add kernels), and BanditCount's `last_product_viewed` -- which only moves when train() is called with a
+    non-empty session -- is re-derived for the kept rows (lvp column) and for the end of the log (carry).  Index plumbing
+    on the device (cumulative sums / maxima over the log columns); the statistics kernels run unchanged.
+
+    greedy action of a row = acting_table[lv]; `samples` = evaluate_agent's running count of bandit steps before this
+    log.  After construction: .n_samples (count after this log), .keep_rows (kept train calls)."""
+
+    def __init__(self, log, acting_table, explored_only, window, samples, prev_last_view):
+        torch = _torch()
+        n = int(log.rows)
+        dev = log.env.torch_device
+        self.env, self.rows, self.train_mode, self.capacity = log.env, n, log.train_mode, log.capacity
+        self._log = log
+        z, flags, a, lv, u = log.z[:n], log.flags[:n], log.a[:n], log.lv[:n], log.u[:n]
+        if not (hasattr(acting_table, "is_cuda") and acting_table.is_cuda):
+            acting_table = torch.as_tensor(np.ascontiguousarray(acting_table, np.int32), device=dev)
+        ar = torch.arange(n, device=dev)
+        is_b = (z == 1) & ((flags & FLAG_PHANTOM) == 0)
+        greedy = a == acting_table[lv.clamp(min=0).long()]
+        ordinal = int(samples) + torch.cumsum(is_b.long(), 0)
+        keep_b = is_b.clone()
+        if explored_only:
+            keep_b &= ~greedy
+        if window:
+            keep_b &= (ordinal % int(window)) == 0
+        # organic rows follow the bandit row that closes their session (always inside the same user: a regular user's log
+        # ends with its phantom bandit row)
+        pos = torch.where(z == 1, ar, torch.full_like(ar, n))
+        nxt = torch.flip(torch.cummin(torch.flip(pos, [0]), 0).values, [0]) if n else pos
+        keep_o = (z == 0) & (nxt < n) & keep_b[nxt.clamp(max=max(n - 1, 0))]
+        self.z = log.z.clone()
+        self.z[:n] = torch.where(keep_b | keep_o | ((z == 1) & ~is_b), z, torch.full_like(z, 2))
+        # last_product_viewed before each kept train call: the last view of the closest earlier KEPT call that came with a
+        # non-empty session (BanditCount.train -> update_lpv, bandit_count.py:54-57); before the first one: the carry
+        prev_org = torch.zeros(n, dtype=torch.bool, device=dev)
+        if n > 1:
+            prev_org[1:] = (z[:-1] == 0) & (u[1:] == u[:-1])
+        cand = keep_b & prev_org
+        run = torch.cummax(torch.where(cand, ar, torch.full_like(ar, -1)), 0).values if n else ar
+        prev = torch.cat([torch.full((1,), -1, dtype=run.dtype, device=dev), run[:-1]]) if n else run
+        self.lvp = log.lvp.clone()
+        self.lvp[:n] = torch.where(prev >= 0, lv[prev.clamp(min=0)], torch.full_like(lv, int(prev_last_view))).to(log.lvp.dtype)
+        last = int(run[-1].item()) if n else -1
+        self.carry = torch.tensor([int(lv[last].item()) if last >= 0 else int(prev_last_view)], dtype=torch.int32, device=dev)
+        self.n_samples = int(samples) + int(is_b.sum().item())
+        self.keep_rows = int(keep_b.sum().item())
+        self.sess, self.flags = log.sess, log.flags
+
+    def struct(self):
+        s = self._log.struct()
+        s.z = self.z.data_ptr()
+        s.lvp = self.lvp.data_ptr()
+        return s
+
+
 def generate_logs_device(env, n_users, policy="uniform", table=None, ps_table=None, user_begin=0, n_organic_users=0,
                          math_mode=L.MATH_TENSOR, prev_last_view=-1, rows_per_user=108.0, log=None,
-                         train_mode=L.TRAIN_TEST_AGENT):
+                         train_mode=L.TRAIN_TEST_AGENT, epsilon=0.0):
     """generate_logs(n_users, agent, n_organic_users) -> DeviceLog, everything on the GPU.  `env` is a DeviceEnv.
     One synchronisation (the row count) per call; a log that does not fit is regenerated into larger columns.
     train_mode (L.TRAIN_*) names the reference training loop whose train calls the derived columns describe."""
     torch = _torch()
     dev = env.torch_device
     n = int(n_users) + int(n_organic_users)
-    if policy == "table" and not (hasattr(table, "is_cuda") and table.is_cuda):
+    if policy in ("table", "eps_table") and not (hasattr(table, "is_cuda") and table.is_cuda):
         table = torch.as_tensor(np.ascontiguousarray(table, np.int32), device=dev)
     if ps_table is not None and not (hasattr(ps_table, "is_cuda") and ps_table.is_cuda):
         ps_table = torch.as_tensor(np.ascontiguousarray(ps_table, np.float64), device=dev)
     cap = int(n * rows_per_user) + 4096
     keep = []
-    pol = _policy_struct(keep, policy, table, env.P, host=False)
+    pol = _policy_struct(keep, policy, table, env.P, host=False, epsilon=epsilon)
     while True:
         if log is None or log.capacity < cap:
             log = DeviceLog(env, cap)

@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--K", type=int, default=20)
     ap.add_argument("--users", type=int, default=1_000_000)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--trained", action="store_true", help="act with bench.py's trained organic_count table instead of a random one")
+    ap.add_argument("--flush", action="store_true", help="flush L2 (256 MiB write) before the timed launch, as bench.py does")
+    ap.add_argument("--user-begin", type=int, default=0)
     args = ap.parse_args()
     import torch
     import recogym_b200 as rg
@@ -32,7 +35,12 @@ def main():
     cfg = rg.Configuration({**rg.env_1_args, "num_products": args.P, "K": args.K, "random_seed": 42})
     sp = draw_static_params(cfg)
     de = rg.DeviceEnv(sp, cfg.sigma_omega_initial, cfg.sigma_omega, 42)
-    table = torch.as_tensor(np.random.RandomState(0).randint(0, args.P, args.P).astype(np.int32), device="cuda")
+    if args.trained:
+        import bench
+        pol = bench.build_policies(["organic_count"], args.P, args.K, 1000, device=0)
+        table = torch.as_tensor(pol[0][2], device="cuda")
+    else:
+        table = torch.as_tensor(np.random.RandomState(0).randint(0, args.P, args.P).astype(np.int32), device="cuda")
     lib = L.lib()
     has_prof = hasattr(lib, "rg_prof_read")
     de.rollout_device(args.users // 4, "table", table, 5_000_000, 0, L.MATH_TENSOR, per_user=False)
@@ -42,8 +50,11 @@ def main():
     if has_prof:
         lib.rg_prof_read(prof, None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.flush:
+        fl = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        fl.fill_(1)
     e0.record()
-    r = de.rollout_device(args.users, "table", table, 0, 0, L.MATH_TENSOR, per_user=False)
+    r = de.rollout_device(args.users, "table", table, args.user_begin, 0, L.MATH_TENSOR, per_user=False)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

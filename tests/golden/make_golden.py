@@ -134,6 +134,9 @@ def main():
     if "--edge-only" in sys.argv:
         edge_cases()
         return
+    if "--evolution-eps-only" in sys.argv:
+        evolution_eps_case()
+        return
     if "--eps-only" in sys.argv:
         eps_greedy_case()
         return
@@ -157,6 +160,7 @@ def main():
     evolution_case()
     edge_cases()
     eps_greedy_case()
+    evolution_eps_case()
     normal_time_case()
 
 
@@ -251,6 +255,44 @@ def evolution_case(name="t2_evolution_seed8_P30_K5"):
             out[tag + "_warm_co"] = agent.co_counts
         print(name, tag, "success", rw[EvolutionCase.SUCCESS], "failure", rw[EvolutionCase.FAILURE])
     save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps,
+         sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
+         change_omega_for_bandits=0, **sp, **out)
+
+
+def evolution_eps_case(name="t2_evolution_eps_seed9_P20_K4"):
+    """The reference's evaluate_agent (evaluate_agent.py:51-146) for EpsilonGreedy(epsilon = 0.3) around its two count
+    agents under every TrainingApproach, on T2 streams (the wrapper's coin and exploring choice drawn from the policy
+    stream at the env's (user, time)): per-step successes / failures, their greedy parts, per-action click histories."""
+    ref = H.load_reference()
+    from recogym.agents import (OrganicCount, organic_count_args, BanditCount, bandit_count_args, EpsilonGreedy,
+                                epsilon_greedy_args)
+    from recogym import evaluate_agent, TrainingApproach, EvolutionCase
+    P = 20
+    args = {"random_seed": 9, "num_products": P, "K": 4}
+    n_init, n_step, n_steps, eps, W = 20, 30, 3, 0.3, 7
+    out = {}
+    sp = cfg = None
+    for itag, ctor, cargs in (("bc", BanditCount, bandit_count_args), ("oc", OrganicCount, organic_count_args)):
+        for atag, approach in (("all", TrainingApproach.ALL_DATA), ("last", TrainingApproach.LAST_STEP),
+                               ("swall", TrainingApproach.SLIDING_WINDOW_ALL_DATA),
+                               ("expl", TrainingApproach.ALL_EXPLORATION_DATA),
+                               ("swexpl", TrainingApproach.SLIDING_WINDOW_EXPLORATION_DATA)):
+            env = H.make_env(args, "T2")
+            sp, cfg = H.static_params(env), env.config
+            inner = ctor(ref.Configuration({**cargs, "num_products": P}))
+            eg = EpsilonGreedy(ref.Configuration({**epsilon_greedy_args, "num_products": P, "epsilon": eps,
+                                                  "random_seed": cfg.random_seed}), inner)
+            eg.rng = H.PhiloxAgentRNG(env, cfg.random_seed)
+            rw = evaluate_agent(env, eg, n_init, n_step, n_steps, approach, sliding_window_samples=W)
+            tag = itag + "_" + atag
+            out[tag + "_success"] = np.array(rw[EvolutionCase.SUCCESS], np.int64)
+            out[tag + "_failure"] = np.array(rw[EvolutionCase.FAILURE], np.int64)
+            out[tag + "_success_greedy"] = np.array(rw[EvolutionCase.SUCCESS_GREEDY], np.int64)
+            out[tag + "_failure_greedy"] = np.array(rw[EvolutionCase.FAILURE_GREEDY], np.int64)
+            out[tag + "_actions"] = np.array([rw[EvolutionCase.ACTIONS][a] for a in range(P)], np.int64)
+            print(name, tag, "success", rw[EvolutionCase.SUCCESS], "greedy", rw[EvolutionCase.SUCCESS_GREEDY],
+                  "failure", rw[EvolutionCase.FAILURE], "greedy", rw[EvolutionCase.FAILURE_GREEDY])
+    save(name, seed=int(cfg.random_seed), n_init=n_init, n_step=n_step, n_steps=n_steps, epsilon=eps, window=W,
          sigma_omega_initial=float(cfg.sigma_omega_initial), sigma_omega=float(cfg.sigma_omega),
          change_omega_for_bandits=0, **sp, **out)
 

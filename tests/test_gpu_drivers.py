@@ -229,3 +229,159 @@ def test_competition_score_runs_the_leaderboard_protocol():
     agent = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, **args, "agent": logger, "num_products": P}))
     q = rg.test_agent(env, agent, 40, 120, 5, 1, True)
     assert (df["q0.500"][0], df["q0.025"][0], df["q0.975"][0]) == q
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
+def test_device_epsilon_greedy_policy_equals_reference_and_oracle(oracle, mode):
+    """RG_POLICY_EPS_TABLE (EpsilonGreedy(epsilon) around a table agent, agents/epsilon_greedy.py:30-68): the fused rollout
+    == the reference's own EpsilonGreedy(OrganicCount) on the T2 policy stream (golden t2_seed41: event log in reference
+    order) and == the C oracle per user at other shapes and epsilons."""
+    from conftest import load_golden, oracle_env_from_golden
+    from test_gpu_parity import MODES, assert_rollout_equal, both_envs, device_env_from_golden
+    from recogym_b200.envs.device_env import rollout_log
+    g = load_golden("t2_seed41_P25_K4_u60_eps_organic_count")
+    oe, de = oracle_env_from_golden(g), device_env_from_golden(g)
+    n, eps, table = int(g["n_users"]), float(g["epsilon"]), g["table"].astype(np.int32)
+    rc = oracle.rollout(oe, 0, n, policy="eps_table", table=table, hist=True, omega=True, epsilon=eps)
+    rg_ = de.rollout_host(n, "eps_table", table, 0, 0, MODES[mode], per_user=True, omega=True, hist=True, epsilon=eps)
+    assert_rollout_equal(rg_, rc)
+    log = rollout_log(de, n, "eps_table", table, 0, 0, MODES[mode], epsilon=eps)
+    for k in "utzvac":
+        assert np.array_equal(log[k].astype(np.int64), g["log_" + k].astype(np.int64)), k
+    de.close()
+    for P, K, e in ((2, 3, 0.5), (300, 8, 0.05), (1025, 20, 0.9)):
+        oe, de = both_envs(P, K, 900 + P)
+        table = np.random.RandomState(P).randint(0, P, P).astype(np.int32)
+        rc = oracle.rollout(oe, 7, 300, policy="eps_table", table=table, n_organic_users=2, hist=True, omega=True, epsilon=e, threads=4)
+        rg_ = de.rollout_host(300, "eps_table", table, 7, 2, MODES[mode], per_user=True, omega=True, hist=True, epsilon=e)
+        assert_rollout_equal(rg_, rc)
+        de.close()
+
+
+def test_epsilon_greedy_agent_compiles_to_the_device_policy_and_logs_its_propensities():
+    """EpsilonGreedy(epsilon > 0) around a count agent: device_policy() is RG_POLICY_EPS_TABLE; generate_logs (fused) gives
+    'ps' = (1 - eps) * greedy ps for greedy actions and eps / (P - 1) for exploring ones (epsilon_greedy.py:44-68), the
+    exploring fraction is epsilon, and the device log's ps column agrees."""
+    import recogym_b200 as rg
+    from recogym_b200 import _lib as L
+    from recogym_b200.logs import generate_logs_device
+    Pn, eps = 40, 0.2
+    env = make_env(num_products=Pn)
+    inner = rg.agents.BanditCount(rg.Configuration({**rg.agents.bandit_count_args, "num_products": Pn}))
+    log0 = generate_logs_device(env.device_env, 300, "uniform", None, None, 0, 0, L.MATH_TENSOR, train_mode=L.TRAIN_TEST_AGENT)
+    inner.device_train(log0)
+    eg = rg.agents.EpsilonGreedy(rg.Configuration({**rg.agents.epsilon_greedy_args, "num_products": Pn, "epsilon": eps}), inner)
+    pol = eg.device_policy()
+    assert pol["policy"] == "eps_table" and pol["epsilon"] == eps
+    table = pol["table"].cpu().numpy() if hasattr(pol["table"], "cpu") else np.asarray(pol["table"])
+    ps_table = pol["ps_table"].cpu().numpy() if hasattr(pol["ps_table"], "cpu") else np.asarray(pol["ps_table"])
+    df = env.generate_logs(400, agent=eg, user_begin=300)
+    z = (df["z"] == "bandit").to_numpy()
+    v = df["v"].to_numpy(dtype="float64", na_value=np.nan)
+    import pandas as pd
+    lv = pd.Series(np.where(z, np.nan, v)).groupby(df["u"].to_numpy(dtype="int64")).ffill().to_numpy()[z].astype(np.int64)
+    a = df["a"].to_numpy(dtype="float64", na_value=-1)[z].astype(np.int64)
+    ps = df["ps"].to_numpy(dtype="float64")[z]
+    greedy = a == table[lv]
+    assert np.array_equal(ps[greedy], (1.0 - eps) * ps_table[lv[greedy]])
+    assert np.array_equal(ps[~greedy], np.full(int((~greedy).sum()), eps * (1.0 / (Pn - 1))))
+    frac = 1.0 - greedy.mean()
+    assert abs(frac - eps) < 4 * np.sqrt(eps * (1 - eps) / len(a)), frac
+    dlog = generate_logs_device(env.device_env, 400, "eps_table", pol["table"], pol["ps_table"], 300, 0, L.MATH_TENSOR, epsilon=eps)
+    h = dlog.to_host()
+    assert np.array_equal(h["ps"][h["z"] == 1], ps) and np.array_equal(h["a"][h["z"] == 1], a)
+    # the A/B driver runs it as one fused rollout
+    out = rg.verify_agents(env, 300, {"eg": eg, "inner": inner}, user_begin=700)
+    assert len(out) == 2 and (out["0.025"] < out["0.975"]).all()
+
+
+def test_device_evolution_under_epsilon_greedy_equals_reference_for_every_training_approach():
+    """evaluate_agent on the GPU (fused rollouts under RG_POLICY_EPS_TABLE, ordered device logs, scatter-add training of
+    the calls each TrainingApproach selects, arg-max tables) == the reference's own evaluate_agent for EpsilonGreedy(0.3)
+    around both count agents under all five approaches (golden t2_evolution_eps: per-step successes / failures, their
+    greedy parts, per-action click histories)."""
+    import recogym_b200 as rg
+    from conftest import load_golden
+    g = load_golden("t2_evolution_eps_seed9_P20_K4")
+    Pn = g["Gamma"].shape[0]
+    env = rg.make("reco-gym-v1")
+    env.init_gym({**rg.env_1_args, "random_seed": int(g["seed"]), "num_products": Pn, "K": g["Gamma"].shape[1]})
+    assert np.array_equal(env.Gamma, g["Gamma"]) and np.array_equal(np.ravel(env.mu_organic), np.ravel(g["mu_organic"]))
+    A, T, E = rg.agents, rg.TrainingApproach, rg.EvolutionCase
+    for itag, ctor, cargs in (("bc", A.BanditCount, A.bandit_count_args), ("oc", A.OrganicCount, A.organic_count_args)):
+        for atag, approach in (("all", T.ALL_DATA), ("last", T.LAST_STEP), ("swall", T.SLIDING_WINDOW_ALL_DATA),
+                               ("expl", T.ALL_EXPLORATION_DATA), ("swexpl", T.SLIDING_WINDOW_EXPLORATION_DATA)):
+            eg = A.EpsilonGreedy(rg.Configuration({**A.epsilon_greedy_args, "num_products": Pn, "epsilon": float(g["epsilon"])}),
+                                 ctor(rg.Configuration({**cargs, "num_products": Pn})))
+            rw = rg.evaluate_agent(copy.deepcopy(env), eg, int(g["n_init"]), int(g["n_step"]), int(g["n_steps"]), approach,
+                                   sliding_window_samples=int(g["window"]))
+            tag = itag + "_" + atag
+            assert rw[E.SUCCESS] == list(g[tag + "_success"]) and rw[E.FAILURE] == list(g[tag + "_failure"]), tag
+            assert rw[E.SUCCESS_GREEDY] == list(g[tag + "_success_greedy"]), tag
+            assert rw[E.FAILURE_GREEDY] == list(g[tag + "_failure_greedy"]), tag
+            assert np.array_equal(np.array([rw[E.ACTIONS][a] for a in range(Pn)]), g[tag + "_actions"]), tag
+    # a bare count agent has no 'greedy' key: the selective approaches fail as in the reference, SLIDING_WINDOW_ALL_DATA runs
+    bare = A.BanditCount(rg.Configuration({**A.bandit_count_args, "num_products": Pn}))
+    rw = rg.evaluate_agent(copy.deepcopy(env), bare, 10, 20, 2, T.SLIDING_WINDOW_ALL_DATA, sliding_window_samples=5)
+    assert len(rw[E.SUCCESS]) == 2 and rw[E.SUCCESS_GREEDY] == [0, 0]
+    with pytest.raises(KeyError):
+        rg.evaluate_agent(copy.deepcopy(env), bare, 10, 20, 1, T.ALL_EXPLORATION_DATA, device=True)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
+def test_normal_time_generator_on_the_device_equals_reference_and_oracle(oracle, mode):
+    """NormalTimeGenerator dynamics (normal_time_generator.py:7-31; reco_env_v1.py:89-99: the omega drift is scaled by the
+    clock step): the fused rollout == the oracle per user (final omega bit-exact) and == the reference's own generator on
+    T2 streams (golden t2_seed51: every log column incl. the float32 clock), in all three math modes."""
+    from conftest import load_golden, oracle_env_from_golden
+    from test_gpu_parity import MODES, assert_rollout_equal, synthetic_env
+    from recogym_b200 import DeviceEnv
+    from recogym_b200.logs import generate_logs_device
+    g = load_golden("t2_seed51_P30_K4_u50_o4_normal_time")
+    nt = tuple(float(x) for x in g["normal_time"])
+    oe = oracle_env_from_golden(g)
+    sp = {k: g[k] for k in ("Gamma", "mu_organic", "beta", "mu_bandit", "state_transition")}
+    de = DeviceEnv(sp, float(g["sigma_omega_initial"]), float(g["sigma_omega"]), int(g["seed"]), False, 0, nt)
+    n, no = int(g["n_users"]), int(g["n_organic_users"])
+    rc = oracle.rollout(oe, 0, n, n_organic_users=no, hist=True, omega=True)
+    rg_ = de.rollout_host(n, "uniform", None, 0, no, MODES[mode], per_user=True, omega=True, hist=True)
+    assert_rollout_equal(rg_, rc)
+    log = generate_logs_device(de, n, "uniform", None, None, 0, no, MODES[mode])
+    h = log.to_host()
+    for k in "uzvac":
+        assert np.array_equal(h[k].astype(np.int64), g["log_" + k].astype(np.int64)), k
+    assert np.array_equal(log.t[:log.rows].cpu().numpy(), g["log_tf"]), "float32 clock column"
+    de.close()
+    cfg, sp2 = synthetic_env(500, 12, 77, sigma_omega=0.3)
+    from oracle import oracle as O
+    oe2 = O.OracleEnv(sp2["Gamma"], sp2["mu_organic"], sp2["beta"], sp2["mu_bandit"], sp2["state_transition"],
+                      cfg.sigma_omega_initial, cfg.sigma_omega, 77, normal_time=(1.0, 0.7))
+    de2 = DeviceEnv(sp2, cfg.sigma_omega_initial, cfg.sigma_omega, 77, False, 0, (1.0, 0.7))
+    rc = oracle.rollout(oe2, 11, 400, hist=True, omega=True, threads=4)
+    rg_ = de2.rollout_host(400, "uniform", None, 11, 0, MODES[mode], per_user=True, omega=True, hist=True)
+    assert_rollout_equal(rg_, rc)
+    de2.close()
+
+
+def test_facade_with_normal_time_generator_reproduces_the_reference_log():
+    """env.init_gym(time_generator=NormalTimeGenerator(...)): generate_logs through the per-step facade and through the
+    fused path give the reference's own rows (golden t2_seed51), float32 clock column included."""
+    import recogym_b200 as rg
+    from conftest import load_golden
+    g = load_golden("t2_seed51_P30_K4_u50_o4_normal_time")
+    mu, sigma = (float(x) for x in g["normal_time"])
+    args = {**rg.env_1_args, "random_seed": int(g["seed"]), "num_products": g["Gamma"].shape[0], "K": g["Gamma"].shape[1],
+            "sigma_omega": float(g["sigma_omega"]), "normal_time_mu": mu, "normal_time_sigma": sigma}
+    args["time_generator"] = rg.NormalTimeGenerator(rg.Configuration(args))
+    env = rg.make("reco-gym-v1")
+    env.init_gym(args)
+    assert np.array_equal(env.Gamma, g["Gamma"])
+    n, no = int(g["n_users"]), int(g["n_organic_users"])
+    for fused in (True, False):
+        df = env.generate_logs(n, num_organic_offline_users=no, fused=fused)
+        z = (df["z"] == "bandit").to_numpy()
+        assert np.array_equal(z.astype(np.int64), g["log_z"].astype(np.int64)), fused
+        assert np.array_equal(df["t"].to_numpy(dtype="float32"), g["log_tf"]), fused
+        assert np.array_equal(df["v"].to_numpy(dtype="float64", na_value=-1)[~z].astype(np.int64), g["log_v"][~z]), fused
+        assert np.array_equal(df["a"].to_numpy(dtype="float64", na_value=-1)[z].astype(np.int64), g["log_a"][z]), fused
+        assert np.array_equal(df["c"].to_numpy(dtype="float64")[z].astype(np.int64), g["log_c"][z]), fused

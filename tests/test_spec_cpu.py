@@ -151,3 +151,13 @@ def test_count_agents_compile_to_tables():
     assert bc.ctr[2, 4] == 2 / 3 and bc.last_product_viewed == 3
     assert device_policy(bc, P)["table"][2] == 4
     assert device_policy(None, P) == {"policy": "uniform"}
+
+
+def test_time_step_spec_equals_oracle_clock(oracle):
+    """rg_spec_time_step (NormalTimeGenerator.new_time's step, normal_time_generator.py:25-28, Philox slot 2) == the
+    oracle's clock normal, bit for bit; the product library and the oracle share no code."""
+    from recogym_b200 import _lib as L
+    f = L.lib().rg_spec_time_step
+    for seed, user, mu, sigma in ((51, 0, 0.5, 2.0), (7, 123456789012, 0.0, 1.0), (2 ** 40 + 3, 5, -1.5, 0.25)):
+        for call in (0, 1, 2, 17, 4095):
+            assert f(seed, user, call, mu, sigma) == abs(mu + sigma * oracle.time_normal(seed, user, call))

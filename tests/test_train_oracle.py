@@ -219,3 +219,25 @@ def test_sparse_count_statistics_equal_dense(oracle):
             tb, psb = T.sparse_bandit_count_table(P, spu, scl, rp, rc)
             tb_d, ps_d = T.bandit_count_table(pu, cl)
             assert np.array_equal(tb, tb_d) and np.array_equal(psb, ps_d)
+
+
+EVO_EPS = "t2_evolution_eps_seed9_P20_K4"
+
+
+def test_evolution_under_epsilon_greedy_matches_reference_for_every_training_approach(oracle):
+    """oracle/train_oracle.py's call-by-call evolution loop on the C oracle's logs (acting policy = EpsilonGreedy(0.3)
+    around the count agent's table, on the policy stream) == the reference's own evaluate_agent for both count agents and
+    all five TrainingApproaches: per-step successes / failures, their greedy parts, per-action click histories."""
+    from oracle import train_oracle as T
+    g = load_golden(EVO_EPS)
+    env = oracle_env_from_golden(g)
+    P = g["Gamma"].shape[0]
+    roll = lambda ub, n, pol, tab, eps: oracle.rollout(env, ub, n, policy=pol, table=tab, log=True, epsilon=eps)["log"]
+    for itag, kind in (("bc", "bandit"), ("oc", "organic")):
+        for atag in ("all", "last", "swall", "expl", "swexpl"):
+            r = T.evolution(roll, P, kind, int(g["n_init"]), int(g["n_step"]), int(g["n_steps"]), atag,
+                            float(g["epsilon"]), int(g["window"]))
+            tag = itag + "_" + atag
+            for k in ("success", "failure", "success_greedy", "failure_greedy"):
+                assert list(r[k]) == list(g[tag + "_" + k]), (tag, k, r[k], g[tag + "_" + k])
+            assert np.array_equal(r["actions"], g[tag + "_actions"]), tag
