@@ -33,25 +33,27 @@ size_t warp_kernel_smem_bytes(const EnvDev &env) {
 // One Markov event in the organic state (abstract.py:110-119): view, then update_state.
 // Returns the view; updates state, t, omega.
 __device__ __forceinline__ int organic_event(const EnvDev &env, const WarpCtx &wc, uint64_t user, int &state,
-                                             uint32_t &t, int lane, unsigned &ambig) {
+                                             uint32_t &t, double &clock, int lane, unsigned &ambig) {
     const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
     const int v = warp_sample_view_exact(env, wc.omega, wc.sc, uniform53(w.x, w.y), lane, ambig);
     state = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
     t += 1;
+    const double omega_k = clock_advance(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma, clock);   // every update_state advances the clock
     if (env.change_omega_for_bandits || state == RG_ORGANIC)
-        warp_omega_update(wc.omega, env.K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t, lane);
+        warp_omega_update(wc.omega, env.K, env.sigma * omega_k, false, env.seed, user, t, lane);
     return v;
 }
 
 // One Markov event in the bandit state (abstract.py:174-181): click, update_state, click override.
 __device__ __forceinline__ int bandit_event(const EnvDev &env, const WarpCtx &wc, uint64_t user, int a, int &state,
-                                            uint32_t &t, int lane) {
+                                            uint32_t &t, double &clock, int lane) {
     const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
     const int click = click_from_uniform(ctr_of_action(env, wc.omega, a), uniform53(w.x, w.y));
     state = next_state(env, RG_BANDIT, uniform53(w.z, w.w));
     t += 1;
+    const double omega_k = clock_advance(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma, clock);   // every update_state advances the clock
     if (env.change_omega_for_bandits || state == RG_ORGANIC)
-        warp_omega_update(wc.omega, env.K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t, lane);
+        warp_omega_update(wc.omega, env.K, env.sigma * omega_k, false, env.seed, user, t, lane);
     if (click) state = RG_ORGANIC;  // abstract.py:180-181: a click overrides any transition, incl. stop
     return click;
 }
@@ -83,6 +85,7 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
         const uint64_t user = (uint64_t)(user_begin + i);
         int state = RG_ORGANIC;
         uint32_t t = 0;
+        double clock = 0.0;     // current_time of the user's clock (NormalTimeGenerator; unused under the default clock)
         int last_view = -1, n_org = 0, n_ban = 0, n_clk = 0;
         uint64_t h = kHashInit;
         warp_omega_update(wc.omega, env.K, env.sigma0, true, env.seed, user, 0u, lane);
@@ -92,7 +95,7 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
         int nd = 0;  // distinct products viewed by this user (per-user features reset, organic_user_count.py:111-116)
         for (;;) {
             if (state == RG_ORGANIC) {
-                const int v = organic_event(env, wc, user, state, t, lane, ambig);
+                const int v = organic_event(env, wc, user, state, t, clock, lane, ambig);
                 last_view = v;
                 n_org += 1;
                 h = hash_fold(h, ((uint64_t)(uint32_t)v << 2) | 0u);
@@ -105,7 +108,7 @@ rollout_warp_kernel(const EnvDev env, const PolicyDev pol, long long user_begin,
                 }
             } else if (state == RG_BANDIT && !organic_only) {
                 const int a = policy_action(env, pol, user, t, last_view, vlist, nd, n_org);
-                const int c = bandit_event(env, wc, user, a, state, t, lane);
+                const int c = bandit_event(env, wc, user, a, state, t, clock, lane);
                 if (out.log && lane == 0) log_write(out, log_reserve(out, 1), i, t - 1u, a, 1 | (c << 1));
                 n_ban += 1;
                 n_clk += c;
@@ -169,23 +172,26 @@ batch_step_kernel(const EnvDev env, int mode, long long N, const long long *__re
         uint32_t t;
         int last_view;
         int len = 0;
+        double clock = 0.0;
         if (mode == 0) {
             state = RG_ORGANIC; t = 0; last_view = -1;
             warp_omega_update(wc.omega, env.K, env.sigma0, true, env.seed, user, 0u, lane);
         } else {
             state = state_io[i]; t = (uint32_t)t_io[i]; last_view = last_view_io[i];
+            // the caller's state holds the event index only: the clock value is re-accumulated (compatibility path)
+            clock = clock_at(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma);
             for (int k = lane; k < env.K; k += 32) wc.omega[k] = omega_io[(size_t)i * env.K + k];
             __syncwarp();
         }
         if (mode == 1) {
             int r = 0;
-            if (state == RG_BANDIT) r = bandit_event(env, wc, user, action[i], state, t, lane);
+            if (state == RG_BANDIT) r = bandit_event(env, wc, user, action[i], state, t, clock, lane);
             if (lane == 0) reward[i] = r;
         }
         if (mode != 1 || state == RG_ORGANIC) {
             // generate_organic_sessions (abstract.py:105-121), at most sess_cap views per call
             while (state == RG_ORGANIC && len < sess_cap) {
-                const int v = organic_event(env, wc, user, state, t, lane, ambig);
+                const int v = organic_event(env, wc, user, state, t, clock, lane, ambig);
                 last_view = v;
                 if (lane == 0) sess_v[(size_t)i * sess_cap + len] = v;
                 ++len;

@@ -213,11 +213,23 @@ RG_HD double time_step(uint64_t seed, uint64_t user, uint32_t call, double mu, d
     const u32x4 w = draw(seed, user, call, SLOT_TIME);
     return fabs(mu + sigma * normal_from_words(w.x, w.y));
 }
-// omega_k of RecoEnv1.update_state (reco_env_v1.py:89-93) for the update INTO event index t (t >= 1)
-RG_HD double omega_k_into(int time_mode, uint64_t seed, uint64_t user, uint32_t t, double mu, double sigma) {
+// RecoEnv1.update_state's clock handling (reco_env_v1.py:89-93) for the update INTO event index t (t >= 1): the clock is the
+// SEQUENTIAL binary64 sum of the steps taken so far (the generator accumulates `current_time += step`), time_delta is the
+// DIFFERENCE of two accumulated values -- not the raw step -- and omega_k = 1 if that difference is exactly 0.
+// `clock` holds the value at event index t - 1 and is advanced to event index t; returns omega_k.  Default clock: 1.
+RG_HD double clock_advance(int time_mode, uint64_t seed, uint64_t user, uint32_t t, double mu, double sigma, double &clock) {
     if (time_mode == 0) return 1.0;
-    const double dt = time_step(seed, user, t - 1u, mu, sigma);
+    const double old = clock;
+    clock = clock + time_step(seed, user, t - 1u, mu, sigma);
+    const double dt = clock - old;
     return dt == 0.0 ? 1.0 : dt;
+}
+// the clock at event index t from scratch (sequential sum of t steps)
+RG_HD double clock_at(int time_mode, uint64_t seed, uint64_t user, uint32_t t, double mu, double sigma) {
+    double c = 0.0;
+    if (time_mode != 0)
+        for (uint32_t i = 0; i < t; ++i) c = c + time_step(seed, user, i, mu, sigma);
+    return c;
 }
 
 RG_HD double sigmoid64(double x) { return 1.0 / (1.0 + exp64(-x)); }  // reco_env_v1.py:32-34

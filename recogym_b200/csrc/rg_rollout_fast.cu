@@ -28,6 +28,7 @@
 // All draws are keyed by (seed, user, event time, slot): the result is independent of scheduling.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "rg_device.cuh"
 #include "rg_host.h"
@@ -54,7 +55,8 @@ constexpr int NBUF = tc::TILE_N == 64 ? 3 : 2;  // tensor mode: accumulator tile
 constexpr int FB = 8;       // users per sweep of the cooperative binary64 sampler
 
 struct Layout {  // byte offsets into dynamic shared memory
-    int mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
+    int clock, dt,   // NormalTimeGenerator only: per-slot clock value and the omega_k of the slot's pending drift
+        mbar, om64, csum, user, hash, t, state, last_view, n_org, n_ban, n_clk, view, live, pos2slot, shift, eps,
         nview, amb_list, fb_slot, fb_pos, fb_unres, fb_u, fb_lse, fb_om, lse, pz, pu, rq_u, rq_lse, ptau, pcum, prsel, wait, rq_slot, q3_slot, q3_u, pend, pend_list, misc, om32, tilesum, gtile, atile,
         total;
 };
@@ -98,6 +100,8 @@ __host__ inline void make_layout(Params &p) {
     L.rq_u = o; o += 8 * TU;
     L.rq_lse = o; o += 8 * TU;
     L.q3_u = o; o += 8 * TU;
+    L.clock = o; if (p.env.time_mode) o += 8 * TU;
+    L.dt = o; if (p.env.time_mode) o += 8 * TU;
     L.ptau = o; if (!p.tc) o += 8 * TU;
     L.pcum = o; if (!p.tc) o += 8 * TU;
     L.user = o; o += 8 * TU;
@@ -741,6 +745,9 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
     int *rq_slot = (int *)(smem + L.rq_slot);
     int *q3_slot = (int *)(smem + L.q3_slot);      // draws tier 2 could not certify, waiting for a tier-3 sweep
     double *q3_u = (double *)(smem + L.q3_u);
+    double *s_clock = (double *)(smem + L.clock);   // only touched when env.time_mode != 0
+    double *s_dt = (double *)(smem + L.dt);
+    const int tmode = env.time_mode;
     int *s_wait = (int *)(smem + L.wait);           // 0 none, 2 queued this round, 1 being re-sampled this round
     double *s_tau = (double *)(smem + L.ptau);
     double *s_cum = (double *)(smem + L.pcum);
@@ -854,6 +861,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
         s_live[slot] = 1;
         s_wait[slot] = 0;
         s_pend[slot] = 2;  // omega = sigma0 * z(user, 0) (reco_env_v1.py:80-82), done by omega_phase()
+        if (tmode) s_clock[slot] = 0.0;   // time_generator.reset(); current_time = new_time() = 0
         return true;
     };
     // Pending omega updates of all slots, spread over the whole CTA: task = (slot, normal pair j).
@@ -877,7 +885,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             const bool init = s_pend[slot] == 2;
             double *om = om64 + (size_t)slot * KP;
             const double scale = init ? env.sigma0
-                                      : env.sigma * omega_k_into(env.time_mode, env.seed, s_user[slot], s_t[slot], env.time_mu, env.time_sigma);
+                                      : env.sigma * (tmode ? s_dt[slot] : 1.0);
             const u32x4 w = draw(env.seed, s_user[slot], s_t[slot], SLOT_NORMAL + (uint32_t)j);
             const double z0 = normal_from_words(w.x, w.y);
             om[2 * j] = (init ? 0.0 : om[2 * j]) + scale * z0;
@@ -1551,9 +1559,19 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
             const u32x4 w = draw(env.seed, user, t, SLOT_EVENT);
             int st = next_state(env, RG_ORGANIC, uniform53(w.z, w.w));
             t += 1;
+            // NormalTimeGenerator: the user's accumulated clock lives in shared memory (no registers on the default clock)
+            auto tick = [&](uint32_t t_new) -> double {
+                if (!tmode) return 1.0;
+                double clock = s_clock[slot];
+                const double dt = clock_advance(1, env.seed, user, t_new, env.time_mu, env.time_sigma, clock);
+                s_clock[slot] = clock;
+                s_dt[slot] = dt;
+                return dt;
+            };
+            double omega_k = tick(t);
             int pend = 0;
             if (st == RG_ORGANIC) pend = 1;
-            else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t);
+            else if (env.change_omega_for_bandits) thread_omega_update(om, K, env.sigma * omega_k, false, env.seed, user, t);
             while (serial_bandit && st == RG_BANDIT && !organic_only) {  // abstract.py:174-181, one event per turn
                 const int a = policy_act(slot, user, t, last_view, n_org);
                 const u32x4 wb = draw(env.seed, user, t, SLOT_EVENT);
@@ -1563,8 +1581,9 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                 st = next_state(env, RG_BANDIT, uniform53(wb.z, wb.w));
                 if (p.out.log) log_write(p.out, log_reserve(p.out, 1), (long long)user - p.user_begin, t, a, 1 | (c << 1));
                 t += 1;
+                omega_k = tick(t);
                 if (st == RG_ORGANIC) pend = 1;  // the loop ends here: deferred
-                else thread_omega_update(om, K, env.sigma * omega_k_into(env.time_mode, env.seed, user, t, env.time_mu, env.time_sigma), false, env.seed, user, t);
+                else thread_omega_update(om, K, env.sigma * omega_k, false, env.seed, user, t);
                 if (c) st = RG_ORGANIC;
                 n_ban += 1;
                 n_clk += c;
@@ -1656,6 +1675,19 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                     if (lane < nev) {
                         if (p.out.action_hist) atomicAdd(p.out.action_hist + a, 1ull);
                         if (c && p.out.click_hist) atomicAdd(p.out.click_hist + a, 1ull);
+                    }
+                    if (tmode) {   // every event of the run advances the clock: the steps in parallel, their SEQUENTIAL sum
+                        const double stp = lane < nev ? time_step(env.seed, user, tt, env.time_mu, env.time_sigma) : 0.0;
+                        double clock = s_clock[slot], omega_k = 1.0;
+                        for (int j = 0; j < nev; ++j) {
+                            const double prev = clock;
+                            clock = clock + __shfl_sync(0xffffffffu, stp, j);
+                            const double d = clock - prev;
+                            omega_k = d == 0.0 ? 1.0 : d;
+                        }
+                        __syncwarp();
+                        if (lane == 0) { s_clock[slot] = clock; s_dt[slot] = omega_k; }   // s_dt: read by the omega phase if the run ends organic
+                        __syncwarp();
                     }
                     n_ban += nev;
                     t += (uint32_t)nev;
@@ -1889,7 +1921,36 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
             e.gsum_bytes = need_g;
         }
         p.gsum = e.d_gsum;
+        // Experiment knob (RG_L2_PERSIST=1): mark the group-sum scratch as L2-persisting for this launch.  Every CTA rewrites
+        // its 162 KB of it each round; with two CTAs per SM the 48 MB do not survive in L2 between rounds and are written
+        // back (28 GB of DRAM writes per 1M-user launch at C3, profiles/r02_roofline_traffic.json) -- 4 % of the HBM
+        // bandwidth, no effect on the kernel's speed.
+        static const bool l2_persist = [] { const char *v = getenv("RG_L2_PERSIST"); return v && v[0] == '1'; }();
+        bool window_set = false;
+        if (l2_persist) {
+            int max_win = 0, max_persist = 0;
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e.device);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e.device);
+            if (max_win > 0 && max_persist > 0) {
+                const size_t want = need_g < (size_t)max_persist ? need_g : (size_t)max_persist;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                cudaStreamAttrValue av;
+                std::memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = e.d_gsum;
+                av.accessPolicyWindow.num_bytes = need_g < (size_t)max_win ? need_g : (size_t)max_win;
+                av.accessPolicyWindow.hitRatio = want >= need_g ? 1.0f : (float)((double)want / (double)need_g);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+                if (!window_set) (void)cudaGetLastError();
+            }
+        }
         rollout_cta_kernel_tc<<<(unsigned)blocks, NT + 32, (size_t)p.L.total, stream>>>(p);
+        if (window_set) {
+            cudaStreamAttrValue av;
+            std::memset(&av, 0, sizeof(av));
+            cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
     } else {
         rollout_cta_kernel_cc<<<(unsigned)blocks, NT, (size_t)p.L.total, stream>>>(p);
     }

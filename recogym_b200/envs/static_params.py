@@ -45,13 +45,57 @@ def flip_index(Gamma, number_of_flips):
     return index
 
 
+BLOCKED_FLIPS_MIN_PRODUCTS = 8192   # above this the P x P covariance (8 P^2 bytes) and its argsort give way to row maxima
+
+
+def flip_index_blocked(Gamma, number_of_flips, block=2048):
+    """flip_index for catalogues whose P x P covariance does not fit (P = 100 000: 80 GB + an argsort of 10^10 entries;
+    SURVEY.md 8f rank 4).  The reference walks ALL pairs in descending covariance and flips a pair when neither product
+    has been used (reco_env_v1.py:152-165): the pair it flips next is always the maximum of the covariance over the
+    still-unused pairs, i.e. the largest of the unused rows' maxima over unused columns.  So: one blocked pass for every
+    row's best partner (O(P^2 K) flops, O(P block) memory), then per flip only the rows whose best partner has just been
+    used are recomputed.  Identical to flip_index unless two DIFFERENT pairs tie to the last bit (the symmetric twins
+    (i, j) / (j, i) select the same flip whichever comes first)."""
+    P = Gamma.shape[0]
+    index = np.arange(P)
+    unused = np.ones(P, bool)
+    best_val = np.full(P, -np.inf)
+    best_j = np.full(P, -1, np.int64)
+
+    def row_best(rows):
+        cov = Gamma[rows] @ Gamma.T                           # [len(rows), P], the rows of the reference's prod_cov
+        cov[np.arange(len(rows)), rows] = 0.0                 # prod_cov - diag(diag(prod_cov)): a zero, not -inf
+        cov[:, ~unused] = -np.inf
+        cov[~unused[rows]] = -np.inf
+        # the reference's descending walk meets equal values in the REVERSE of argsort's order; exact ties between different
+        # pairs are the caveat above, any maximiser will do
+        j = cov.argmax(axis=1)
+        best_val[rows] = cov[np.arange(len(rows)), j]
+        best_j[rows] = j
+
+    for b0 in range(0, P, block):
+        row_best(np.arange(b0, min(P, b0 + block)))
+    for _ in range(int(number_of_flips)):
+        i = int(np.argmax(np.where(unused, best_val, -np.inf)))
+        if not np.isfinite(best_val[i]):
+            break                                              # fewer than two unused products left
+        j = int(best_j[i])
+        index[i], index[j] = j, i
+        unused[i] = unused[j] = False
+        best_val[i] = best_val[j] = -np.inf
+        stale = np.flatnonzero(unused & ((best_j == i) | (best_j == j)))
+        for b0 in range(0, len(stale), block):
+            row_best(stale[b0:b0 + block])
+    return index
+
+
 def make_beta(Gamma, mu_organic, number_of_flips, normalize):
     """beta / mu_bandit from Gamma / mu_organic (reco_env_v1.py:133-174).  With zero flips beta IS
     Gamma (same array object in the reference, :137-138)."""
     if number_of_flips == 0:
         beta, mu_bandit = Gamma, mu_organic
     else:
-        idx = flip_index(Gamma, number_of_flips)
+        idx = (flip_index_blocked if Gamma.shape[0] >= BLOCKED_FLIPS_MIN_PRODUCTS else flip_index)(Gamma, number_of_flips)
         beta, mu_bandit = Gamma[idx, :], mu_organic[idx, :]
     if normalize:
         beta = beta / np.sqrt((beta ** 2).sum(1)[:, np.newaxis])  # reco_env_v1.py:130-131

@@ -161,3 +161,19 @@ def test_time_step_spec_equals_oracle_clock(oracle):
     for seed, user, mu, sigma in ((51, 0, 0.5, 2.0), (7, 123456789012, 0.0, 1.0), (2 ** 40 + 3, 5, -1.5, 0.25)):
         for call in (0, 1, 2, 17, 4095):
             assert f(seed, user, call, mu, sigma) == abs(mu + sigma * oracle.time_normal(seed, user, call))
+
+
+def test_blocked_flip_search_equals_the_reference_walk():
+    """static_params.flip_index_blocked (row maxima instead of the P x P argsort: what number_of_flips > 0 needs at
+    P = 100 000) == flip_index, the literal restatement of reco_env_v1.py:142-165 that is pinned to the reference,
+    including when the flips exhaust the catalogue; and it runs at a size where the dense form cannot."""
+    from recogym_b200.envs.static_params import flip_index, flip_index_blocked
+    for P, K, flips, seed in ((50, 8, 10, 11), (333, 5, 40, 2), (1200, 20, 150, 3), (64, 4, 40, 4), (7, 3, 3, 5)):
+        G = np.random.RandomState(seed).normal(size=(P, K))
+        a, b = flip_index(G, flips), flip_index_blocked(G, flips, block=97)
+        assert np.array_equal(a, b), (P, flips)
+        assert (a != np.arange(P)).sum() == 2 * min(flips, P // 2)
+    G = np.random.RandomState(9).normal(size=(20000, 16))
+    idx = flip_index_blocked(G, 25)
+    moved = np.flatnonzero(idx != np.arange(20000))
+    assert len(moved) == 50 and np.array_equal(idx[idx[moved]], moved)

@@ -241,3 +241,111 @@ def test_evolution_under_epsilon_greedy_matches_reference_for_every_training_app
             for k in ("success", "failure", "success_greedy", "failure_greedy"):
                 assert list(r[k]) == list(g[tag + "_" + k]), (tag, k, r[k], g[tag + "_" + k])
             assert np.array_equal(r["actions"], g[tag + "_actions"]), tag
+
+
+def _derived_columns(log, prev_lpv=-1):
+    """numpy restatement of the device log's derived columns (csrc/rg_logs.cu columns_kernel) for a log without
+    organic-only users: lv, lvp (BanditCount's last_product_viewed before each bandit row when EVERY row trains), sess,
+    flags (1 phantom, 2 final session, 4 user without a real bandit row)."""
+    u, z, v = (np.asarray(log[k]) for k in ("u", "z", "v"))
+    n = len(u)
+    lv = np.full(n, -1, np.int32); lvp = np.full(n, -1, np.int32); sess = np.zeros(n, np.int32); flags = np.zeros(n, np.int8)
+    lpv = prev_lpv
+    i = 0
+    while i < n:
+        j = i
+        while j < n and u[j] == u[i]:
+            j += 1
+        cur, run, pending = -1, 0, None
+        last_real = max([r for r in range(i, j - 1) if z[r] == 1], default=-1)
+        for r in range(i, j):
+            if z[r] == 0:
+                cur = int(v[r]); sess[r] = run; run += 1; pending = cur
+                if r > last_real:
+                    flags[r] |= 2
+            else:
+                lvp[r] = lpv
+                if pending is not None:
+                    lpv = pending
+                run, pending = 0, None
+                if r == j - 1:
+                    flags[r] |= 1
+            if last_real < 0:
+                flags[r] |= 4
+            lv[r] = cur
+        i = j
+    return lv, lvp, sess, flags
+
+
+def test_masked_training_log_selects_the_reference_train_calls(oracle):
+    """logs.MaskedTrainingLog (the device evolution loop's view of a step log under the selective TrainingApproaches) on
+    CPU tensors: the rows it keeps and the last_product_viewed it re-derives give, through the scatter-add kernels'
+    semantics (restated in numpy), the statistics of the call-by-call walk that is pinned to the reference."""
+    import torch
+    from oracle import train_oracle as T
+    from recogym_b200.logs import MaskedTrainingLog
+    g = load_golden(EVO_EPS)
+    env = oracle_env_from_golden(g)
+    P = g["Gamma"].shape[0]
+    table = np.random.RandomState(1).randint(0, P, P).astype(np.int32)
+    log = oracle.rollout(env, 40, 60, policy="eps_table", table=table, log=True, epsilon=0.4)["log"]
+    n = len(log["u"])
+    lv, lvp, sess, flags = _derived_columns(log, prev_lpv=3)
+
+    class FakeEnv:
+        torch_device = torch.device("cpu")
+
+    class FakeLog:
+        pass
+    fl = FakeLog()
+    fl.env, fl.rows, fl.train_mode, fl.capacity = FakeEnv(), n, 1, n
+    for name, arr in (("z", log["z"].astype(np.int8)), ("flags", flags), ("a", log["a"].astype(np.int32)), ("lv", lv), ("u", log["u"].astype(np.int32)),
+                      ("lvp", lvp), ("sess", sess)):
+        setattr(fl, name, torch.as_tensor(arr))
+    fl.struct = lambda: None
+    for explored_only, window, samples0 in ((True, 0, 0), (False, 5, 13), (True, 3, 7)):
+        view = MaskedTrainingLog(fl, table, explored_only, window, samples0, 3)
+        z2, lvp2 = view.z.numpy(), view.lvp.numpy()
+        # the kernels' semantics (organic_pairs_kernel / bandit_stats_kernel, train_mode 1) on the masked columns
+        co = np.zeros((P, P)); pulls = np.zeros((P, P)); clicks = np.zeros((P, P))
+        for r in range(n):
+            if z2[r] == 0 and not (flags[r] & 2):
+                vr = int(log["v"][r]); co[vr, vr] += 1
+                for k in range(1, int(sess[r]) + 1):
+                    vj = int(log["v"][r - k]); co[vr, vj] += 1; co[vj, vr] += 1
+            elif z2[r] == 1 and not (flags[r] & 1):
+                ix, ar, rew = int(lvp2[r]), int(log["a"][r]), int(log["c"][r] == 1)
+                if ix >= 0:
+                    pulls[ix, ar] += 1; clicks[ix, ar] += rew
+                else:
+                    pulls[ar, :] += 1; clicks[ar, :] += rew
+        # the walk: evaluate_agent's step loop with the approach's update rule (oracle/train_oracle.py evolution())
+        wco = np.zeros((P, P)); wp = np.zeros((P, P)); wc = np.zeros((P, P)); lpv = 3; samples = samples0; kept = 0
+        u, z, v, a, c = (np.asarray(log[k]) for k in ("u", "z", "v", "a", "c"))
+        i = 0
+        while i < n:
+            j = i
+            while j < n and u[j] == u[i]:
+                j += 1
+            session, last_view = [], None
+            for r in range(i, j):
+                if z[r] == 0:
+                    session.append(int(v[r])); last_view = int(v[r]); continue
+                if r == j - 1:
+                    break
+                samples += 1
+                greedy = int(a[r]) == int(table[last_view])
+                upd = (not explored_only or not greedy) and (not window or samples % window == 0)
+                if upd:
+                    kept += 1
+                    if session:
+                        b = np.bincount(session, minlength=P).astype(np.float64).reshape(P, 1); wco += b @ b.T
+                    ix = lpv
+                    if session:
+                        lpv = session[-1]
+                    wp[ix, int(a[r])] += 1; wc[ix, int(a[r])] += int(c[r] == 1)
+                session = []
+            i = j
+        assert kept == view.keep_rows and samples == view.n_samples and kept > 3
+        assert np.array_equal(co, wco) and np.array_equal(pulls, wp) and np.array_equal(clicks, wc), (explored_only, window)
+        assert int(view.carry.item()) == lpv
