@@ -175,30 +175,34 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     // tf32 hi/lo UMMA tiles of the tensor-core sampler (layout: rg_tensor.cuh)
     int KC = 0, KCs = 0, nslab = 0;
     rg::tc::kt_slabs(K, &KC, &KCs, &nslab);
-    const size_t slab_floats = (size_t)2 * KCs * (rg::tc::CHUNK_BYTES_B / 4);   // one K slab of one B tile, hi + lo
-    const size_t tile_floats = slab_floats * nslab;
-    std::vector<float> GTC((size_t)nsub * (128 / rg::tc::TILE_N) * tile_floats, 0.f);
+    using rg::tc::EPC;
+    using rg::tc::opnd_t;
+    const size_t slab_elems = (size_t)2 * KCs * (rg::tc::CHUNK_BYTES_B / sizeof(opnd_t));   // one K slab of one B tile, hi + lo
+    const size_t tile_elems = slab_elems * nslab;
+    std::vector<opnd_t> GTC((size_t)nsub * (128 / rg::tc::TILE_N) * tile_elems);
+    std::memset(GTC.data(), 0, GTC.size() * sizeof(opnd_t));
+    bool opnd_range_ok = true;   // fp16 operands: the tensor mode is refused for parameters outside the element range
     for (int p = 0; p < nsub * 128; ++p) {
-        float *tile0 = GTC.data() + (size_t)(p / rg::tc::TILE_N) * tile_floats;
+        opnd_t *tile0 = GTC.data() + (size_t)(p / rg::tc::TILE_N) * tile_elems;
         const int row = p % rg::tc::TILE_N;
-        for (int k = 0; k < KC * 4; ++k) {
-            float *tile = tile0 + (size_t)(k / (4 * KCs)) * slab_floats;
-            const int kk = k % (4 * KCs);
+        for (int k = 0; k < KC * EPC; ++k) {
+            opnd_t *tile = tile0 + (size_t)(k / (EPC * KCs)) * slab_elems;
+            const int kk = k % (EPC * KCs);
             float x = 0.f;
             if (p < P) {
                 if (k < K) x = (float)(d->Gamma[(size_t)p * K + k] * kLog2e);
                 else if (k == K) x = (float)(d->mu_organic[p] * kLog2e);
                 else if (k == K + 1) x = 1.f;
+                if (!(std::fabs(x) <= rg::tc::kOpndMax / 2)) { opnd_range_ok = false; x = 0.f; }
             } else if (k == K) {
-                x = -1e30f;
+                x = rg::tc::kPadLogit;
             }
-            const float hi = rg::tc::tf32_hi(x);
-            tile[rg::tc::tile_index_b(0, KCs, row, kk)] = hi;
-            tile[rg::tc::tile_index_b(1, KCs, row, kk)] = rg::tc::tf32_hi(x - hi);
+            rg::tc::split_hi_lo(x, tile[rg::tc::tile_index_b(0, KCs, row, kk)], tile[rg::tc::tile_index_b(1, KCs, row, kk)]);
         }
     }
 
     cudaError_t ce = cudaSuccess;
+    e.tc_operands_ok = opnd_range_ok;
     if (ce == cudaSuccess) ce = upload(&e.d_GTC, GTC);
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT, GT);
     if (ce == cudaSuccess) ce = upload(&e.d_mu_o, mu);

@@ -24,7 +24,7 @@ struct EnvDev {
     double muabsmax;           // max_p |mu_organic[p]|
     const float *G32;          // [nsub][K+1][128] fp32 tiles of log2(e)*Gamma (row K = log2(e)*mu_organic)
     int nsub;                  // number of 128-product tiles
-    const float *GTC;          // [tiles][nslab][2][KCs][TILE_N/8][8][4] tf32 hi/lo UMMA tiles in K slabs (rg_tensor.cuh)
+    const void *GTC;           // [tiles][nslab][2][KCs][TILE_N/8][8][EPC] hi/lo UMMA operand tiles in K slabs (rg_tensor.cuh)
     int KC, KCs, nslab;        // 16-byte K chunks per operand row: padded total, per slab, slabs (KC = KCs * nslab)
     int change_omega_for_bandits;
     int time_mode;             // 0 default clock, 1 NormalTimeGenerator (include/recogym_b200.h rg_env_desc.time_generator)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "rg_device.cuh"
+#include "rg_tensor.cuh"
 
 struct rg_env_impl {
     int device = 0;
@@ -12,7 +13,8 @@ struct rg_env_impl {
     double *d_GammaT = nullptr, *d_mu_o = nullptr, *d_beta = nullptr, *d_mu_b = nullptr;
     float *d_GammaT32 = nullptr, *d_mu_o32 = nullptr;
     float *d_Gamma32 = nullptr;          // [nsub][K+1][128] fp32 tiles (fast path)
-    float *d_GTC = nullptr;              // [nsub][2][KC][16][8][4] tf32 hi/lo UMMA tiles (rg_tensor.cuh)
+    rg::tc::opnd_t *d_GTC = nullptr;     // [tiles][nslab][2][KCs][TILE_N/8][8][EPC] hi/lo UMMA operand tiles (rg_tensor.cuh)
+    bool tc_operands_ok = true;          // Gamma', mu' inside the operand element range (else: CUDA-core contraction)
     double *d_om_scratch = nullptr;      // RG_MATH_TENSOR: omega rows of the resident slots
     size_t om_scratch_bytes = 0;
     double *d_csum_scratch = nullptr;    // CUDA-core form with large P x K: re-sampling partial sums spilled to global memory

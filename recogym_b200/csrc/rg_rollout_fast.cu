@@ -759,7 +759,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
     float *om32 = (float *)(smem + L.om32);
     float *tilesum = (float *)(smem + L.tilesum);
     float *gtile = (float *)(smem + L.gtile);
-    float *a_tile = (float *)(smem + L.atile);
+    tc::opnd_t *a_tile = (tc::opnd_t *)(smem + L.atile);
     uint64_t *dfull = mbar + kMaxStages;                   // TC: accumulator tile ready, one per TMEM buffer
     uint64_t *dempty = dfull + NBUF;                       // TC: accumulator tile drained by the 4 epilogue warps that read it
     uint32_t *tmem_slot = (uint32_t *)(dempty + NBUF);
@@ -809,7 +809,8 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                         case 2: tc::issue_slab_mmas_lean<2>(td, a_lo, a_term16, b_lo, accf, el); break;
                         case 4: tc::issue_slab_mmas_lean<4>(td, a_lo, a_term16, b_lo, accf, el); break;
                         case 6: tc::issue_slab_mmas_lean<6>(td, a_lo, a_term16, b_lo, accf, el); break;
-                        default: tc::issue_slab_mmas_lean<8>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        case 8: tc::issue_slab_mmas_lean<8>(td, a_lo, a_term16, b_lo, accf, el); break;
+                        default: tc::issue_slab_mmas_lean<10>(td, a_lo, a_term16, b_lo, accf, el); break;
                     }
                     if (sl == nslab - 1) umma_commit_s(dfull_s + buf * 8u, el);   // the accumulator tile is complete
                     RG_PROF_ONLY(const long long pd = clock64(); pf[0] += pd - pc; pf[1] += pc - pb; pf[2] += pb - pa; pf[3] += 1ull;
@@ -910,7 +911,7 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
         const int sub = (int)(seq % (unsigned)nunit);
         mbar_expect_tx(&mbar[stage], tile_bytes);
         if (TC)
-            tma_bulk_g2s((unsigned char *)gtile + (size_t)stage * tile_bytes, env.GTC + (size_t)sub * (tile_bytes / 4),
+            tma_bulk_g2s((unsigned char *)gtile + (size_t)stage * tile_bytes, (const unsigned char *)env.GTC + (size_t)sub * tile_bytes,
                          tile_bytes, &mbar[stage]);
         else
             tma_bulk_g2s(gtile + (size_t)stage * K1 * SUB, env.G32 + (size_t)sub * K1 * SUB, tile_bytes, &mbar[stage]);
@@ -992,7 +993,12 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                     // tensor-core tile sums: dropped lo*lo term (2^-22 per product term, doubled) and the fp32
                     // accumulation of the UMMA, whose rounding is undocumented: 8 roundings at the largest
                     // magnitude.  Measured (tests): <= 0.5 of this bound for K = 5..64.
-                    const double dtc = aub * 4.76837158203125e-07 + 8.0 * u24 * (aub + fabs(shift));
+                    double dtc = aub * 4.76837158203125e-07 + 8.0 * u24 * (aub + fabs(shift));
+#if RG_TC_F16
+                    // fp16 operand elements: a `lo` term below 2^-14 is subnormal and carries an absolute error of up to
+                    // 2^-25 per element: sum_k (|dG_k| |w_k| + |G'_k| |dw_k|) + the mu' and shift columns
+                    dtc += 2.98023223876953125e-08 * (sqrt((double)K) * (nrm + env.gmax * kLog2e) + 2.0);
+#endif
                     dl2 = fmax(dl2, dtc);
                 }
                 // relative mass error: exp of that, ex2.approx (2^-21 covers its 2 ulp), fp32 partial sums of pass 1
@@ -1023,22 +1029,23 @@ __device__ __forceinline__ void rollout_cta_body(const Params &p) {
                 const bool alive = row < nlive;
                 const double *om = om64 + (size_t)(alive ? pos2slot[row] : 0) * KP;
                 const float nshift = alive ? -s_shift[row] : 0.f;
+                bool in_range = true;
                 for (int c = c0; c < c0 + KC / 2; ++c) {
-                    float x[4];
+                    union { tc::opnd_t e[tc::EPC]; uint4 v; } hi, lo;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = 4 * c + j;
+                    for (int j = 0; j < tc::EPC; ++j) {
+                        const int k = tc::EPC * c + j;
                         float v = 0.f;
                         if (alive) v = k < K ? (float)om[k] : (k == K ? 1.f : (k == K + 1 ? nshift : 0.f));
-                        x[j] = v;
+                        if (!(fabsf(v) <= tc::kOpndMax)) { in_range = false; v = 0.f; }
+                        tc::split_hi_lo(v, hi.e[j], lo.e[j]);
                     }
-                    float4 hi, lo;
-                    hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
-                    lo.x = tc::tf32_hi(x[0] - hi.x); lo.y = tc::tf32_hi(x[1] - hi.y);
-                    lo.z = tc::tf32_hi(x[2] - hi.z); lo.w = tc::tf32_hi(x[3] - hi.w);
-                    *reinterpret_cast<float4 *>(a_tile + tc::tile_index(0, KC, row, 4 * c)) = hi;
-                    *reinterpret_cast<float4 *>(a_tile + tc::tile_index(1, KC, row, 4 * c)) = lo;
+                    *reinterpret_cast<uint4 *>(a_tile + tc::tile_index(0, KC, row, tc::EPC * c)) = hi.v;
+                    *reinterpret_cast<uint4 *>(a_tile + tc::tile_index(1, KC, row, tc::EPC * c)) = lo.v;
                 }
+                // a latent state (or shift) outside the operand element range cannot be sampled by this kernel: counted in
+                // totals[9] ("must be 0"), like the overflow of a view list
+                if (!in_range && p.out.totals) atomicAdd(p.out.totals + 9, 1ull);
             }
             tc::fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core
             tc::tc_fence_before();

@@ -36,9 +36,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 
 // Writes the A operand (omega tile) of 128 users into shared memory: hi and lo tf32 terms.
 // omega: [128][K] binary64 (row stride ldo), shift: [128] fp32 (log2 units).  All threads of the CTA.
-__device__ void build_a_tile(float *a_tile, int KC, int K, const double *omega, int ldo, const float *shift,
+__device__ void build_a_tile(opnd_t *a_tile, int KC, int K, const double *omega, int ldo, const float *shift,
                              int nrows, int tid, int nthreads) {
-    const int KT = KC * 4;
+    const int KT = KC * EPC;
     for (int idx = tid; idx < TILE * KT; idx += nthreads) {
         const int row = idx / KT, k = idx - row * KT;
         float x = 0.f;
@@ -47,22 +47,19 @@ __device__ void build_a_tile(float *a_tile, int KC, int K, const double *omega, 
             else if (k == K) x = 1.f;
             else if (k == K + 1) x = -shift[row];
         }
-        const float hi = tf32_hi(x);
-        const float lo = tf32_hi(x - hi);
-        a_tile[tile_index(0, KC, row, k)] = hi;
-        a_tile[tile_index(1, KC, row, k)] = lo;
+        split_hi_lo(x, a_tile[tile_index(0, KC, row, k)], a_tile[tile_index(1, KC, row, k)]);
     }
 }
 
-__global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict__ GTC, int nsub, int KC, int KCs,
+__global__ void __launch_bounds__(128) tc_logits_kernel(const opnd_t *__restrict__ GTC, int nsub, int KC, int KCs,
                                                         int nslab, int K,
                                                         const double *__restrict__ omega,
                                                         const float *__restrict__ shift, float *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned a_bytes = 2u * (unsigned)KC * CHUNK_BYTES, tile_bytes = 2u * (unsigned)KCs * CHUNK_BYTES_B;  // one slab
-    float *a_tile = (float *)smem;
-    float *b_tile = (float *)(smem + a_bytes);
+    opnd_t *a_tile = (opnd_t *)smem;
+    opnd_t *b_tile = (opnd_t *)(smem + a_bytes);
     uint64_t *bars = (uint64_t *)(smem + a_bytes + tile_bytes);  // [0] TMA, [1] MMA
     uint32_t *tmem_slot = (uint32_t *)(bars + 2);
 
@@ -85,7 +82,7 @@ __global__ void __launch_bounds__(128) tc_logits_kernel(const float *__restrict_
             const unsigned parity = unit & 1u;
             if (tid == 0) {
                 mbar_expect_tx(&bars[0], tile_bytes);
-                bulk_g2s(b_tile, GTC + (size_t)unit * (tile_bytes / 4), tile_bytes, &bars[0]);
+                bulk_g2s(b_tile, (const unsigned char *)GTC + (size_t)unit * tile_bytes, tile_bytes, &bars[0]);
             }
             mbar_wait(&bars[0], parity);
             if (tid == 0) {

@@ -15,9 +15,34 @@
 // Columns: k < K: log2e-scaled Gamma / omega;  k = K: mu' / 1;  k = K+1: 1 / -shift_u;  rest 0.
 #pragma once
 #include <cstdint>
+#ifndef RG_TC_F16
+#define RG_TC_F16 1   // operand element type of the UMMA: 1 = fp16 hi/lo (kind::f16, K = 16 per MMA), 0 = tf32 hi/lo (K = 8)
+#endif
+#if RG_TC_F16
+#include <cuda_fp16.h>
+#endif
 
 namespace rg {
 namespace tc {
+
+// Operand elements.  Both forms split a value into two 11-significant-bit terms x = hi + lo and contract three of the
+// four products (the dropped lo*lo term is ~2^-22 relative), accumulating in fp32.  fp16 elements carry the same
+// significand as tf32 in half the bytes: one MMA step covers K = 16 instead of 8, and a B tile is half the L2 -> shared
+// memory traffic -- which, not the tensor pipe, is what pass 1 waits for with two CTAs per SM.  The price
+// is fp16's exponent range: |x| must stay below 65504 (checked: Gamma', mu' at rg_env_create, omega and the shift when the
+// A tile is built), and a `lo` term below 2^-14 is subnormal, i.e. carries an ABSOLUTE error of up to 2^-25 instead of a
+// relative one (a term of the error bound: rollout_cta_body, phase A).
+#if RG_TC_F16
+typedef __half opnd_t;
+constexpr int EPC = 8;               // elements per 16-byte K chunk
+constexpr float kOpndMax = 65000.f;  // largest magnitude an operand may have
+constexpr float kPadLogit = -60000.f; // mu' of the padding products (exactly representable; ex2 of it is 0)
+#else
+typedef float opnd_t;
+constexpr int EPC = 4;
+constexpr float kOpndMax = 3.0e38f;
+constexpr float kPadLogit = -1e30f;
+#endif
 
 constexpr int TILE = 128;            // users per tile (UMMA M)
 #ifndef RG_TC_TILE_N
@@ -28,7 +53,7 @@ constexpr int CHUNK_BYTES = 2048;    // A: one 16-byte K chunk of all 128 rows
 constexpr int CHUNK_BYTES_B = TILE_N / 8 * 128;  // B: one 16-byte K chunk of all TILE_N rows
 
 __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks (even: one MMA eats two)
-    int kc = (K + 2 + 3) / 4;
+    int kc = (K + 2 + EPC - 1) / EPC;
     return (kc + 1) & ~1;
 }
 
@@ -38,7 +63,7 @@ __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks
 // stage stays 24 KB (K = 64 -> 3 slabs).  KC = nslab * KCs is the padded total the A tile is built with.
 __host__ __device__ inline void kt_slabs(int K, int *KC, int *KCs, int *nslab) {
     const int kc0 = kt_chunks(K);
-    if (kc0 <= 8) { *KCs = kc0; *nslab = 1; }
+    if (kc0 <= (RG_TC_F16 ? 10 : 8)) { *KCs = kc0; *nslab = 1; }   // fp16: K = 64 is one 40 KB slab
     else { *KCs = 6; *nslab = (kc0 + 5) / 6; }
     *KC = *KCs * *nslab;
 }
@@ -49,13 +74,25 @@ __host__ __device__ inline float tf32_hi(float x) {
     v.u &= 0xFFFFE000u;
     return v.f;
 }
-
-// float index of element (row, k) of term t inside one operand tile [2 terms][KC][rows/8][8][4]
-__host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {  // A: 128 rows
-    return ((((size_t)t * KC + (k >> 2)) * 16 + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+#if defined(__CUDACC__)
+// x ~= hi + lo in operand elements
+__host__ __device__ inline void split_hi_lo(float x, opnd_t &hi, opnd_t &lo) {
+#if RG_TC_F16
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+#else
+    hi = tf32_hi(x);
+    lo = tf32_hi(x - hi);
+#endif
 }
-__host__ __device__ inline size_t tile_index_b(int t, int KC, int row, int k) {  // B: 64 rows
-    return ((((size_t)t * KC + (k >> 2)) * (TILE_N / 8) + (row >> 3)) * 8 + (row & 7)) * 4 + (k & 3);
+#endif
+
+// element index of (row, k) of term t inside one operand tile [2 terms][KC][rows/8][8][EPC]
+__host__ __device__ inline size_t tile_index(int t, int KC, int row, int k) {  // A: 128 rows
+    return ((((size_t)t * KC + (k / EPC)) * 16 + (row >> 3)) * 8 + (row & 7)) * EPC + (k % EPC);
+}
+__host__ __device__ inline size_t tile_index_b(int t, int KC, int row, int k) {  // B: TILE_N rows
+    return ((((size_t)t * KC + (k / EPC)) * (TILE_N / 8) + (row >> 3)) * 8 + (row & 7)) * EPC + (k % EPC);
 }
 
 #if defined(__CUDACC__)
@@ -66,8 +103,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
            (1ull << 46);
 }
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = 64 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)TILE_N >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D fp32 (bit 4), A/B format (bits 7, 10: 0 = f16, 2 = tf32), both K-major, M = 128, N = TILE_N
+// (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kOpndFmt = RG_TC_F16 ? 0u : 2u;
+constexpr uint32_t kIdescTf32 = (1u << 4) | (kOpndFmt << 7) | (kOpndFmt << 10) | (((uint32_t)TILE_N >> 3) << 17) | ((128u >> 4) << 24);
+#if RG_TC_F16
+#define RG_UMMA_KIND "kind::f16"
+#else
+#define RG_UMMA_KIND "kind::tf32"
+#endif
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols)
@@ -87,7 +131,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1." RG_UMMA_KIND " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -139,7 +183,7 @@ __device__ __forceinline__ void umma_tf32_pred(uint32_t tmem_d, uint64_t desc_a,
         "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "setp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "@q tcgen05.mma.cta_group::1." RG_UMMA_KIND " [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
         : "memory");
 }

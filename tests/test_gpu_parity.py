@@ -358,7 +358,7 @@ def test_drivers_test_agent_and_verify_agents():
 
 
 def test_tensor_core_logits_match_binary64():
-    """tcgen05 contraction (tf32 hi/lo split, three UMMA terms) against binary64 logits: validates the
+    """tcgen05 contraction (fp16 hi/lo operand split, three UMMA terms, fp32 accumulation) against binary64 logits: validates the
     UMMA descriptors / operand layout / TMEM read-back and measures the error the tensor-core sampler's
     filter has to cover."""
     import ctypes as C
@@ -389,7 +389,7 @@ def test_tensor_core_logits_match_binary64():
         scale = np.abs(ref).max()
         print("tc logits P=%d K=%d: max abs err %.3e (log2 units), max |ref| %.1f" % (P, K, err.max(), scale))
         assert err.max() < 2e-4, (P, K, err.max())
-        assert (got[:, P:] < -1e29).all()          # padded products carry no mass
+        assert (got[:, P:] < -5e4).all()           # padded products carry no mass (ex2 of their logit is exactly 0)
         de.close()
 
 
