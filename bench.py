@@ -427,7 +427,7 @@ def main():
     line = {
         "metric": "simulated user-steps/sec", "value": value, "unit": "user-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tensor": "f64+tf32x2", "fast": "f64+f32", "exact": "f64"}[args.math],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tensor": "f64+f16x2", "fast": "f64+f32", "exact": "f64"}[args.math],
         "data": "synthetic",
         "config": {"workload": wl["label"], "num_products": P, "K": K, "users_per_gpu_per_step": U,
                    "policy": wl["policy"], "device_policies": [p for _, p, _ in policies], "math_mode": args.math, "seed": SEED, "parallelism": "users sharded dp%d" % world,
@@ -457,8 +457,8 @@ def main():
                                  "unit": "Tex2/s", "frac": organic_per_s * P / mufu_peak,
                                  "ex2_per_organic_draw": P}
         line["roofline_tensor"] = {"bound": "tensor", "achieved": organic_per_s * 3 * 2.0 * P * (K + 2) / 1e12,
-                                   "peak": None, "unit": "TFLOP/s (tf32, three-term split)",
-                                   "note": "not the binding unit: <20% tensor-pipe active (profiles/)"}
+                                   "peak": None, "unit": "TFLOP/s (fp16 hi/lo operands, three-term split, fp32 accumulate)",
+                                   "note": "not the binding unit: ~30% tensor-pipe active (profiles/)"}
     else:
         line["roofline_fp32"] = {"bound": "fp32-fma", "achieved": per_gpu_steps_s * flops_per_step / 1e12,
                                  "peak": fp32_peak / 1e12, "unit": "TFLOP/s",

@@ -39,7 +39,7 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 }
 
 void free_env(rg_env_impl &e) {
-    cudaFree(e.d_GammaT); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
+    cudaFree(e.d_GammaT); cudaFree(e.d_GammaB); cudaFree(e.d_mu_o); cudaFree(e.d_beta); cudaFree(e.d_mu_b);
     cudaFree(e.d_GammaT32); cudaFree(e.d_mu_o32); cudaFree(e.d_Gamma32); cudaFree(e.d_GTC); cudaFree(e.d_om_scratch); cudaFree(e.d_csum_scratch); cudaFree(e.d_gsum); cudaFree(e.d_views); cudaFree(e.diag); cudaFree(e.d_t4); cudaFree(e.d_host_arena); cudaFree(e.d_hole_cdf);
 }
 
@@ -204,6 +204,14 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
     cudaError_t ce = cudaSuccess;
     e.tc_operands_ok = opnd_range_ok;
     if (ce == cudaSuccess) ce = upload(&e.d_GTC, GTC);
+    // the same binary64 Gamma in 8-product blocks for the DMMA sweeps of tier 2 (rg_rollout_fast.cu): one product group's
+    // operands are one contiguous run of KQ * 64 bytes instead of 64-byte pieces of K rows 8 * Ppad bytes apart
+    const int KQ = 4 * rg::dmma_ksteps(K);
+    const size_t nblk = (size_t)((P + 255) / 256) * 32;
+    std::vector<double> GB(nblk * KQ * 8, 0.0);
+    for (int p = 0; p < P; ++p)
+        for (int k = 0; k < K; ++k) GB[((size_t)(p >> 3) * KQ + k) * 8 + (p & 7)] = d->Gamma[(size_t)p * K + k];
+    if (ce == cudaSuccess) ce = upload(&e.d_GammaB, GB);
     if (ce == cudaSuccess) ce = upload(&e.d_GammaT, GT);
     if (ce == cudaSuccess) ce = upload(&e.d_mu_o, mu);
     if (ce == cudaSuccess) ce = upload(&e.d_beta, beta);
@@ -225,6 +233,7 @@ int rg_env_create(const rg_env_desc *d, int device, rg_env **out) {
 
     rg::EnvDev &v = e.dev;
     v.P = P; v.K = K; v.Ppad = Ppad;
+    v.GammaB = e.d_GammaB; v.KQ = KQ;
     v.GammaT = e.d_GammaT; v.mu_o = e.d_mu_o; v.beta = e.d_beta; v.mu_b = e.d_mu_b;
     v.GammaT32 = e.d_GammaT32; v.mu_o32 = e.d_mu_o32;
     for (int r = 0; r < 3; ++r) {

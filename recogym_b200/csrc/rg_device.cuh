@@ -9,10 +9,16 @@ namespace rg {
 constexpr int kMaxK = 128;          // latent dimension limit of the kernels
 constexpr int kSuperChunk = 1024;   // products per recorded partial sum in the exact sampler
 
+// k-steps (of 4) of the DMMA sweep template instantiated for K (rg_rollout_fast.cu, block_sample_views)
+__host__ __device__ inline int dmma_ksteps(int K) { return K <= 20 ? 5 : (K <= 32 ? 8 : (K <= 64 ? 16 : 32)); }
+
 // Static parameters as the kernels see them (all pointers are device memory owned by rg_env).
 struct EnvDev {
     int P, K, Ppad;            // Ppad = P rounded up to 32
     const double *GammaT;      // [K][Ppad]  K-major f64: lane-consecutive products are contiguous
+    const double *GammaB;      // [ceil(P/256)*32][KQ][8] f64: the (8 products x KQ) operand block of a DMMA product group is
+                               // contiguous (KQ = 4 * dmma_ksteps(K), zero rows; zero products beyond P): tier-2 sweeps
+    int KQ;
     const double *mu_o;        // [Ppad]
     const double *beta;        // [P][K] row-major f64 (one row gathered per bandit event)
     const double *mu_b;        // [P]

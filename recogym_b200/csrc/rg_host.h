@@ -10,7 +10,7 @@ struct rg_env_impl {
     int num_sms = 0;
     rg::EnvDev dev{};
     // owned device allocations
-    double *d_GammaT = nullptr, *d_mu_o = nullptr, *d_beta = nullptr, *d_mu_b = nullptr;
+    double *d_GammaT = nullptr, *d_mu_o = nullptr, *d_beta = nullptr, *d_mu_b = nullptr, *d_GammaB = nullptr;
     float *d_GammaT32 = nullptr, *d_mu_o32 = nullptr;
     float *d_Gamma32 = nullptr;          // [nsub][K+1][128] fp32 tiles (fast path)
     rg::tc::opnd_t *d_GTC = nullptr;     // [tiles][nslab][2][KCs][TILE_N/8][8][EPC] hi/lo UMMA operand tiles (rg_tensor.cuh)

@@ -370,31 +370,31 @@ __device__ __forceinline__ void batch_partial_sums_mma(const EnvDev &env, const 
     const int g = lane >> 2, q = lane & 3;
     const int gu = g < nb ? g : nb - 1;          // rows beyond the batch repeat the last user (results discarded)
     double a[KS];
-    const double *grow[KS];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const int k = 4 * ks + q;
-        a[ks] = k < K ? om_s[gu * KP + k] : 0.0;                       // zero omega: the clamped Gamma row adds 0
-        grow[ks] = env.GammaT + (size_t)(k < K ? k : K - 1) * Ppad;
+        a[ks] = k < K ? om_s[gu * KP + k] : 0.0;
     }
+    // B operands from the blocked copy of Gamma: the 8 products x KQ rows of a product group are contiguous
+    const double *gb = env.GammaB + q * 8 + g;
+    const size_t blk = (size_t)env.KQ * 8;
     const double sv = shiftv[gu];
     const int nch = (Ppad + CHUNK - 1) / CHUNK;
     for (int c = warp; c < nch; c += nwarps) {
         double part = 0.0, perr = 0.0;
         for (int g0 = 0; g0 < CHUNK / 8; g0 += G) {
             double acc[G][2];
-            int pb[G];
+            const double *pb[G];
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 acc[i][0] = 0.0; acc[i][1] = 0.0;
-                const int p = c * CHUNK + (g0 + i) * 8 + g;
-                pb[i] = p < Ppad ? p : Ppad - 1;
+                pb[i] = gb + (size_t)(c * (CHUNK / 8) + g0 + i) * blk;
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 double b[G];
 #pragma unroll
-                for (int i = 0; i < G; ++i) b[i] = __ldg(grow[ks] + pb[i]);
+                for (int i = 0; i < G; ++i) b[i] = __ldg(pb[i] + 32 * ks);
 #pragma unroll
                 for (int i = 0; i < G; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a[ks], b[i]);
             }
@@ -421,6 +421,98 @@ __device__ __forceinline__ void batch_partial_sums_mma(const EnvDev &env, const 
             csum[(size_t)g * ncs + c] = part;
             esum[(size_t)g * ncs + c] = perr;
         }
+    }
+}
+
+// The same sweep for LARGE K (K > 20: KS >= 8 k-steps per product group), where it is bound by the latency of the Gamma
+// loads instead of the FP64 pipe: at C4 (P = 100 000, K = 64) the binary64 Gamma is 51 MB, mostly out of L2 by the time a
+// sweep starts, and the compiler schedules the form above as load, DMMA, load, DMMA (one or two loads in flight per lane:
+// 8 B/clk per SM).  Here the loads run DEPTH - 1 = 7 k-steps ahead of the DMMAs in a register ring (14 loads in flight per
+// lane), across product groups and chunks, in an order pinned by volatile asm; omega comes from shared memory per k-step
+// (16 steps of fragments do not fit the register budget next to the ring).
+__device__ __forceinline__ double ldg_f64_pinned(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <int KS>
+__device__ __forceinline__ void batch_partial_sums_mma_deep(const EnvDev &env, const double *om_s, int KP, double *csum,
+                                                            double *esum, int ncs, int nb, const double *shiftv, int lane,
+                                                            int warp, int nwarps) {
+    constexpr int G = 2;       // 8-product groups per step (independent accumulators)
+    constexpr int DEPTH = 8;   // ring of k-steps: step ks + DEPTH - 1 is loaded while step ks is multiplied
+    static_assert(KS % DEPTH == 0, "a group's k-steps must map onto the same ring entries in every group");
+    const int K = env.K, P = env.P, Ppad = env.Ppad;
+    const int g = lane >> 2, q = lane & 3;
+    const int gu = g < nb ? g : nb - 1;          // rows beyond the batch repeat the last user (results discarded)
+    const double *arow = om_s + gu * KP;
+    const double *gb = env.GammaB + q * 8 + g;   // blocked copy of Gamma: one product group = one contiguous run
+    const size_t blk = (size_t)env.KQ * 8;
+    const double sv = shiftv[gu];
+    const int nch = (Ppad + CHUNK - 1) / CHUNK;
+    constexpr int NG = CHUNK / 8;   // 8-product groups per chunk
+    int c = warp, g0 = 0;
+    if (c >= nch) return;
+    auto group_products = [&](int cc, int gg, const double *(&pbv)[G]) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) pbv[i] = gb + (size_t)(cc * NG + gg + i) * blk;
+    };
+    double b[DEPTH][G];
+    const double *pb[G], *pbn[G];
+    group_products(c, 0, pb);
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) b[d][i] = ldg_f64_pinned(pb[i] + 32 * d);
+    }
+    double part = 0.0, perr = 0.0;
+    for (;;) {
+        int cn = c, gn = g0 + G;
+        if (gn >= NG) { gn = 0; cn = c + nwarps; }
+        const bool has_next = cn < nch;
+        group_products(has_next ? cn : c, has_next ? gn : g0, pbn);   // (no next group: harmless re-loads)
+        double acc[G][2];
+#pragma unroll
+        for (int i = 0; i < G; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int sn = ks + DEPTH - 1;   // the step loaded now: of this group, or of the next one
+            const int kn = sn < KS ? sn : sn - KS;
+#pragma unroll
+            for (int i = 0; i < G; ++i) b[sn % DEPTH][i] = ldg_f64_pinned((sn < KS ? pb[i] : pbn[i]) + 32 * kn);
+            const double a = 4 * ks + q < K ? arow[4 * ks + q] : 0.0;
+#pragma unroll
+            for (int i = 0; i < G; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a, b[ks % DEPTH][i]);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int p0 = c * CHUNK + (g0 + i) * 8 + 2 * q;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = p0 + h;
+                if (j < P) {
+                    const double x = (acc[i][h] + __ldg(env.mu_o + j)) * 1.4426950408889634074 - sv;
+                    const double m = (double)ex2_approx((float)x);
+                    part += m;
+                    perr = fma(m, fma(fabs(x), 4.14e-8, 4.8e-7), perr);
+                }
+            }
+        }
+        if (gn == 0) {   // last group of chunk c
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            perr += __shfl_xor_sync(0xffffffffu, perr, 1);
+            perr += __shfl_xor_sync(0xffffffffu, perr, 2);
+            if (q == 0 && g < nb) {
+                csum[(size_t)g * ncs + c] = part;
+                esum[(size_t)g * ncs + c] = perr;
+            }
+            part = 0.0; perr = 0.0;
+        }
+        if (!has_next) break;
+        c = cn; g0 = gn;
+#pragma unroll
+        for (int i = 0; i < G; ++i) pb[i] = pbn[i];
     }
 }
 
@@ -467,9 +559,9 @@ __device__ __noinline__ void block_sample_views(const EnvDev &env, const double 
     if (T2) {   // FP64 tensor path (any nb <= 8 in one pass)
 #endif
         if (K <= 20) batch_partial_sums_mma<5>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
-        else if (K <= 32) batch_partial_sums_mma<8>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
-        else if (K <= 64) batch_partial_sums_mma<16>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
-        else batch_partial_sums_mma<32>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else if (K <= 32) batch_partial_sums_mma_deep<8>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else if (K <= 64) batch_partial_sums_mma_deep<16>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
+        else batch_partial_sums_mma_deep<32>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps);
     } else
     switch (nb) {
         case 1: batch_partial_sums<1, 8, T2>(env, om_s, KP, csum, esum, ncs, nb, sh_shift, lane, warp, nwarps); break;
