@@ -79,21 +79,36 @@ class BanditCount(Agent):
     # ---- device residency (recogym_b200/logs.py) --------------------------------------------------------------
     _stats = None
 
-    def device_train(self, log):
-        """`train` for every bandit row of a DeviceLog (scatter-add kernel).  The log must have been generated with
-        prev_last_view = self.device_last_view()."""
+    def _device_stats(self, device):
         from ..logs import CountStats
         import torch
         if self._stats is None:
-            self._stats = CountStats(self.config.num_products, log.env.device, organic=False, bandit=True,
+            self._stats = CountStats(self.config.num_products, device, organic=False, bandit=True,
                                      sparse=self._sp is not None)
             if self._sp is None:
                 self._stats.pulls.copy_(torch.as_tensor(self.pulls_a.astype(np.int64)))
                 self._stats.clicks.copy_(torch.as_tensor(self.clicks_a.astype(np.int64)))
             elif self._sp.n_cells() or self._sp.row_a:
                 self._stats.load_host(None, self._sp)
-        self._stats.train(log)
-        self.last_product_viewed = None if self._stats.last_view < 0 else int(self._stats.last_view)
+        return self._stats
+
+    def device_train(self, log):
+        """`train` for every bandit row of a DeviceLog (scatter-add kernel).  The log must have been generated with
+        prev_last_view = self.device_last_view()."""
+        stats = self._device_stats(log.env.device)
+        stats.train(log)
+        self.last_product_viewed = None if stats.last_view < 0 else int(stats.last_view)
+
+    def device_train_sharded(self, log, final_view, group=None):
+        """`log` holds THIS rank's shard of the users of a training log, its `lvp` column already chained to the lower
+        ranks' shards (parallel.resolve_carry); `final_view` = last_product_viewed after the WHOLE log.  The shard's
+        statistics go into a zero copy; the sum over the ranks is added to the replicated statistics."""
+        stats = self._device_stats(log.env.device)
+        delta = stats.zeros_like()
+        delta.train(log)
+        stats.add_reduced(delta, group)
+        stats.last_view = int(final_view)
+        self.last_product_viewed = None if final_view < 0 else int(final_view)
 
     def device_last_view(self):
         return -1 if self.last_product_viewed is None else int(self.last_product_viewed)

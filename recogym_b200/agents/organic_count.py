@@ -59,19 +59,30 @@ class OrganicCount(Agent):
     # ---- device residency (recogym_b200/logs.py): train() over a whole fused log, act() as a table ----------
     _stats = None
 
-    def device_train(self, log):
-        """`train` for every observation of a DeviceLog (scatter-add kernel); the statistics then live on the GPU
-        until `sync_host()`."""
+    def _device_stats(self, device):
         from ..logs import CountStats
         import torch
         if self._stats is None:
-            self._stats = CountStats(self.config.num_products, log.env.device, organic=True, bandit=False,
+            self._stats = CountStats(self.config.num_products, device, organic=True, bandit=False,
                                      sparse=self._sp is not None)
             if self._sp is None:
                 self._stats.co_counts.copy_(torch.as_tensor(self.co_counts.astype(np.int64)))
             elif self._sp.n_cells():
                 self._stats.load_host(self._sp, None)
-        self._stats.train(log)
+        return self._stats
+
+    def device_train(self, log):
+        """`train` for every observation of a DeviceLog (scatter-add kernel); the statistics then live on the GPU
+        until `sync_host()`."""
+        self._device_stats(log.env.device).train(log)
+
+    def device_train_sharded(self, log, final_view, group=None):
+        """`log` holds THIS rank's shard of the users of a training log: the shard's statistics go into a zero copy and
+        the sum over the ranks is added to the (replicated) statistics -- one all-reduce per step boundary."""
+        stats = self._device_stats(log.env.device)
+        delta = stats.zeros_like()
+        delta.train(log)
+        stats.add_reduced(delta, group)
 
     def sync_host(self):
         if self._stats is not None:

@@ -69,17 +69,34 @@ def _device_evolution_agent(agent):
 
 
 def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps, training_approach,
-                           math_mode=None, sliding_window_samples=10000):
+                           math_mode=None, sliding_window_samples=10000, group=None, sharded=None):
     """evaluate_agent (evaluate_agent.py:51-146) with every phase on the GPU: the warm-up users are rolled out under
     the env's logging policy and the agent trains on their log (RG_TRAIN_EVOLUTION_INIT); each evolution step is ONE
     fused rollout of the frozen acting policy -- the table, or EpsilonGreedy(epsilon) around it (RG_POLICY_EPS_TABLE) --
     whose ordered log feeds the training copy (RG_TRAIN_EVOLUTION_STEP, all of its train calls or the ones the
     TrainingApproach selects: logs.MaskedTrainingLog) through the scatter-add kernels; the next acting table is a row
-    arg-max kernel.  'greedy' of a logged action: it equals the acting table's (an exploring action never does)."""
+    arg-max kernel.  'greedy' of a logged action: it equals the acting table's (an exploring action never does).
+
+    Multi-GPU (torch.distributed initialised, one process per GPU): the users of the warm-up and of
+    every step are sharded over the ranks in contiguous id ranges; each rank rolls out and logs its shard, collects the
+    shard's training statistics into a zero copy, and the sums over the ranks are added to the replicated statistics at
+    the step boundary (`device_train_sharded`: one all-reduce per matrix, an all-gather of cells for the sparse tables),
+    so every rank computes the same next acting table.  What the reference's strictly sequential loop threads through
+    the users -- BanditCount's last viewed product and the running sample count of the sliding windows -- is chained
+    across the shards with two small all-gathers (parallel.resolve_carry).  Counters are all-reduced per step.  The
+    result equals the single-GPU one for any number of ranks (scripts/dist_evolution_check.py)."""
     import numpy as np
     import torch
     from . import _lib as L
     from .logs import MaskedTrainingLog, generate_logs_device
+    from .parallel import allgather_ints, allreduce_counters, dist_info, resolve_carry, shard_range
+    rank, world = dist_info(group)
+    if sharded is None:
+        sharded = world > 1
+    if sharded and min(num_initial_train_users if num_initial_train_users > 0 else world, num_step_users) < world:
+        sharded = False                  # fewer users than ranks: every rank computes the whole thing
+    if not sharded:
+        rank, world = 0, 1
     mm = L.MATH_TENSOR if math_mode is None else math_mode
     de = env.device_env
     P = env.config.num_products
@@ -93,11 +110,25 @@ def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_
     lpv = lambda a: a.device_last_view() if hasattr(a, "device_last_view") else -1
     initial_agent = deepcopy(inner)
     log_pol = device_policy(env.agent, P) if env.agent else {"policy": "uniform"}
+    def chain(view, n, prev0):
+        """sharded logs are derived with prev_last_view = -1: point the rows that start from "no previous view" at the view
+        the lower ranks' shards end with; -> last_product_viewed after the whole log"""
+        carries = [c[0] for c in allgather_ints([int(view.carry.item())], de.torch_device, group)]
+        prev, final = resolve_carry(carries, rank, prev0)
+        if prev >= 0 and n:
+            col = view.lvp[:n]
+            col[col == -1] = prev
+        return final
+
     if num_initial_train_users > 0:
-        log = generate_logs_device(de, num_initial_train_users, log_pol["policy"], log_pol.get("table"), None, 0, 0, mm,
-                                   prev_last_view=lpv(inner), train_mode=L.TRAIN_EVOLUTION_INIT,
+        first, count = shard_range(num_initial_train_users, rank, world, 0)
+        log = generate_logs_device(de, count, log_pol["policy"], log_pol.get("table"), None, first, 0, mm,
+                                   prev_last_view=lpv(inner) if world == 1 else -1, train_mode=L.TRAIN_EVOLUTION_INIT,
                                    epsilon=log_pol.get("epsilon", 0.0))
-        inner.device_train(log)
+        if world == 1:
+            inner.device_train(log)
+        else:
+            inner.device_train_sharded(log, chain(log, log.rows, lpv(inner)), group)
     unique_user_id = num_initial_train_users
     rewards = {EvolutionCase.SUCCESS: [], EvolutionCase.SUCCESS_GREEDY: [], EvolutionCase.FAILURE: [],
                EvolutionCase.FAILURE_GREEDY: [], EvolutionCase.ACTIONS: dict()}
@@ -108,24 +139,41 @@ def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_
         pol = acting.device_policy()
         if not (hasattr(pol["table"], "is_cuda") and pol["table"].is_cuda):
             pol = {**pol, "table": torch.as_tensor(np.ascontiguousarray(pol["table"], np.int32), device=de.torch_device)}
-        log = generate_logs_device(de, num_step_users, "eps_table" if eps > 0.0 else pol["policy"], pol.get("table"),
-                                   pol.get("ps_table"), unique_user_id, 0, mm, prev_last_view=lpv(training),
+        first, count = shard_range(num_step_users, rank, world, unique_user_id)
+        log = generate_logs_device(de, count, "eps_table" if eps > 0.0 else pol["policy"], pol.get("table"),
+                                   pol.get("ps_table"), first, 0, mm, prev_last_view=lpv(training) if world == 1 else -1,
                                    train_mode=L.TRAIN_EVOLUTION_STEP, epsilon=eps)
-        tot = log.totals.cpu().numpy()
-        successes, failures = int(tot[4]), int(tot[3] - tot[4])        # real bandit events only: the loop stops at done
         n = log.rows
         real = (log.z[:n] == 1) & ((log.flags[:n] & 1) == 0)
         is_greedy = real & (log.a[:n] == pol["table"][log.lv[:n].clamp(min=0).long()]) if wrapped else None
         clicked = log.a[:n][log.c[:n] == 1].long()
-        hist = torch.bincount(clicked, minlength=P).cpu().numpy()
+        # counters of the step: [bandit events, clicks, greedy clicks, greedy non-clicks | clicks per action]
+        counters = torch.zeros(4 + P, dtype=torch.int64, device=de.torch_device)
+        counters[0:2] = torch.stack([log.totals[3], log.totals[4]])
+        if wrapped:
+            counters[2] = (is_greedy & (log.c[:n] == 1)).sum()
+            counters[3] = (is_greedy & (log.c[:n] != 1)).sum()
+        counters[4:] = torch.bincount(clicked, minlength=P)
+        n_bandit_local = int(log.totals[3].item())
+        if world > 1:
+            allreduce_counters(counters, group=group)
+        counters = counters.cpu().numpy()
+        successes, failures = int(counters[1]), int(counters[0] - counters[1])   # real bandit events only: the loop stops at done
+        hist = counters[4:]
         if explored_only and not wrapped:
             raise KeyError("greedy")     # the reference reads action['greedy'], which only EpsilonGreedy provides
-        if explored_only or window:
+        if world > 1:
+            # the running sample count before this rank's shard: the lower ranks' bandit events of this step
+            before = samples + sum(c[0] for c in allgather_ints([n_bandit_local], de.torch_device, group)[:rank])
+            view = MaskedTrainingLog(log, pol["table"], explored_only, window, before, -1) if explored_only or window else log
+            training.device_train_sharded(view, chain(view, n, lpv(training)), group)
+            samples += int(counters[0])
+        elif explored_only or window:
             view = MaskedTrainingLog(log, pol["table"], explored_only, window, samples, lpv(training))
             samples = view.n_samples
             training.device_train(view)
         else:
-            samples += int(tot[3])
+            samples += int(counters[0])
             training.device_train(log)
         unique_user_id += num_step_users
         acting = training
@@ -133,11 +181,7 @@ def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_
             per_action[a][-1] += int(hist[a])
             per_action[a].append(0)
         training = deepcopy(initial_agent if training_approach == TrainingApproach.LAST_STEP else acting)
-        if wrapped:
-            sg = int((is_greedy & (log.c[:n] == 1)).sum().item())
-            fg = int((is_greedy & (log.c[:n] != 1)).sum().item())
-        else:
-            sg = fg = 0
+        sg, fg = int(counters[2]), int(counters[3])
         rewards[EvolutionCase.SUCCESS].append(successes)
         rewards[EvolutionCase.SUCCESS_GREEDY].append(sg)
         rewards[EvolutionCase.FAILURE].append(failures)
@@ -147,11 +191,13 @@ def _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_
 
 
 def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000, num_steps=10,
-                   training_approach=TrainingApproach.ALL_DATA, sliding_window_samples=10000, device=None):
+                   training_approach=TrainingApproach.ALL_DATA, sliding_window_samples=10000, device=None, group=None):
     """Explore/exploit evolution (evaluate_agent.py:51-146): the acting policy is frozen inside a step and swapped at
     the step boundary.  device=None: count agents (bare or under a never-exploring EpsilonGreedy) with the ALL_DATA /
     LAST_STEP approaches run entirely on the GPU (`_evaluate_agent_device`); anything else goes user by user through
-    the gym facade with the Python agents, exactly as the reference does."""
+    the gym facade with the Python agents, exactly as the reference does.  With torch.distributed initialised (one
+    process per GPU) the device loop shards every phase's users over the ranks of `group` and reduces the training
+    statistics at the step boundaries; every rank returns the same dict."""
     inner = _device_evolution_agent(agent)
     if device is None:
         device = (inner is not None
@@ -162,7 +208,7 @@ def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000,
         if inner is None:
             raise ValueError("the device evolution loop needs a count agent (OrganicCount / BanditCount)")
         return _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps,
-                                      training_approach, sliding_window_samples=sliding_window_samples)
+                                      training_approach, sliding_window_samples=sliding_window_samples, group=group)
     initial_agent = deepcopy(agent)
     unique_user_id = 0
     for u in range(num_initial_train_users):

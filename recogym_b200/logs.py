@@ -243,6 +243,21 @@ class DenseCountStats:
                                                C.c_void_p(table.data_ptr()), C.c_void_p(ps.data_ptr()), self._stream()))
         return {"policy": "table", "table": table, "ps_table": ps}
 
+    def zeros_like(self):
+        return DenseCountStats(self.P, self.device, self.co_counts is not None, self.pulls is not None)
+
+    def add_reduced(self, delta, group=None):
+        """self += sum over ranks of `delta` (the statistics each rank collected on ITS shard of a training log): the
+        count matrices are additive, so one all-reduce(sum) per matrix at the step boundary keeps every rank's copy equal to
+        the single-GPU statistics (SURVEY 8e "not shardable ... deferred to (f)" / f1)."""
+        import torch.distributed as dist
+        for name in ("co_counts", "pulls", "clicks"):
+            mine, d = getattr(self, name), getattr(delta, name)
+            if mine is None:
+                continue
+            dist.all_reduce(d, op=dist.ReduceOp.SUM, group=group)
+            mine.add_(d)
+
     def organic_count_policy(self):
         """OrganicCount.act as a device table (agents/organic_count.py:54-72)."""
         return self._policy(0, self.co_counts, None)
@@ -356,6 +371,58 @@ class SparseCountStats:
 
     def bandit_count_policy(self):
         return self._policy(1, self.bandit)
+
+    def zeros_like(self):
+        return SparseCountStats(self.P, self.device, *self._want)
+
+    def add_reduced(self, delta, group=None):
+        """self += sum over ranks of `delta`: every rank all-gathers the occupied cells of all the deltas (padded to the
+        largest) into an un-hashed staging table and adds them through the device insertion path (duplicates of a key
+        accumulate); the whole-row increments are all-reduced.  Every rank ends with the same cells."""
+        torch = _torch()
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        dev = torch.device("cuda", self.device)
+        for name, is_bandit in (("co", False), ("bandit", True)):
+            if not self._want[1 if is_bandit else 0]:
+                continue
+            t = getattr(delta, name)
+            if t is None:
+                t = _DeviceHash(self.P, 1024, self.device, is_bandit)
+            used = t.keys != -1
+            n_mine = int(used.sum().item())
+            sizes = torch.tensor([n_mine], dtype=torch.int64, device=dev)
+            all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+            dist.all_gather(all_sizes, sizes, group=group)
+            n_max = max(int(s.item()) for s in all_sizes)
+            total = sum(int(s.item()) for s in all_sizes)
+            cols = [t.keys[used], t.a[used]] + ([t.b[used]] if is_bandit else [])
+            gathered = []
+            for ci, c in enumerate(cols):
+                pad = torch.full((n_max,), -1 if ci == 0 else 0, dtype=torch.int64, device=dev)
+                pad[:n_mine] = c
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad, group=group)
+                gathered.append(torch.cat(parts))
+            if is_bandit:
+                dist.all_reduce(t.row_a, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(t.row_b, op=dist.ReduceOp.SUM, group=group)
+            target = self._room(getattr(self, name), is_bandit, total)
+            if total:
+                m = world * n_max
+                stage = _DeviceHash(self.P, 1 << max(10, int(m - 1).bit_length()), self.device, is_bandit)
+                stage.keys[:m] = gathered[0]
+                stage.a[:m] = gathered[1]
+                if is_bandit:
+                    stage.b[:m] = gathered[2]
+                so, sn = stage.struct(), target.struct()
+                L.check(L.lib().rg_sparse_rehash_device(C.byref(so), C.byref(sn), self._stream()))
+                if int(target.stats[1].item()) != 0:
+                    raise RuntimeError("sparse count statistics: hash table overflow while merging the ranks' cells")
+            if is_bandit:
+                target.row_a.add_(t.row_a)
+                target.row_b.add_(t.row_b)
+            setattr(self, name, target)
 
     # ---- host <-> device (agents/_sparse.py HostSparseCounts) --------------------------------------------------------
     def load_host(self, co_host, bandit_host):

@@ -27,6 +27,42 @@ def allreduce_counters(*tensors, group=None):
     return tensors
 
 
+def dist_info(group=None):
+    """-> (rank, world_size); (0, 1) when torch.distributed is not initialised"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def resolve_carry(carries, rank, initial):
+    """BanditCount's `last_product_viewed` across the shards of ONE training log (statistics reduced at
+    step boundaries).  Every rank derives its columns with "no previous view" (-1) and reports the view its last train
+    call left behind (-1: none of its calls carried a session).  The reference trains the users in id order, so the
+    view rank r starts from is the last one reported by a LOWER rank, else `initial` (the agent's state before the
+    log); the state after the log is the last one reported by ANY rank.  -> (previous view of `rank`, final view)"""
+    prev = final = int(initial)
+    for r, c in enumerate(carries):
+        if int(c) >= 0:
+            if r < rank:
+                prev = int(c)
+            final = int(c)
+    return prev, final
+
+
+def allgather_ints(values, device, group=None):
+    """values: list of python ints of this rank -> [world][len(values)] python ints (one small all-gather)"""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info(group)
+    mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    if world == 1:
+        return [mine.tolist()]
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [t.tolist() for t in out]
+
+
 def ctr_quantiles(successes, failures):
     """Beta(s+1, f+1) median and 95% credible interval (bench_agents.py:247-251)."""
     return (beta.ppf(0.500, successes + 1, failures + 1), beta.ppf(0.025, successes + 1, failures + 1),

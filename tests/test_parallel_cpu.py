@@ -63,3 +63,69 @@ def test_two_rank_gloo_allreduce_equals_single_run():
     for rank, tot, vh, _ in res:
         assert tot == full["totals"].tolist() and vh == full["view_hist"].tolist()
     assert res[0][3] + res[1][3] == full["hash"].tolist()     # concatenated shards == unsharded run
+
+
+def _chain_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from recogym_b200.parallel import allgather_ints, resolve_carry, shard_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for case, (views, initial) in enumerate(_chain_cases()):
+        first, count = shard_range(len(views), rank, world)
+        mine = views[first:first + count]
+        # the shard alone, derived with "no previous view" (-1), as every rank derives its lvp column
+        lvp, cur = [], -1
+        for v in mine:
+            lvp.append(cur)
+            if v >= 0:
+                cur = v
+        n_before = sum(c[0] for c in allgather_ints([len(mine)], "cpu")[:rank])      # the sliding windows' sample offset
+        carries = [c[0] for c in allgather_ints([cur], "cpu")]
+        prev, final = resolve_carry(carries, rank, initial)
+        lvp = [prev if x == -1 else x for x in lvp]
+        out.append((case, first, n_before, lvp, final))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def _chain_cases():
+    """train calls of one log in user order: the view each call's session ends with, -1 = a call without a session (or a
+    call a selective TrainingApproach dropped); and the agent's last viewed product before the log"""
+    rs = np.random.RandomState(5)
+    cases = [([3, -1, -1, 4, -1, 2, -1, -1], -1), ([-1, -1, -1, -1, -1, 7], 9), ([-1] * 6, 4), ([-1] * 5, -1)]
+    for n in (2, 3, 17, 64):
+        v = rs.randint(0, 10, n)
+        v[rs.rand(n) < 0.6] = -1
+        cases.append((v.tolist(), int(rs.randint(-1, 10))))
+    return cases
+
+
+def test_last_view_chain_over_shards_equals_sequential_training():
+    """BanditCount.last_product_viewed before every train call when the calls are sharded over two ranks (the
+    multi-GPU evolution loop: evaluate_agent._evaluate_agent_device) == the sequential loop's; same for the state the
+    log leaves behind and for the running sample count."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chain_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for case, (views, initial) in enumerate(_chain_cases()):
+        want, cur = [], initial
+        for v in views:
+            want.append(cur)
+            if v >= 0:
+                cur = v
+        got = []
+        for r in range(2):
+            c, first, n_before, lvp, final = res[r][case]
+            assert c == case and first == n_before == len(got) and final == cur
+            got += lvp
+        assert got == want, (case, got, want)
