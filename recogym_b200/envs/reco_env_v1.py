@@ -369,74 +369,24 @@ class RecoEnv1:
         return pd.DataFrame().from_dict(data)
 
     def _generate_logs_fused(self, num_offline_users, pol, num_organic_offline_users, user_begin=0):
+        """ONE fused rollout with the event-log output, ordered and turned into the DataFrame's columns on the device
+        (rg_generate_logs_device: scan + scatter, t / u / z / v / a / c / ps incl. the NormalTimeGenerator clock), one
+        device -> host copy per column, DataFrame built without per-row Python objects (logs.DeviceLog.to_dataframe)."""
         import pandas as pd
-        from .device_env import rollout_log
-        r = rollout_log(self.device_env, num_offline_users, pol["policy"], pol.get("table"), int(user_begin),
-                        num_organic_offline_users, epsilon=pol.get("epsilon", 0.0))
-        tcol = r["t"].astype(np.float32)
-        nt = self._normal_time()
-        if nt is not None:      # NormalTimeGenerator: the row's clock = sequential sum of its user's steps (host spec calls)
-            tcol = np.empty(len(r["t"]), np.float32)
-            f = L.lib().rg_spec_time_step
-            start = 0
-            while start < len(tcol):
-                key = int(r["u"][start])
-                end = start
-                while end < len(tcol) and r["u"][end] == key:
-                    end += 1
-                cum = [0.0]
-                for i in range(int(r["t"][start:end].max())):
-                    cum.append(cum[-1] + f(self._epoch_seed, key, i, nt[0], nt[1]))
-                tcol[start:end] = np.asarray(cum, np.float64)[r["t"][start:end]].astype(np.float32)
-                start = end
-        r["u"] = r["u"] - int(user_begin)          # labels are 0-based per call, as in the reference
-        organic = r["z"] == 0
-        P = self.config.num_products
-        if pol["policy"] == "uniform":
-            ps = np.where(organic, np.nan, 1.0 / P)
-        elif pol["policy"] == "user_views":
+        from ..logs import generate_logs_device
+        log = generate_logs_device(self.device_env, num_offline_users, pol["policy"], pol.get("table"), pol.get("ps_table"),
+                                   int(user_begin), num_organic_offline_users, epsilon=pol.get("epsilon", 0.0))
+        df = log.to_dataframe(zero_based_users=True)      # labels are 0-based per call, as in the reference
+        if pol["policy"] == "user_views":
             # ps = (1 - epsilon) * action_proba[a] = views of product a by this user so far / all its views so far
-            # (agents/organic_user_count.py:66-72 with epsilon = 0)
+            # (agents/organic_user_count.py:66-72 with epsilon = 0): per-user running counts, on the host
+            organic = (df["z"] == "organic").to_numpy()
+            u = df["u"].to_numpy(dtype=np.int64)
+            x = np.where(organic, df["v"].to_numpy(dtype=np.int64, na_value=0), df["a"].to_numpy(dtype=np.int64, na_value=0))
             org = organic.astype(np.int64)
-            x = np.where(organic, r["v"], r["a"]).astype(np.int64)
-            seen = pd.Series(org).groupby(r["u"].astype(np.int64) * P + x).cumsum().to_numpy()
-            total = pd.Series(org).groupby(r["u"]).cumsum().to_numpy()
-            ps = np.where(organic, np.nan, seen / np.maximum(total, 1))
-        else:
-            ps_table = pol.get("ps_table")
-            ps = np.where(organic, np.nan, 1.0)
-            eps = float(pol.get("epsilon", 0.0)) if pol["policy"] == "eps_table" else 0.0
-            if ps_table is not None or eps > 0.0:   # e.g. BanditCount reports its click-rate estimate as 'ps'
-                # the acting last view of a bandit row is the most recent organic view of the same user
-                lv = pd.Series(np.where(organic, r["v"], np.nan)).groupby(r["u"]).ffill().to_numpy()
-                bidx = np.flatnonzero(~organic)
-                lvb = lv[bidx].astype(np.int64)
-                if ps_table is not None:
-                    if hasattr(ps_table, "is_cuda"):   # trained on the device
-                        ps_table = ps_table.detach().cpu().numpy()
-                    ps[bidx] = np.asarray(ps_table)[lvb]
-                if eps > 0.0:   # epsilon_greedy.py:44-68: an action is greedy iff it is the wrapped agent's
-                    table = pol["table"].detach().cpu().numpy() if hasattr(pol["table"], "is_cuda") else np.asarray(pol["table"])
-                    greedy = r["a"][bidx] == table[lvb]
-                    ps[bidx] = np.where(greedy, (1.0 - eps) * ps[bidx], eps * (1.0 / float(P - 1)))
-        nan = np.float32("nan")
-        df = pd.DataFrame({
-            "t": tcol,
-            "u": pd.array(r["u"], dtype=pd.Int32Dtype()),
-            "z": np.where(organic, "organic", "bandit"),
-            "v": pd.array(np.where(organic, r["v"], 0), dtype=pd.Int32Dtype()),
-            "a": pd.array(np.where(organic, 0, r["a"]), dtype=pd.Int32Dtype()),
-            "c": np.where(organic, nan, r["c"].astype(np.float32)),
-            "ps": ps,
-        })
-        df.loc[~organic, "v"] = pd.NA
-        df.loc[organic, "a"] = pd.NA
-        psa = np.empty(len(df), dtype=object)
-        psa[:] = None
-        empty = np.empty(1, dtype=object)
-        empty[0] = ()          # the reference logs `()` for bandit rows without with_ps_all (abstract.py:290)
-        psa[~organic] = empty
-        df["ps-a"] = psa
+            seen = pd.Series(org).groupby(u * int(self.config.num_products) + x).cumsum().to_numpy()
+            total = pd.Series(org).groupby(u).cumsum().to_numpy()
+            df["ps"] = np.where(organic, np.nan, seen / np.maximum(total, 1))
         return df
 
     # --------------------------------------------------------------------- throughput entry point

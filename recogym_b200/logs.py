@@ -56,25 +56,32 @@ class DeviceLog:
         out["c"] = np.where(np.isnan(c), -1, c).astype(np.int8)
         return out
 
-    def to_dataframe(self):
-        """The generate_logs DataFrame: t f32, u/v/a Int32 (nullable), z str, c f32, ps, ps-a."""
+    def to_dataframe(self, zero_based_users=False):
+        """The generate_logs DataFrame: t f32, u/v/a Int32 (nullable), z str, c f32, ps, ps-a; `u` = the global user id, or
+        (zero_based_users, what the reference's per-call labels are) the id minus the call's user_begin.  Built from whole columns:
+        the nullable integer columns straight from (values, mask), the `z` strings by decoding a two-entry Arrow
+        dictionary (a numpy unicode array costs pandas 0.5 us per row to convert: 5.6 of the 6.5 s of a 10M-row frame)."""
         import pandas as pd
         n = self.rows
         z = self.z[:n].cpu().numpy()
         organic = z == 0
-        v = self.v[:n].cpu().numpy()
-        a = self.a[:n].cpu().numpy()
+        bandit = ~organic
+        try:
+            import pyarrow as pa
+            zcol = pd.array(pa.DictionaryArray.from_arrays(pa.array(z), pa.array(["organic", "bandit"])).dictionary_decode(),
+                            dtype="str")
+        except Exception:       # no pyarrow (or an object-string pandas): the plain numpy route
+            zcol = np.where(organic, "organic", "bandit")
+        none = np.zeros(n, dtype=bool)
         df = pd.DataFrame({
             "t": self.t[:n].cpu().numpy(),
-            "u": pd.array(self.u[:n].cpu().numpy(), dtype=pd.Int32Dtype()),
-            "z": np.where(organic, "organic", "bandit"),
-            "v": pd.array(v, dtype=pd.Int32Dtype()),
-            "a": pd.array(a, dtype=pd.Int32Dtype()),
+            "u": pd.arrays.IntegerArray(self.u[:n].cpu().numpy() - np.int32(self.user_begin if zero_based_users else 0), none),
+            "z": zcol,
+            "v": pd.arrays.IntegerArray(self.v[:n].cpu().numpy(), bandit),
+            "a": pd.arrays.IntegerArray(self.a[:n].cpu().numpy(), organic),
             "c": self.c[:n].cpu().numpy(),
             "ps": self.ps[:n].cpu().numpy(),
         })
-        df.loc[~organic, "v"] = pd.NA
-        df.loc[organic, "a"] = pd.NA
         psa = np.empty(n, dtype=object)
         psa[:] = None
         empty = np.empty(1, dtype=object)

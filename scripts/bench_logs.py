@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--P", type=int, default=100)
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--df-users", type=int, default=100_000, help="users of the generate_logs -> pandas DataFrame end-to-end line")
     a = ap.parse_args()
     import torch
     import recogym_b200 as rg
@@ -72,6 +73,20 @@ def main():
     table = st.organic_count_policy()["table"]
     ms_ips = timed(lambda: ips_table_policy(log, table))
     line("ips_table_policy", ms_ips, rows * 25)
+    # end to end through the reference-facing call: env.generate_logs(n) -> pandas DataFrame (fused rollout + ordered
+    # device log + device->host copy of the columns + DataFrame construction), wall clock
+    import time
+    env = rg.make("reco-gym-v1")
+    env.init_gym({**rg.env_1_args, "num_products": a.P, "K": a.K, "random_seed": 42})
+    env.generate_logs(1000)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    df = env.generate_logs(a.df_users)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"stage": "env.generate_logs -> pandas DataFrame (end to end, wall clock)", "users": a.df_users,
+                      "rows": int(len(df)), "seconds": dt, "rows_per_s": len(df) / dt,
+                      "user_steps_per_s": (len(df) - a.df_users) / dt,
+                      "d2h_bytes": int(df.memory_usage(index=False, deep=False).sum())}))
 
 
 if __name__ == "__main__":

@@ -21,6 +21,9 @@ echo "== bench c5 / c2 / c4 (1 GPU)"
 timeout -k 10 900 python bench.py --workload c5 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | tee gpurun_out/bench_c5_$TAG.json | cut -c1-200
 timeout -k 10 900 python bench.py --workload c2 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | tee gpurun_out/bench_c2_$TAG.json | cut -c1-200
 timeout -k 10 900 python bench.py --workload c4 --users 200000 --train-users 200 --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | tee gpurun_out/bench_c4_$TAG.json | cut -c1-200
+echo "== log pipeline (C2 and C3 shapes) incl. generate_logs -> DataFrame end to end"
+timeout -k 10 600 python scripts/bench_logs.py --users 1000000 --P 100 --K 5 2>/dev/null > gpurun_out/bench_logs_c2_$TAG.jsonl; tail -1 gpurun_out/bench_logs_c2_$TAG.jsonl | cut -c1-300
+timeout -k 10 600 python scripts/bench_logs.py --users 200000 --P 10000 --K 20 --df-users 50000 2>/dev/null > gpurun_out/bench_logs_c3_$TAG.jsonl; tail -1 gpurun_out/bench_logs_c3_$TAG.jsonl | cut -c1-300
 echo "== ncu launch list of the default bench command"
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1

@@ -349,3 +349,39 @@ def test_masked_training_log_selects_the_reference_train_calls(oracle):
         assert kept == view.keep_rows and samples == view.n_samples and kept > 3
         assert np.array_equal(co, wco) and np.array_equal(pulls, wp) and np.array_equal(clicks, wc), (explored_only, window)
         assert int(view.carry.item()) == lpv
+
+
+def test_device_log_dataframe_has_the_reference_schema():
+    """DeviceLog.to_dataframe (whole-column construction: masked Int32 arrays, Arrow-decoded `z`) == the frame the
+    reference's generate_logs builds row by row (abstract.py:256-327): dtypes, NA pattern, `()` in 'ps-a' of bandit rows."""
+    import pandas as pd
+    import torch
+    from recogym_b200.logs import DeviceLog
+    rs = np.random.RandomState(3)
+    n = 500
+    z = (rs.rand(n) < 0.7).astype(np.int8)
+    organic = z == 0
+    log = DeviceLog.__new__(DeviceLog)
+    log.rows, log.user_begin = n, 0
+    cols = {"t": rs.randint(0, 50, n + 7).astype(np.float32), "u": np.sort(rs.randint(0, 40, n + 7)).astype(np.int32),
+            "z": np.concatenate([z, np.zeros(7, np.int8)]), "v": rs.randint(0, 9, n + 7).astype(np.int32),
+            "a": rs.randint(0, 9, n + 7).astype(np.int32),
+            "c": np.concatenate([np.where(organic, np.nan, rs.rand(n) < 0.1), np.zeros(7)]).astype(np.float32),
+            "ps": np.concatenate([np.where(organic, np.nan, 1.0 / 9), np.zeros(7)])}
+    for k, v in cols.items():
+        setattr(log, k, torch.from_numpy(v.copy()))
+    df = log.to_dataframe()
+    # the reference's construction: python lists with None, then typed (abstract.py:318-326; ids widened to Int32)
+    want = pd.DataFrame({
+        "t": cols["t"][:n],
+        "u": pd.array(cols["u"][:n], dtype=pd.Int32Dtype()),
+        "z": ["organic" if o else "bandit" for o in organic],
+        "v": pd.array([int(x) if o else None for x, o in zip(cols["v"][:n], organic)], dtype=pd.Int32Dtype()),
+        "a": pd.array([None if o else int(x) for x, o in zip(cols["a"][:n], organic)], dtype=pd.Int32Dtype()),
+        "c": cols["c"][:n], "ps": cols["ps"][:n],
+        "ps-a": [None if o else () for o in organic]})
+    assert list(df.columns) == ["t", "u", "z", "v", "a", "c", "ps", "ps-a"] and len(df) == n
+    assert (df.dtypes == want.dtypes).all(), (df.dtypes, want.dtypes)
+    pd.testing.assert_frame_equal(df, want)
+    assert df["v"].isna().sum() == (~organic).sum() and df["a"].isna().sum() == organic.sum()
+    assert (df["z"] == "organic").sum() == organic.sum() and df.loc[~organic, "ps-a"].map(lambda x: x == ()).all()
