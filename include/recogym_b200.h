@@ -57,8 +57,11 @@ extern "C" {
 #define RG_MATH_EXACT 0 /* every view sampled in binary64 (reference arithmetic) */
 #define RG_MATH_FAST 1  /* fp32 CUDA-core contraction with a rigorous ambiguity filter; ambiguous
                            events are re-sampled in binary64, so discrete results equal RG_MATH_EXACT */
-#define RG_MATH_TENSOR 2 /* as RG_MATH_FAST with the contraction on the tensor cores (tcgen05, tf32 hi/lo split,
-                            accumulators in TMEM); the filter bound for the tensor-core sums is empirical */
+#define RG_MATH_TENSOR 2 /* as RG_MATH_FAST with the contraction on the tensor cores (tcgen05, fp16 hi/lo operand split,
+                            fp32 accumulators in TMEM); the filter bound for the tensor-core sums is empirical
+                            (DESIGN.md).  Operands outside the fp16 range: Gamma / mu_organic -> the CUDA-core
+                            contraction runs instead (same results); omega or the shift of a user at run time ->
+                            counted in totals[9], which must be 0 */
 
 /* Static parameters of one environment == what RecoEnv1.set_static_params() builds
  * (recogym/envs/reco_env_v1.py:51-75) plus the config scalars update_state()/reset() read. */
@@ -118,8 +121,9 @@ typedef struct rg_rollout_out {
     int64_t *totals;     /* [16] accumulated: [0] users, [1] events, [2] organic, [3] bandit, [4] clicks,
                             [5] phantom rows, [6] draws the fp32 filter sent to tier 2, [7] draws whose uniform lay within
                             binary64 rounding distance of a CDF boundary and were therefore re-drawn in the oracle's own operation
-                            order (tier 4; ~1e-7 of the views; correct by construction, reported for information), [8] draws tier 2 sent to tier 3, [9] RG_POLICY_USER_VIEWS:
-                            users whose distinct views overflowed the device list (must be 0); [10..15] diagnostic, CTA-batched
+                            order (tier 4; ~1e-7 of the views; correct by construction, reported for information), [8] draws tier 2 sent to tier 3, [9] users whose
+                            results are invalid (must be 0): RG_POLICY_USER_VIEWS users whose distinct views overflowed the
+                            device list, RG_MATH_TENSOR users whose omega left the fp16 operand range (|x| >= 65000); [10..15] diagnostic, CTA-batched
                             kernels: SM cycles per phase (compact, pass 1, pass 2, re-sampling, advance, omega) */
     /* Event log == the rows of the generate_logs DataFrame (abstract.py:256-327), unordered: one int32x4
      * record {u = user_id - user_begin, t, x = product viewed | action, flags} per row, flags bit 0: z
@@ -271,7 +275,8 @@ double rg_spec_time_step(uint64_t seed, uint64_t user, uint32_t call, double mu,
 int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *out_device, void *stream);
 
 /* Test hook of the tensor-core contraction: shifted log2-logits of 128 users against every product,
- * out[128][ceil(P/128)*128] = log2(e)*(Gamma omega + mu_organic) - shift (tcgen05, tf32 hi/lo split).
+ * out[128][ceil(P/128)*128] = log2(e)*(Gamma omega + mu_organic) - shift (tcgen05, fp16 hi/lo split); the padding
+ * products beyond P come out below -5e4.
  * omega: device [128][K] double, shift: device [128] float (log2 units). */
 int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *shift_device, float *out_device,
                         void *stream);

@@ -627,6 +627,7 @@ int rg_spec_eval_device(int kind, int64_t n, const double *in_device, double *ou
 int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *shift_device, float *out_device,
                         void *stream) {
     if (!env || !omega_device || !shift_device || !out_device) return fail(RG_EINVAL, "null argument");
+    if (!env->impl.tc_operands_ok) return fail(RG_EINVAL, "Gamma / mu_organic outside the range of the tensor-core operand elements");
     RG_CUDA(cudaSetDevice(env->impl.device));
     RG_CUDA(rg::launch_tc_logits(env->impl, omega_device, shift_device, out_device, (cudaStream_t)stream));
     return RG_OK;

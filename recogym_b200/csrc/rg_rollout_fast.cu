@@ -1884,6 +1884,9 @@ cudaError_t launch_rollout_fast(rg_env_impl &e, const PolicyDev &pol, long long 
                                 cudaStream_t stream, bool tensor) {
     using namespace fast;
     if (n_total <= 0) return cudaSuccess;
+    // parameters outside the range of the UMMA operand elements: same kernel with the CUDA-core contraction
+    // (identical discrete results)
+    if (tensor && !e.tc_operands_ok) return launch_rollout_fast(e, pol, user_begin, n_organic_users, n_total, out, stream, false);
     Params p;
     p.env = e.dev;
     p.pol = pol;

@@ -393,6 +393,36 @@ def test_tensor_core_logits_match_binary64():
         de.close()
 
 
+def test_parameters_outside_the_fp16_operand_range_take_the_cuda_core_contraction(oracle):
+    """The UMMA operand elements are fp16: a catalogue whose log2e-scaled Gamma / mu leave their range is still sampled
+    exactly in RG_MATH_TENSOR (the launch runs the CUDA-core contraction), and the tensor-core test hook refuses it."""
+    import ctypes as C
+    import torch
+    from oracle import oracle as O
+    from recogym_b200 import DeviceEnv, _lib as L
+    cfg, sp = synthetic_env(300, 8, 21)
+    sp["mu_organic"] = sp["mu_organic"].copy()
+    sp["mu_organic"][5] = 3.0e4          # * log2(e) = 4.3e4 > 32 500
+    sp["mu_organic"][9] = 3.0e4 - 1.0
+    sp["mu_bandit"] = sp["mu_organic"] if cfg.number_of_flips == 0 else sp["mu_bandit"]
+    oe = O.OracleEnv(sp["Gamma"], sp["mu_organic"], sp["beta"], sp["mu_bandit"], sp["state_transition"],
+                     cfg.sigma_omega_initial, cfg.sigma_omega, 21, cfg.change_omega_for_bandits)
+    de = DeviceEnv(sp, cfg.sigma_omega_initial, cfg.sigma_omega, 21, cfg.change_omega_for_bandits)
+    ro = oracle.rollout(oe, 0, 300)
+    for mode in ("exact", "tensor"):
+        r = de.rollout_device(300, "uniform", None, 0, 0, MODES[mode])
+        assert np.array_equal(r["hash"].cpu().numpy().view(np.uint64), ro["hash"]), mode
+        assert np.array_equal(r["last_view"].cpu().numpy(), ro["last_view"]) and int(r["totals"][9]) == 0
+    views = set(np.unique(ro["last_view"]).tolist())
+    assert views <= {5, 9} and len(views) == 2       # the two dominant products, one unit of logit apart
+    om = torch.zeros((128, 8), dtype=torch.float64, device="cuda")
+    sh = torch.zeros(128, dtype=torch.float32, device="cuda")
+    out = torch.zeros((128, 384), dtype=torch.float32, device="cuda")
+    rc = L.lib().rg_tc_logits_device(de._h, C.c_void_p(om.data_ptr()), C.c_void_p(sh.data_ptr()), C.c_void_p(out.data_ptr()), None)
+    assert rc != 0 and b"operand" in L.lib().rg_last_error()
+    de.close()
+
+
 @pytest.mark.parametrize("mode", ["exact", "fast", "tensor"])
 def test_event_log_equals_oracle_and_reference_rows(oracle, mode):
     """The event-log output of the fused rollout == the rows of generate_logs: against the T2 reference logs
