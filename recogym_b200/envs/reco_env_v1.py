@@ -370,24 +370,13 @@ class RecoEnv1:
 
     def _generate_logs_fused(self, num_offline_users, pol, num_organic_offline_users, user_begin=0):
         """ONE fused rollout with the event-log output, ordered and turned into the DataFrame's columns on the device
-        (rg_generate_logs_device: scan + scatter, t / u / z / v / a / c / ps incl. the NormalTimeGenerator clock), one
+        (rg_generate_logs_device: scan + scatter, t / u / z / v / a / c / ps incl. the NormalTimeGenerator clock; the 'ps' of
+        OrganicUserEventCounterAgent's actions by logs.user_views_ps), one
         device -> host copy per column, DataFrame built without per-row Python objects (logs.DeviceLog.to_dataframe)."""
-        import pandas as pd
         from ..logs import generate_logs_device
         log = generate_logs_device(self.device_env, num_offline_users, pol["policy"], pol.get("table"), pol.get("ps_table"),
                                    int(user_begin), num_organic_offline_users, epsilon=pol.get("epsilon", 0.0))
-        df = log.to_dataframe(zero_based_users=True)      # labels are 0-based per call, as in the reference
-        if pol["policy"] == "user_views":
-            # ps = (1 - epsilon) * action_proba[a] = views of product a by this user so far / all its views so far
-            # (agents/organic_user_count.py:66-72 with epsilon = 0): per-user running counts, on the host
-            organic = (df["z"] == "organic").to_numpy()
-            u = df["u"].to_numpy(dtype=np.int64)
-            x = np.where(organic, df["v"].to_numpy(dtype=np.int64, na_value=0), df["a"].to_numpy(dtype=np.int64, na_value=0))
-            org = organic.astype(np.int64)
-            seen = pd.Series(org).groupby(u * int(self.config.num_products) + x).cumsum().to_numpy()
-            total = pd.Series(org).groupby(u).cumsum().to_numpy()
-            df["ps"] = np.where(organic, np.nan, seen / np.maximum(total, 1))
-        return df
+        return log.to_dataframe(zero_based_users=True)      # labels are 0-based per call, as in the reference
 
     # --------------------------------------------------------------------- throughput entry point
     def generate_logs_counters(self, num_offline_users, policy="uniform", table=None, num_organic_offline_users=0,

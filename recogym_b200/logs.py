@@ -154,6 +154,37 @@ class MaskedTrainingLog:
         return s
 
 
+def user_views_ps(u, z, v, a, P):
+    """'ps' of OrganicUserEventCounterAgent's logged actions (agents/organic_user_count.py:66-72 with epsilon = 0):
+    ps = action_proba[a] = views of product a by this user so far / all its views so far, NaN on organic rows.  Running
+    counts per (user, product) over ordered log columns (torch tensors, any device): a stable sort by the pair key,
+    segmented cumulative sums (cumsum minus its value at the segment start, propagated by a running maximum), scattered
+    back.  The columns kernel leaves this policy's ps undefined (it would need the per-user view lists again)."""
+    torch = _torch()
+    n = int(u.numel())
+    organic = z == 0
+    org = organic.to(torch.int64)
+    x = torch.where(organic, v, a).to(torch.int64)
+    key = u.to(torch.int64) * int(P) + x
+
+    def segmented_cumsum(keys, vals):
+        c = torch.cumsum(vals, 0)
+        start = torch.ones(n, dtype=torch.bool, device=keys.device)
+        if n > 1:
+            start[1:] = keys[1:] != keys[:-1]
+        base = torch.cummax(torch.where(start, c - vals, torch.zeros_like(c)), 0).values   # c - vals never decreases
+        return c - base
+
+    if n == 0:
+        return torch.empty(0, dtype=torch.float64, device=u.device)
+    order = torch.argsort(key, stable=True)
+    seen = torch.empty(n, dtype=torch.int64, device=u.device)
+    seen[order] = segmented_cumsum(key[order], org[order])
+    total = segmented_cumsum(u.to(torch.int64), org)            # the log is ordered by user already
+    ps = seen.to(torch.float64) / total.clamp(min=1).to(torch.float64)
+    return torch.where(organic, torch.full_like(ps, float("nan")), ps)
+
+
 def generate_logs_device(env, n_users, policy="uniform", table=None, ps_table=None, user_begin=0, n_organic_users=0,
                          math_mode=L.MATH_TENSOR, prev_last_view=-1, rows_per_user=108.0, log=None,
                          train_mode=L.TRAIN_TEST_AGENT, epsilon=0.0):
@@ -188,6 +219,8 @@ def generate_logs_device(env, n_users, policy="uniform", table=None, ps_table=No
             C.c_void_p(log.totals.data_ptr()), int(math_mode), env._stream()))
         need = int(rows.item())
         if need <= log.capacity:
+            if policy == "user_views" and need:
+                log.ps[:need] = user_views_ps(log.u[:need], log.z[:need], log.v[:need], log.a[:need], env.P)
             log.rows = need
             log.n_users_total = n
             log.n_organic_users = int(n_organic_users)

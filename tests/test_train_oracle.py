@@ -385,3 +385,26 @@ def test_device_log_dataframe_has_the_reference_schema():
     pd.testing.assert_frame_equal(df, want)
     assert df["v"].isna().sum() == (~organic).sum() and df["a"].isna().sum() == organic.sum()
     assert (df["z"] == "organic").sum() == organic.sum() and df.loc[~organic, "ps-a"].map(lambda x: x == ()).all()
+
+
+def test_user_views_ps_equals_the_reference_agents_propensity():
+    """logs.user_views_ps (segmented running counts over the ordered log columns) == ps of
+    OrganicUserEventCounterAgent.act with the default arguments (agents/organic_user_count.py:49-72: action ~
+    Categorical(view counts), ps = counts[a] / sum(counts)), recomputed row by row."""
+    import torch
+    from recogym_b200.logs import user_views_ps
+    rs = np.random.RandomState(8)
+    P, rows = 7, []
+    for user in range(40):
+        seen = np.zeros(P)
+        for _ in range(rs.randint(1, 6)):
+            for _ in range(rs.randint(1, 5)):
+                v = rs.randint(P); seen[v] += 1
+                rows.append((user + 100, 0, v, -1, np.nan))
+            a = rs.choice(P, p=seen / seen.sum())
+            rows.append((user + 100, 1, -1, a, seen[a] / seen.sum()))
+    u, z, v, a, want = (np.array(c) for c in zip(*rows))
+    got = user_views_ps(torch.from_numpy(u.astype(np.int32)), torch.from_numpy(z.astype(np.int8)),
+                        torch.from_numpy(v.astype(np.int32)), torch.from_numpy(a.astype(np.int32)), P).numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(want))
+    assert user_views_ps(*(torch.zeros(0, dtype=torch.int32),) * 4, P).numel() == 0
