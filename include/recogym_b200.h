@@ -286,6 +286,64 @@ int rg_tc_logits_device(rg_env *env, const double *omega_device, const float *sh
  * the draws.  Process-wide; returns the previous value.  (oracle/rg_oracle.c user_product_view = reco_env_v1.py:119-128.) */
 int rg_debug_force_tier4(int on);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * reco-gym-v0, the toy environment (recogym/envs/reco_env_v0.py:17-69 on the AbstractEnv loops of abstract.py:90-197):
+ * no latent state -- the next organic view is uniform inside the current view's product cluster, a click is
+ * Bernoulli(click_probs[action, current view]); the clock never advances (every row of its logs has t = 0).
+ *
+ * RNG spec (same counter RNG as v1, keyed by the EVENT INDEX e = update_state() calls of the user so far):
+ *   slot 3, counter 0, words 0,1: the uniform of reset()'s first product view, choice(P, p=initial_product_probs) (:55);
+ *   slot 0 (event), counter e: words 0,1: update_product_view's choice(P, p=product_transition[view]) (:68-69) of an
+ *     organic event / draw_click's binomial(1, p) (:64-65) of a bandit event; words 2,3: update_state's choice(3, p) (:60);
+ *   slot 1 (policy), counter e: word 0 -> the uniform logging policy's action (abstract.py:214), as in v1.
+ * The host builds the tables with NumPy exactly as the reference does (so that they equal it bit for bit) and the
+ * device only searches them: cumulative distributions as numpy.random.RandomState.choice normalises them (cumsum,
+ * divide by the last entry, searchsorted side='right'), click thresholds as numpy's legacy binomial inversion computes
+ * them for n = 1 (click iff U > exp(log(1-p)) for p <= 0.5; the mirrored form for p > 0.5, stored negated). */
+typedef struct rg_env0 rg_env0;
+typedef struct rg_env0_desc {
+    int32_t num_products;       /* P */
+    int32_t num_clusters;       /* C: rows of view_cdf */
+    const double *init_cdf;     /* host [P]: CDF of initial_product_probs (reco_env_v0.py:46-47) */
+    const double *view_cdf;     /* host [C][P]: CDF of product_transition[v] for the products v of each cluster (:31-36) */
+    const int32_t *cluster_of;  /* host [P] */
+    const double *click_thr;    /* host [P][P], [action][view]: click iff U > thr (thr >= 0) / iff !(U > -thr) (thr < 0) */
+    double trans_cdf[9];        /* [state][3]: CDF of state_transition[state] (:22-29), as choice() normalises it */
+    uint64_t seed;
+    int32_t device;
+    int32_t reserved;
+} rg_env0_desc;
+
+#define RG0_POLICY_UNIFORM 0 /* abstract.py:214 */
+#define RG0_POLICY_TABLE 1   /* a = table[current view] */
+#define RG0_POLICY_REPLAY 2  /* ONE user (n_users = 1): the actions are given; the rollout stops at the first bandit event
+                                without one (state_out = 1: the env waits for step(action)).  Every gym step() of the
+                                facade is such a replay: a trajectory is a pure function of (seed, user, actions so far) */
+
+typedef struct rg_env0_out {     /* all nullable except totals; *_host entry points take host pointers, *_device device ones */
+    int64_t *totals;             /* [8] accumulated: users, events, organic, bandit, clicks, phantom rows, 0, 0 */
+    int32_t *n_events, *n_organic, *n_bandit, *n_clicks, *last_view, *state; /* per user [n]; state: 2 done, 1 waiting */
+    int32_t *log;                /* [log_capacity][4]: {user - user_begin, event index, product viewed | action,
+                                    flags: bit 0 bandit, bit 1 click, bit 2 phantom row after done (abstract.py:311-316)} */
+    int64_t log_capacity;
+    int64_t *log_count;          /* rows produced (rows beyond the capacity are dropped: call again) */
+} rg_env0_out;
+
+int rg_env0_create(const rg_env0_desc *desc, rg_env0 **out);
+void rg_env0_destroy(rg_env0 *env);
+int rg_env0_set_seed(rg_env0 *env, uint64_t seed);   /* reset_random_seed(epoch) (abstract.py:59-62) */
+/* generate_logs(n_users, agent, n_organic_users) of users user_begin.. (abstract.py:241-327) in one launch: organic-only
+ * users first (their first session only), then regular users with the phantom bandit row after done. */
+int rg_env0_rollout_device(rg_env0 *env, int policy_kind, const int32_t *table_or_actions_device, int64_t n_table,
+                           int64_t user_begin, int64_t n_organic_users, int64_t n_users, const rg_env0_out *out_device,
+                           void *stream);
+int rg_env0_rollout_host(rg_env0 *env, int policy_kind, const int32_t *table_or_actions_host, int64_t n_table,
+                         int64_t user_begin, int64_t n_organic_users, int64_t n_users, const rg_env0_out *out_host);
+/* Test hook (CPU tests only; nothing in the package calls it): the per-user body of the kernel instantiated for the host
+ * and run over the users in a loop, on the descriptor's host tables. */
+int rg_spec_env0_rollout(const rg_env0_desc *desc, int policy_kind, const int32_t *table_or_actions_host, int64_t n_table,
+                         int64_t user_begin, int64_t n_organic_users, int64_t n_users, const rg_env0_out *out_host);
+
 int rg_device_count(void);              /* 0 when no usable GPU: callers must fail, not fall back */
 int rg_version(void);
 const char *rg_last_error(void);

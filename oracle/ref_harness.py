@@ -247,3 +247,77 @@ def logs_to_arrays(df):
         return np.where(np.isnan(x), -1, x).astype(np.int64)
     return {"u": col("u").astype(np.int32), "t": df["t"].to_numpy().astype(np.int32), "z": z,
             "v": col("v").astype(np.int32), "a": col("a").astype(np.int32), "c": col("c").astype(np.int8)}
+
+
+# ------------------------------------------------------------------------------------------ reco-gym-v0
+class PhiloxUserRNGv0:
+    """Drop-in for `env.rng` of the reference's RecoEnv0 (reco_env_v0.py) after init_gym: the dynamics draw from the
+    build's RNG spec for v0 (include/recogym_b200.h "reco-gym-v0"), keyed by the user and its EVENT INDEX e = the number
+    of update_state() calls so far (the v0 clock never advances, so the time cannot serve as the key):
+      reset                reco_env_v0.py:54   choice(P, p=initial_product_probs)   -> slot 3, counter 0, uniform 0
+      update_product_view  reco_env_v0.py:68   choice(P, p=product_transition[v])   -> event uniform 0 at e
+      draw_click           reco_env_v0.py:65   binomial(1, p)                       -> event uniform 0 at e (numpy's legacy
+                                                                                       inversion for n = 1 on that uniform)
+      update_state         reco_env_v0.py:60   choice(3, p)                         -> event uniform 1 at e; then e += 1
+      step_offline         abstract.py:214     choice(P)                            -> policy stream at e
+    """
+
+    def __init__(self, env, seed):
+        self.env = env
+        self.seed = int(seed)
+        self.e = 0
+
+    @staticmethod
+    def _search(p, x):
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
+        return int(cdf.searchsorted(x, side="right"))
+
+    def choice(self, a, p=None):
+        from oracle import oracle as O
+        caller = sys._getframe(1).f_code.co_name
+        u = int(self.env.current_user_id)
+        if caller == "reset":
+            self.e = 0
+            w = O.philox(self.seed, u, 0, 3)
+            x = ((int(w[0]) >> 5) * 67108864.0 + (int(w[1]) >> 6)) / 9007199254740992.0
+            return self._search(p, x)
+        if caller == "step_offline":
+            assert p is None
+            return O.policy_uniform_action(self.seed, u, self.e, int(a))
+        if caller == "update_product_view":
+            return self._search(p, O.event_uniform(self.seed, u, self.e, 0))
+        assert caller == "update_state", caller
+        s = self._search(p, O.event_uniform(self.seed, u, self.e, 1))
+        self.e += 1
+        return s
+
+    def binomial(self, n, p):
+        from oracle import oracle as O
+        from oracle.v0_oracle import binomial1
+        assert n == 1 and sys._getframe(1).f_code.co_name == "draw_click"
+        return binomial1(float(p), O.event_uniform(self.seed, int(self.env.current_user_id), self.e, 0))
+
+
+def make_env0(args, tier):
+    """The reference's RecoEnv0 with `args` over env_0_args.  T1: literal (MT19937); T2: static parameters from the literal
+    init_gym, dynamics from PhiloxUserRNGv0."""
+    ref = load_reference()
+    from copy import deepcopy
+    import recogym.envs.reco_env_v0 as r0
+    env = r0.RecoEnv0()
+    full = {**deepcopy(r0.env_0_args), "num_clusters": 2, "phi_var": 0.1, **args}
+    env.init_gym(full)
+    if tier == "T2":
+        def reset_random_seed(epoch=0, _env=env):
+            _env.rng = PhiloxUserRNGv0(_env, _env.config.random_seed + epoch)
+        env.reset_random_seed = reset_random_seed
+        env.reset_random_seed()
+    return env
+
+
+def static_params_v0(env):
+    return {"state_transition": np.array(env.state_transition, np.float64),
+            "product_transition": np.array(env.product_transition, np.float64), "phi": np.array(env.phi, np.float64),
+            "click_probs": np.array(env.click_probs, np.float64),
+            "initial_product_probs": np.array(env.initial_product_probs, np.float64)}

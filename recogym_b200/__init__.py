@@ -2,10 +2,10 @@
 
 Exports the names a user of `recogym` imports for this path (reference: recogym/__init__.py:1-45):
 value types, env args, enums, `test_agent`, `verify_agents`, `evaluate_agent`, `build_agent_init`,
-and `make('reco-gym-v1')` in place of gym's registry (gym is not a dependency).
+and `make('reco-gym-v1')` / `make('reco-gym-v0')` in place of gym's registry (gym is not a dependency).
 """
-from .envs import (Configuration, Context, DefaultContext, Observation, Session, OrganicSessions, RecoEnv1,
-                   env_args, env_1_args, DeviceEnv, BatchState, rollout_log, DefaultTimeGenerator,
+from .envs import (Configuration, Context, DefaultContext, Observation, Session, OrganicSessions, RecoEnv1, RecoEnv0,
+                   env_args, env_1_args, env_0_args, DeviceEnv, DeviceEnv0, BatchState, rollout_log, DefaultTimeGenerator,
                    NormalTimeGenerator)
 from .constants import AgentStats, AgentInit, EvolutionCase, TrainingApproach, RoiMetrics
 from .bench_agents import test_agent
@@ -16,7 +16,7 @@ from .competition import competition_score
 from . import agents
 from ._lib import MATH_EXACT, MATH_FAST, MATH_TENSOR, RecoGymB200Error
 
-_REGISTRY = {"reco-gym-v1": RecoEnv1}
+_REGISTRY = {"reco-gym-v1": RecoEnv1, "reco-gym-v0": RecoEnv0}      # recogym/__init__.py:36-45
 
 
 def make(env_id):

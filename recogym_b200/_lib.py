@@ -52,6 +52,20 @@ class LogColumns(C.Structure):
         "t", "u", "z", "v", "a", "c", "ps", "lv", "lvp", "sess", "flags")]
 
 
+class Env0Desc(C.Structure):       # rg_env0_desc (reco-gym-v0)
+    _fields_ = [("num_products", C.c_int32), ("num_clusters", C.c_int32), ("init_cdf", C.c_void_p), ("view_cdf", C.c_void_p),
+                ("cluster_of", C.c_void_p), ("click_thr", C.c_void_p), ("trans_cdf", C.c_double * 9), ("seed", C.c_uint64),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Env0Out(C.Structure):        # rg_env0_out
+    _fields_ = [(n, C.c_void_p) for n in ("totals", "n_events", "n_organic", "n_bandit", "n_clicks", "last_view", "state",
+                                          "log")] + [("log_capacity", C.c_int64), ("log_count", C.c_void_p)]
+
+
+POLICY0_UNIFORM, POLICY0_TABLE, POLICY0_REPLAY = 0, 1, 2
+
+
 class SparseCounts(C.Structure):
     _fields_ = [("capacity", C.c_int64)] + [(n, C.c_void_p) for n in ("keys", "a", "b", "row_a", "row_b", "stats")]
 
@@ -68,6 +82,8 @@ EXPORTS = (
     "rg_spec_eval_device", "rg_tc_logits_device", "rg_device_count", "rg_version", "rg_last_error",
     "rg_debug_force_tier4", "rg_sparse_count_stats_device", "rg_sparse_count_policy_device",
     "rg_sparse_rehash_device",
+    "rg_env0_create", "rg_env0_destroy", "rg_env0_set_seed", "rg_env0_rollout_device", "rg_env0_rollout_host",
+    "rg_spec_env0_rollout",
 )
 
 
@@ -138,6 +154,18 @@ def lib():
     L.rg_debug_force_tier4.argtypes = [C.c_int]
     L.rg_tc_logits_device.restype = C.c_int
     L.rg_tc_logits_device.argtypes = [vp, vp, vp, vp, vp]
+    L.rg_env0_create.restype = C.c_int
+    L.rg_env0_create.argtypes = [C.POINTER(Env0Desc), C.POINTER(vp)]
+    L.rg_env0_destroy.restype = None
+    L.rg_env0_destroy.argtypes = [vp]
+    L.rg_env0_set_seed.restype = C.c_int
+    L.rg_env0_set_seed.argtypes = [vp, u64]
+    L.rg_env0_rollout_device.restype = C.c_int
+    L.rg_env0_rollout_device.argtypes = [vp, C.c_int, vp, i64, i64, i64, i64, C.POINTER(Env0Out), vp]
+    L.rg_env0_rollout_host.restype = C.c_int
+    L.rg_env0_rollout_host.argtypes = [vp, C.c_int, vp, i64, i64, i64, i64, C.POINTER(Env0Out)]
+    L.rg_spec_env0_rollout.restype = C.c_int
+    L.rg_spec_env0_rollout.argtypes = [C.POINTER(Env0Desc), C.c_int, vp, i64, i64, i64, i64, C.POINTER(Env0Out)]
     _lib = L
     return L
 

@@ -79,6 +79,10 @@ int check_rollout_args(const rg_env *env, const rg_policy *policy, int64_t n_org
 
 }  // namespace
 
+namespace rg {
+int set_error(int code, const char *msg) { return fail(code, "%s", msg); }   // for the other translation units (rg_env0.cu)
+}
+
 extern "C" {
 
 const char *rg_last_error(void) { return g_err; }

@@ -73,3 +73,7 @@ cudaError_t launch_recall(const rg_log_columns &c, long long rows, long long u_e
                           const int32_t *topk, int k, unsigned long long *out2, int num_sms, cudaStream_t stream);
 cudaError_t launch_spec_eval(int kind, long long n, const double *in, double *out, cudaStream_t stream);
 }  // namespace rg
+
+namespace rg {
+int set_error(int code, const char *msg);   // sets rg_last_error()'s text (rg_capi.cu), returns code
+}

@@ -119,9 +119,74 @@ def t2_case(name, args, n_users, n_organic=0, agent_kind=None, n_train=0, normal
     print(name, "rows", len(df), "clicks", int((A["c"] == 1).sum()))
 
 
+def v0_cases():
+    """reco-gym-v0 (recogym/envs/reco_env_v0.py): T1 static parameters + the literal generate_logs statistics, T2 logs
+    (uniform policy with organic-only users; the reference's own BanditCount trained with its own loop and then logged
+    as the acting agent; a step() trace under given actions)."""
+    ref = H.load_reference()
+    # T1: literal reference, seed 42, defaults
+    env = H.make_env0({"random_seed": 42}, "T1")
+    sp = H.static_params_v0(env)
+    df = env.generate_logs(200)
+    A = H.logs_to_arrays(df)
+    save("t1_v0_seed42_P10", seed=42, num_clusters=2, **sp, n_rows=len(df), n_organic=int((A["z"] == 0).sum()),
+         n_bandit=int((A["z"] == 1).sum()), n_clicks=int((A["c"] == 1).sum()),
+         view_hist=np.bincount(A["v"][A["z"] == 0], minlength=10), t_values=np.unique(df["t"].to_numpy()))
+    for name, args, n_users, n_org, agent_kind in (
+            ("t2_v0_seed42_P10_u120_o5", {"random_seed": 42}, 120, 5, None),
+            ("t2_v0_seed7_P30_c3_u150", {"random_seed": 7, "num_products": 30, "num_clusters": 3, "phi_var": 4.0,
+                                         "prob_leave_organic": 0.03}, 150, 0, None),
+            ("t2_v0_seed9_P12_c4_bandit_count", {"random_seed": 9, "num_products": 12, "num_clusters": 4, "phi_var": 40.0},
+             150, 2, "bandit_count")):
+        env = H.make_env0(args, "T2")
+        cfg = env.config
+        extra, agent = {}, None
+        if agent_kind:
+            from recogym.agents import BanditCount, bandit_count_args
+            agent = BanditCount(ref.Configuration({**bandit_count_args, "num_products": cfg.num_products}))
+            train_env = H.make_env0(args, "T2")
+            for uid in range(60):              # the reference's training loop (bench_agents.py:176-190), users 0..59
+                train_env.reset(uid)
+                new_obs, _, done, reward = train_env.step(None)
+                while not done:
+                    old_obs = new_obs
+                    action, new_obs, reward, done, _ = train_env.step_offline(old_obs, reward, done)
+                    agent.train(old_obs, action, reward, False)
+                old_obs = new_obs
+                action, _, reward, done, _ = train_env.step_offline(old_obs, reward, done)
+                agent.train(old_obs, action, reward, True)
+            extra["table"] = agent.ctr.argmax(axis=1).astype(np.int32)
+            extra["ps_table"] = agent.ctr[np.arange(cfg.num_products), extra["table"]]
+            extra["pulls"], extra["clicks"] = agent.pulls_a.copy(), agent.clicks_a.copy()
+        df = env.generate_logs(n_users, agent=agent, num_organic_offline_users=n_org)
+        A = H.logs_to_arrays(df)
+        extra["log_ps"] = df["ps"].to_numpy(dtype="float64", na_value=np.nan)
+        # a step() trace of one user under GIVEN actions: views of every observation, rewards, done flags
+        tenv = H.make_env0(args, "T2")
+        tenv.reset(77)
+        obs, reward, done, _ = tenv.step(None)
+        views, rewards, dones, acts = [[int(x["v"]) for x in obs.sessions()]], [], [bool(done)], []
+        rs = np.random.RandomState(5)
+        while not done and len(acts) < 400:
+            a = int(rs.randint(cfg.num_products))
+            obs, reward, done, _ = tenv.step(a)
+            acts.append(a); rewards.append(int(reward)); dones.append(bool(done))
+            views.append([int(x["v"]) for x in obs.sessions()])
+        save(name, seed=int(cfg.random_seed), n_users=n_users, n_organic_users=n_org, num_clusters=int(cfg.num_clusters),
+             policy="table" if agent is not None else "uniform", **H.static_params_v0(env),
+             **{"log_" + k: v for k, v in A.items()}, **extra,
+             trace_user=77, trace_actions=np.array(acts, np.int32), trace_rewards=np.array(rewards, np.int32),
+             trace_done=np.array(dones, np.int8), trace_views=np.concatenate([np.array(v, np.int32) for v in views] or [np.zeros(0, np.int32)]),
+             trace_view_counts=np.array([len(v) for v in views], np.int32))
+        print(name, "rows", len(df), "clicks", int((A["c"] == 1).sum()), "trace steps", len(acts))
+
+
 def main():
     if not H.reference_available():
         raise SystemExit("reference not available at " + H.REFERENCE_ROOT)
+    if "--v0-only" in sys.argv:
+        v0_cases()
+        return
     if "--user-views-only" in sys.argv:
         user_views_cases()
         return
