@@ -129,3 +129,51 @@ def test_last_view_chain_over_shards_equals_sequential_training():
             assert c == case and first == n_before == len(got) and final == cur
             got += lvp
         assert got == want, (case, got, want)
+
+
+def _dense_reduce_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    from recogym_b200.logs import DenseCountStats
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = 6
+
+    def stats(seed):
+        s = DenseCountStats.__new__(DenseCountStats)      # CPU tensors: the reduction logic does not care where they live
+        rs = np.random.RandomState(seed)
+        s.P, s.device, s.last_view = P, 0, -1
+        s.co_counts = None
+        s.pulls = torch.from_numpy(rs.randint(0, 9, (P, P)).astype(np.int64))
+        s.clicks = torch.from_numpy(rs.randint(0, 3, (P, P)).astype(np.int64))
+        return s
+
+    mine, delta = stats(100), stats(rank)                 # replicated statistics; this rank's shard of the step
+    mine.add_reduced(delta)
+    q.put((rank, mine.pulls.numpy().tolist(), mine.clicks.numpy().tolist()))
+    dist.destroy_process_group()
+
+
+def test_dense_statistics_reduce_to_the_sum_of_the_shards():
+    """DenseCountStats.add_reduced (the step-boundary all-reduce of the multi-GPU evolution loop): every rank ends with
+    the replicated statistics plus the SUM of all ranks' shard statistics."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dense_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (a, b)) for r, a, b in (q.get(timeout=120) for _ in procs))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    P = 6
+    def both(seed):
+        rs = np.random.RandomState(seed)
+        return rs.randint(0, 9, (P, P)).astype(np.int64), rs.randint(0, 3, (P, P)).astype(np.int64)
+    base, d0, d1 = both(100), both(0), both(1)
+    for r in range(2):
+        assert np.array_equal(np.array(res[r][0]), base[0] + d0[0] + d1[0])
+        assert np.array_equal(np.array(res[r][1]), base[1] + d0[1] + d1[1])
