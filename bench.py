@@ -458,7 +458,7 @@ def main():
                                  "ex2_per_organic_draw": P}
         line["roofline_tensor"] = {"bound": "tensor", "achieved": organic_per_s * 3 * 2.0 * P * (K + 2) / 1e12,
                                    "peak": None, "unit": "TFLOP/s (fp16 hi/lo operands, three-term split, fp32 accumulate)",
-                                   "note": "not the binding unit: ~30% tensor-pipe active (profiles/)"}
+                                   "note": "not the binding unit: 22% tensor-pipe active at the benched launch (profiles/r02_tensor_1M_ncu_summary.txt)"}
     else:
         line["roofline_fp32"] = {"bound": "fp32-fma", "achieved": per_gpu_steps_s * flops_per_step / 1e12,
                                  "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
