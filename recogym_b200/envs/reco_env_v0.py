@@ -228,6 +228,21 @@ class RecoEnv0:
             new.device_env = DeviceEnv0(self.device_env._keep, self._epoch_seed, self._device)
         return new
 
+    def __getstate__(self):
+        """picklable (the reference's drivers send envs to Pool workers: evaluate_agent.py:172-173): the device handle is
+        dropped and re-created from the host tables on load"""
+        st = dict(self.__dict__)
+        de = st.pop("device_env", None)
+        st["device_env"] = None
+        st["_tables"] = de._keep if de is not None else None
+        return st
+
+    def __setstate__(self, st):
+        tables = st.pop("_tables", None)
+        self.__dict__.update(st)
+        if tables is not None:
+            self.device_env = DeviceEnv0(tables, self._epoch_seed, self._device)
+
     # ---------------------------------------------------------------------------------- gym protocol, by replay
     def reset(self, user_id=0):
         """abstract.py:90-103 + reco_env_v0.py:50-56"""
