@@ -1,17 +1,17 @@
 // rg_tensor.cuh -- tcgen05 / TMEM primitives (inline PTX) and the operand layout of the tensor-core
 // contraction used by the organic-view sampler.
 //
-// Logits of 128 users x 64 products are one UMMA tile:  D[u][p] = sum_k A[u][k] * B[p][k]  with
-//   A = omega tile   (128 x KT tf32, K-major), rebuilt by the CTA every round,
-//   B = Gamma tile   ( 64 x KT tf32, K-major), precomputed on the host (GTC array),
-// both in the canonical no-swizzle K-major layout of the UMMA shared-memory descriptor:
-//   element (row r, column k) -> chunk kc = k/4 (16 bytes), row group g = r/8:
-//   byte offset = kc * (rows/8 * 128) + g * 128 + (r % 8) * 16 + (k % 4) * 4
-// so LBO (between the two 16-byte K chunks of one K=8 MMA step) = 2048 B for A, 1024 B for B, and SBO (between
-// 8-row groups) = 128 B.  (64-product tiles keep four accumulator tiles in 256 TMEM columns and make the
-// L2 -> shared-memory stream of B fine grained: 12 KB per stage at K = 20.)
-// fp32 accuracy comes from a two-term tf32 split of both operands, x = hi + lo (hi = top 19 bits):
-//   D = A_hi B_hi + A_hi B_lo + A_lo B_hi   (the dropped lo*lo term is ~2^-22 relative)
+// Logits of 128 users x TILE_N products are one UMMA tile:  D[u][p] = sum_k A[u][k] * B[p][k]  with
+//   A = omega tile   (128 x KT operand elements, K-major), rebuilt by the CTA every round,
+//   B = Gamma tile   (TILE_N x KT, K-major), precomputed on the host (GTC array),
+// both in the canonical no-swizzle K-major layout of the UMMA shared-memory descriptor, in 16-byte K CHUNKS of EPC
+// elements (8 fp16 / 4 tf32):
+//   element (row r, column k) -> chunk kc = k / EPC, row group g = r/8:
+//   byte offset = kc * (rows/8 * 128) + g * 128 + (r % 8) * 16 + (k % EPC) * sizeof(element)
+// so LBO (between the two 16-byte K chunks of one MMA step: K = 16 fp16 / 8 tf32) = 2048 B for A and TILE_N * 16 B for B,
+// and SBO (between 8-row groups) = 128 B.
+// fp32-grade accuracy comes from a two-term split of both operands, x = hi + lo (11 significant bits each):
+//   D = A_hi B_hi + A_hi B_lo + A_lo B_hi   (the dropped lo*lo term is ~2^-22 relative), accumulated in fp32 in TMEM.
 // Columns: k < K: log2e-scaled Gamma / omega;  k = K: mu' / 1;  k = K+1: 1 / -shift_u;  rest 0.
 #pragma once
 #include <cstdint>
@@ -60,7 +60,8 @@ __host__ __device__ inline int kt_chunks(int K) {  // number of 16-byte K chunks
 // K slabs.  The K dimension (K + 2 columns, padded) is cut into `nslab` slabs of `KCs` 16-byte chunks: one slab of a B
 // tile is the unit the TMA ring streams and one group of UMMAs consumes, all slabs of a tile accumulating into the same
 // TMEM columns.  Small K (<= 8 chunks, e.g. K = 20 -> 6) is a single slab; larger K uses 6-chunk slabs, so that the ring
-// stage stays 24 KB (K = 64 -> 3 slabs).  KC = nslab * KCs is the padded total the A tile is built with.
+// stage stays 24 KB (tf32: K = 64 -> 3 slabs; fp16: one slab up to 10 chunks, K <= 78).  KC = nslab * KCs is the padded
+// total the A tile is built with.
 __host__ __device__ inline void kt_slabs(int K, int *KC, int *KCs, int *nslab) {
     const int kc0 = kt_chunks(K);
     if (kc0 <= (RG_TC_F16 ? 10 : 8)) { *KCs = kc0; *nslab = 1; }   // fp16: K = 64 is one 40 KB slab
@@ -125,7 +126,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 tf32 step; issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem]^T, one MMA step (two K chunks); issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
