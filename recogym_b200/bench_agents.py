@@ -33,7 +33,7 @@ def _collect_stats(args):
     train_begin = uid
     log_pol = device_policy(train_env.agent, train_env.config.num_products) if train_env.agent else {"policy": "uniform"}
     if args.get("device_training", True) and hasattr(new_agent, "device_train") and log_pol is not None \
-            and not getattr(new_agent.config, "with_ps_all", False):
+            and not getattr(new_agent.config, "with_ps_all", False) and getattr(train_env, "supports_device_training", True):
         # count agents: the whole training phase is ONE fused rollout of the logging policy + scatter-add kernels over
         # its ordered device log (recogym_b200/logs.py) -- the same train calls as the loops below
         from . import _lib as L
@@ -72,6 +72,8 @@ def _collect_stats(args):
         eval_env = env
     eval_begin = train_begin if args["epoch_with_random_reset"] else uid
     pol = device_policy(new_agent, eval_env.config.num_products, allow_probe=args.get("allow_probe", False))
+    if pol is not None and pol["policy"] not in getattr(eval_env, "device_policies", (pol["policy"],)):
+        pol = None          # (reco-gym-v0 runs uniform and table policies on the device; anything else through its gym protocol)
     if pol is not None:
         r = eval_env.generate_logs_counters(args["num_online_users"], pol["policy"], pol.get("table"),
                                             user_begin=eval_begin, epsilon=pol.get("epsilon", 0.0))

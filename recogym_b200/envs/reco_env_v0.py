@@ -171,6 +171,8 @@ class RecoEnv0:
     """`gym.make('reco-gym-v0')` object of the reference (zero-arg constructor, then init_gym)."""
 
     metadata = {"render.modes": []}
+    device_policies = ("uniform", "table")      # what rg_env0_rollout_* runs; other agents go through the gym protocol
+    supports_device_training = False            # the count agents train through the gym protocol here (small catalogues)
 
     def __init__(self):
         self.first_step = True
@@ -347,6 +349,18 @@ class RecoEnv0:
             "a": pd.arrays.IntegerArray(r["x"].astype(np.int32), org),
             "c": np.where(org, np.float32("nan"), r["c"].astype(np.float32)),
             "ps": ps, "ps-a": psa})
+
+    def generate_logs_counters(self, num_offline_users, policy="uniform", table=None, num_organic_offline_users=0,
+                               user_begin=0, epsilon=0.0, **_):
+        """generate_logs() reduced to its counters, all users in one launch: successes / failures as test_agent and
+        verify_agents count them (bench_agents.py:203-206, evaluate_agent.py:742-745: phantom rows are failures)."""
+        if policy not in self.device_policies or epsilon:
+            raise NotImplementedError("reco-gym-v0 runs the uniform and table policies on the device; got %r" % (policy,))
+        if table is not None and hasattr(table, "is_cuda"):
+            table = table.detach().cpu().numpy()
+        tot = self.device_env.rollout(num_offline_users, policy, table, int(user_begin), num_organic_offline_users,
+                                      log=False, per_user=False)["totals"]
+        return {"successes": int(tot[4]), "failures": int(tot[3] + tot[5] - tot[4]), "totals": tot}
 
     def _generate_logs_stepwise(self, num_offline_users, agent, num_organic_offline_users, user_begin=0):
         import pandas as pd

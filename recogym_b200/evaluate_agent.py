@@ -34,6 +34,8 @@ def verify_agents(env, number_of_users, agents, allow_probe=False, user_begin=0)
     for agent_id, agent in agents.items():
         e = deepcopy(env)
         pol = device_policy(agent, e.config.num_products, allow_probe=allow_probe)
+        if pol is not None and pol["policy"] not in getattr(e, "device_policies", (pol["policy"],)):
+            pol = None      # (reco-gym-v0 runs uniform and table policies on the device; anything else through its gym protocol)
         if pol is not None:
             r = e.generate_logs_counters(number_of_users, pol["policy"], pol.get("table"), user_begin=user_begin,
                                          epsilon=pol.get("epsilon", 0.0))
