@@ -202,13 +202,15 @@ def evaluate_agent(env, agent, num_initial_train_users=100, num_step_users=1000,
     statistics at the step boundaries; every rank returns the same dict."""
     inner = _device_evolution_agent(agent)
     if device is None:
-        device = (inner is not None
+        device = (inner is not None and getattr(env, "supports_device_training", True)
                   and (inner is not agent or training_approach in (TrainingApproach.ALL_DATA, TrainingApproach.LAST_STEP,
                                                                    TrainingApproach.SLIDING_WINDOW_ALL_DATA))
                   and (not env.agent or device_policy(env.agent, env.config.num_products) is not None))
     if device:
         if inner is None:
             raise ValueError("the device evolution loop needs a count agent (OrganicCount / BanditCount)")
+        if not getattr(env, "supports_device_training", True):
+            raise ValueError("the device evolution loop runs on reco-gym-v1; %s goes through the gym protocol" % type(env).__name__)
         return _evaluate_agent_device(env, agent, inner, num_initial_train_users, num_step_users, num_steps,
                                       training_approach, sliding_window_samples=sliding_window_samples, group=group)
     initial_agent = deepcopy(agent)

@@ -181,11 +181,41 @@ def v0_cases():
         print(name, "rows", len(df), "clicks", int((A["c"] == 1).sum()), "trace steps", len(acts))
 
 
+def v0_evolution_case(name="t2_v0_evolution_seed4_P12_c3"):
+    """The reference's evaluate_agent (evaluate_agent.py:51-146) and verify_agents (:732-750) on RecoEnv0 with the v0 T2
+    streams, for its two count agents."""
+    ref = H.load_reference()
+    from recogym.agents import OrganicCount, organic_count_args, BanditCount, bandit_count_args
+    from recogym import evaluate_agent, verify_agents, TrainingApproach, EvolutionCase
+    args = {"random_seed": 4, "num_products": 12, "num_clusters": 3, "phi_var": 9.0}
+    n_init, n_step, n_steps = 25, 35, 3
+    out = {}
+    for tag, ctor, cargs, approach in (("bc_all", BanditCount, bandit_count_args, TrainingApproach.ALL_DATA),
+                                       ("oc_last", OrganicCount, organic_count_args, TrainingApproach.LAST_STEP)):
+        env = H.make_env0(args, "T2")
+        agent = ctor(ref.Configuration({**cargs, "num_products": 12}))
+        rw = evaluate_agent(env, agent, n_init, n_step, n_steps, approach)
+        out[tag + "_success"] = np.array(rw[EvolutionCase.SUCCESS], np.int64)
+        out[tag + "_failure"] = np.array(rw[EvolutionCase.FAILURE], np.int64)
+        out[tag + "_actions"] = np.array([rw[EvolutionCase.ACTIONS][a] for a in range(12)], np.int64)
+        print(name, tag, "success", rw[EvolutionCase.SUCCESS], "failure", rw[EvolutionCase.FAILURE])
+        # A/B of the agent evaluate_agent left trained (its warm-up statistics), 50 users from the env's seed
+        env = H.make_env0(args, "T2")
+        df = verify_agents(env, 50, {tag: agent})
+        out[tag + "_ab"] = df[["0.025", "0.500", "0.975"]].to_numpy(dtype=np.float64)[0]
+    env = H.make_env0(args, "T2")
+    save(name, seed=4, n_init=n_init, n_step=n_step, n_steps=n_steps, num_clusters=3, phi_var=9.0, **H.static_params_v0(env), **out)
+
+
 def main():
     if not H.reference_available():
         raise SystemExit("reference not available at " + H.REFERENCE_ROOT)
     if "--v0-only" in sys.argv:
         v0_cases()
+        v0_evolution_case()
+        return
+    if "--v0-evolution-only" in sys.argv:
+        v0_evolution_case()
         return
     if "--user-views-only" in sys.argv:
         user_views_cases()
@@ -227,6 +257,8 @@ def main():
     eps_greedy_case()
     evolution_eps_case()
     normal_time_case()
+    v0_cases()
+    v0_evolution_case()
 
 
 def train_case(name="t2_train_seed5_P60_K8_u40_o4", n_users=40, n_organic=4):
